@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the DynaBOA per-frame hot path: adapted frames/sec on the synthetic 3DPW-shape stream.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+
+One "step" = one adapted frame at BASELINE.json configs[1] (C2: 1 inner step, batch 1; S-adapt scope of
+SURVEY.md §8d: adaptation + one output forward/SMPL).  Prints ONE JSON line (see DESIGN.md "Measurement").
+``--impl reference`` times the CPU oracle port of the reference path on the host cores (the reference itself
+cannot travel to the GPU box and has no importable package; see oracle/__init__.py).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = 'adapted frames/sec (224x224, 1 inner step)'
+WORKLOADS = {
+    'c2': dict(inner_step=1, retrieval=0, lower_level_mixtrain=0, upper_level_mixtrain=0, dynamic_boa=0, sample_num=1),
+    'c3': dict(inner_step=3, retrieval=1, lower_level_mixtrain=1, upper_level_mixtrain=1, dynamic_boa=0, sample_num=8),
+}
+W_MB = 107.91            # fp32 parameters
+FWD_MB = lambda b: 107.91 + 89.51 * b
+BWD_MB = lambda b: 215.8 + 133.4 * b
+
+
+def default_options(**over):
+    """Flag defaults of reference dynaboa_benchmark.py:16-65."""
+    o = dict(seed=22, seq_seed=22, batch_size=1, lr=3e-6, beta1=0.5, beta2=0.9, use_boa=1, fastlr=8e-6, inner_step=1,
+             s2dloss_weight=10.0, shape_prior_weight=2e-6, pose_prior_weight=1e-4, use_frame_losses_lower=1,
+             use_frame_losses_upper=1, use_temporal_losses_lower=0, use_temporal_losses_upper=1, sample_num=1, retrieval=1,
+             dynamic_boa=1, cos_sim_threshold=3.1e-4, optim_steps=7, lower_level_mixtrain=1, upper_level_mixtrain=1,
+             labelloss_weight=0.1, use_meanteacher=1, alpha=0.1, teacherloss_weight=0.1, use_motion=1, interval=5,
+             motionloss_weight=0.8, teacher_dropout=1, dataset='3dpw', save_res=0, tensorboard=0)
+    o.update(over)
+    return SimpleNamespace(**o)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace('.', '').isdigit()]
+        smax = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------------ CPU oracle arm
+def build_oracle(workload, n_frames):
+    from dynaboa_b200 import constants as C, synthetic
+    from oracle import adaptor_ref
+    opts = adaptor_ref.default_options(**WORKLOADS[workload])
+    gmm = dict(np.load(os.path.join(REPO, 'dynaboa_b200', 'assets', 'gmm_08.npz')))
+    bank = synthetic.make_exemplar_bank() if opts.retrieval else None
+    clusters = synthetic.make_clusters() if opts.retrieval else None
+    ora = adaptor_ref.OracleAdaptor(opts, synthetic.make_basemodel(),
+                                    {g: synthetic.make_smpl_model(g) for g in ('neutral', 'male', 'female')},
+                                    synthetic.make_extra_regressors(), gmm, bank=bank, clusters=clusters,
+                                    joint_map=C.JOINT_MAP_49, vertex_ids=C.SMPL_EXTRA_VERTEX_IDS, h36m_to_j14=C.H36M_TO_J14)
+    return ora, synthetic.SyntheticStream(length=n_frames, batch_size=1)
+
+
+def time_oracle(workload, steps, warmup):
+    """Reference CPU path (oracle port), S-adapt scope, all host threads.  Returns frames/s (median-based)."""
+    torch.set_num_threads(os.cpu_count())
+    PRELUDE = 7
+    warmup = warmup + PRELUDE
+    ora, stream = build_oracle(workload, steps + warmup)
+    times = []
+    for t in range(steps + warmup):
+        ora.global_step, ora.fit_losses = t, {}
+        t0 = time.perf_counter()
+        ora.adaptation(stream[t], with_inference=False)
+        ora.predict(stream[t]['image'])
+        dt = time.perf_counter() - t0
+        if t >= warmup:
+            times.append(dt)
+    return 1.0 / float(np.median(times)), float(np.sum(times))
+
+
+def cpu_model():
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.startswith('model name'):
+                return line.split(':', 1)[1].strip()
+    except Exception:
+        pass
+    return 'unknown'
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    fps, total = time_oracle(args.workload, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    line = {'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1000.0 / fps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': f'{args.workload}: 3DPW-shape synthetic stream, S-adapt scope', 'batch': 1,
+                       'sample': f'{args.steps} frames on the host CPU'},
+            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'cpu': cpu_model(),
+                             'sample': f'{args.steps} timed frames after {args.warmup} warm-up ({total:.1f} s), oracle/adaptor_ref.py'},
+            'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, world, local):
+    from dynaboa_b200 import _lib, config, dist as ddist, hmr as hmr_mod, synthetic
+    from dynaboa_b200.adaptor import Adaptor
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    lib = _lib.load()
+    work = tempfile.mkdtemp(prefix=f'dboa_bench_r{rank}_')
+    synthetic.write_asset_dir(os.path.join(work, 'data'))
+    config.set_data_root(os.path.join(work, 'data'))
+    PRELUDE = 7          # untimed frames so that the history ring is full and the motion loss is live (step - interval > 0)
+    n_frames = PRELUDE + args.steps + args.warmup
+    opts = default_options(expdir=work, expname='bench', model_file=config.BASE_MODEL, synthetic_frames=n_frames, rank=rank,
+                           **WORKLOADS[args.workload])
+    ad = Adaptor(opts)
+    ad.fused_eval = 'none'
+    if world > 1:
+        ad.optimizer.pre_step_hook = ddist.make_grad_sync(world)
+    stream = synthetic.SyntheticStream(length=n_frames, batch_size=1, rank=rank)
+    keys = ('image', 'smpl_j2d')
+    host = [{k: stream[t][k].pin_memory() for k in keys} for t in range(n_frames)]
+    resident = [{k: host[t][k].to(dev) for k in keys} for t in range(n_frames)]
+    out_host = {k: torch.empty(s, pin_memory=True) for k, s in (('rotmat', (1, 24, 3, 3)), ('betas', (1, 10)), ('cam', (1, 3)),
+                                                                  ('joints', (1, 49, 3)), ('vertices', (1, 6890, 3)))}
+    h2d = sum(v.numel() * 4 for v in host[0].values())
+    d2h = sum(v.numel() * 4 for v in out_host.values())
+
+    def step(t, from_host):
+        ad.global_step, ad.fit_losses = t, {}
+        if from_host:
+            batch = {k: host[t][k].to(dev, non_blocking=True) for k in keys}
+        else:
+            batch = resident[t]
+        ad.adapt(batch)
+        pred = ad.predict(batch['image'])
+        if from_host:
+            for k, v in out_host.items():
+                v.copy_(pred[k], non_blocking=True)
+        return pred
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    def timed(from_host):
+        ad.reset_records()
+        for t in range(PRELUDE + args.warmup):
+            step(t, from_host)
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        l0 = lib.dboa_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(PRELUDE + args.warmup, n_frames):
+            step(t, from_host)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.dboa_launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        return ddist.max_over_ranks(ms, dev), launches, clocks
+
+    # reset model state between the two measurements so both see the same trajectory
+    snapshot = (ad.model.module.arena.clone(), ad.teacher.arena.clone())
+
+    def restore():
+        ad.model.module.arena.copy_(snapshot[0]); ad.teacher.arena.copy_(snapshot[1])
+        ad.optimizer.m.zero_(); ad.optimizer.v.zero_(); ad.optimizer.step_count = 0
+
+    ms_dev, launches, clocks = timed(False)
+    restore()
+    ms_e2e, _, clocks_e2e = timed(True)
+    value = world * args.steps / (ms_dev / 1000.0)
+    e2e = world * args.steps / (ms_e2e / 1000.0)
+
+    # ---- roofline of the dominant unit: the HMR forward launch sequence (b = 1), timed alone with CUDA events
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        model = ad.model.module
+        x = resident[0]['image']
+        tape = torch.empty(hmr_mod.tape_floats(1), dtype=torch.float32, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            hmr_mod.raw_forward(model.arena, model._buffers, x, None, tape)
+        torch.cuda.synchronize()
+        reps, tot = 20, 0.0
+        l0 = lib.dboa_launch_count()
+        for _ in range(reps):
+            flush.zero_()                                            # evict L2 (126 MB) between timed iterations
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            hmr_mod.raw_forward(model.arena, model._buffers, x, None, tape)
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        fwd_ms = tot / reps
+        fwd_launches = (lib.dboa_launch_count() - l0) // reps
+        achieved = FWD_MB(1) / 1e3 / (fwd_ms / 1e3)
+        roof = {'bound': 'hbm', 'kernel': f'dboa_hmr_forward b=1 ({fwd_launches} launches: 53 conv + 53 GroupNorm + head)',
+                'achieved': achieved, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': None, 'algorithmic_MB_per_launch': FWD_MB(1), 'ms_per_launch': fwd_ms,
+                'step_model': {'algorithmic_GB_per_frame': 3.63, 'achieved_GBps': 3.63 / (ms_dev / 1000.0 / args.steps),
+                               'frac': 3.63 / (ms_dev / 1000.0 / args.steps) / peak}}
+        if world == 1 and not args.no_cpu_baseline:
+            fps, total = time_oracle(args.workload, args.cpu_frames, 1)
+            cpu_base = {'value': fps, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port', 'cpu': cpu_model(),
+                        'sample': f'{args.cpu_frames} frames of the same stream after 1 warm-up ({total:.1f} s), oracle/adaptor_ref.py'}
+        line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic',
+                'config': {'workload': f'{args.workload}: 3DPW-shape synthetic stream, batch 1 per GPU, S-adapt scope '
+                                       '(adaptation + one output forward/SMPL)', 'flags': WORKLOADS[args.workload],
+                           'parallelism': f'dp{world}: frames sharded over ranks, 1 all-reduce of the 107.9 MB outer gradient per step'
+                           if world > 1 else 'single GPU',
+                           'l2': 'per-step working set (theta, fast weights, Adam m/v, teacher, gradient arena: 6 x 108 MB + '
+                                 'activations) exceeds the 126 MB L2; the isolated forward timing flushes L2 with a 256 MB memset'},
+                'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'ms_per_step': ms_e2e / args.steps},
+                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu_base}
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--cpu-frames', type=int, default=8)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+    from dynaboa_b200 import dist as ddist
+    if args.impl == 'reference':
+        rank = int(os.environ.get('RANK', '0'))
+        run_reference(args, rank, int(os.environ.get('WORLD_SIZE', '1')))
+        return
+    rank, world, local = ddist.init_from_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}')
+    run_ours(args, rank, world, local)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

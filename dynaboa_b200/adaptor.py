@@ -1,0 +1,151 @@
+"""Benchmark driver on top of ``BaseAdaptor`` (the role of reference dynaboa_benchmark.py ``Adaptor``
+:69-262: ``excute`` frame loop, ``adaptation`` bilevel + dynamic loop, ``inference`` metrics).
+
+Two entry points per frame:
+
+* ``adaptation(batch)``    -- the reference's control flow through torch autograd (``learner.adapt``,
+  ``loss.backward()``, ``optimizer.step()``), every op a libdynaboa_b200 kernel.  This is the path the
+  unchanged reference driver also exercises.
+* ``adapt(batch)``         -- the same arithmetic without autograd: direct C-ABI calls into one flat gradient
+  arena, Adam and the teacher EMA fused in one sweep, no host syncs except the ``dynamic_boa`` decision
+  (see fused.py).  This is what ``bench.py`` times.
+"""
+import os.path as osp
+
+import numpy as np
+import torch
+
+from . import constants
+from .base_adaptor import BaseAdaptor
+from .pose_utils import compute_similarity_transform_batch
+
+
+class Adaptor(BaseAdaptor):
+    def __init__(self, options):
+        super().__init__(options)
+        self.reset_records()
+
+    def reset_records(self):
+        n = len(self.dataloader)
+        self.feat_sims, self.optim_step_record = {}, []
+        self.mpjpe_statistics, self.pampjpe_statistics = [[] for _ in range(n)], [[] for _ in range(n)]
+        self.mpjpe_all_lower = [[] for _ in range(self.options.inner_step)]
+        self.pampjpe_all_lower = [[] for _ in range(self.options.inner_step)]
+        self.history, self.kp2dlosses_lower, self.kp2dlosses_upper = {}, [], {}
+
+    # ------------------------------------------------------------------ frame loop (reference :71-123)
+    def excute(self, max_frames=None, fused=False):
+        self.reset_records()
+        mpjpe_all, pampjpe_all, pve_all = [], [], []
+        for step, batch in enumerate(self.dataloader):
+            if max_frames is not None and step >= max_frames:
+                break
+            self.global_step, self.fit_losses = step, {}
+            batch = {k: v.to(self.device) if isinstance(v, torch.Tensor) else v for k, v in batch.items()}
+            self.model.eval()
+            mpjpe, pampjpe, pve = (self.adapt(batch) if fused else self.adaptation(batch))
+            self.fit_losses.update({'metrics/mpjpe': mpjpe, 'metrics/pampjpe': pampjpe, 'metrics/pve': pve})
+            self.write_summaries(self.fit_losses)
+            mpjpe_all.append(mpjpe); pampjpe_all.append(pampjpe); pve_all.append(pve)
+        summary = dict(mpjpe=float(np.mean(mpjpe_all)), pampjpe=float(np.mean(pampjpe_all)), pve=float(np.mean(pve_all)))
+        torch.save({'mpjpe': mpjpe_all, 'pampjpe': pampjpe_all, 'pve': pve_all}, osp.join(self.exppath, 'res.pt'))
+        torch.save({'step': self.optim_step_record}, osp.join(self.exppath, 'optim_step_record.pt'))
+        with open(osp.join(self.exppath, 'res.txt'), 'w') as f:
+            f.write(f"Step:{self.global_step}: MPJPE:{summary['mpjpe']}, PAMPJPE:{summary['pampjpe']}, PVE:{summary['pve']}\n")
+        return summary
+
+    def _outer_step(self, loss):
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.optimizer.step()
+        if self.options.use_meanteacher:
+            self.update_teacher(self.teacher, self.model)
+
+    # ------------------------------------------------------------------ bilevel step through autograd (reference :126-201)
+    def adaptation(self, batch):
+        o = self.options
+        image, kp = batch['image'], batch['smpl_j2d']
+        self.save_hist(image, kp)
+        if not o.use_boa:
+            loss, _ = self.lower_level_adaptation(image, kp, None, self.model)
+            self.optimizer.zero_grad(); loss.backward(); self.optimizer.step()
+            return self.inference(batch, self.model)
+
+        with torch.no_grad():
+            init_features = self.model(image, need_feature=True)[3]
+        learner = self.model.clone()
+        for i in range(o.inner_step):
+            lower_loss, _ = self.lower_level_adaptation(image, kp, None, learner)
+            learner.adapt(lower_loss)
+            mpjpe, pampjpe, _ = self.inference(batch, learner)
+            self.fit_losses[f'metrics/lower_{i}_mpjpe'], self.fit_losses[f'metrics/lower_{i}_pampjpe'] = mpjpe, pampjpe
+            self.mpjpe_all_lower[i].append(mpjpe); self.pampjpe_all_lower[i].append(pampjpe)
+        upper_loss, _ = self.upper_level_adaptation(image, kp, None, learner)
+        self.last_upper_loss = upper_loss.detach()
+        self._outer_step(upper_loss)
+        mpjpe, pampjpe, pve = self.inference(batch, self.model)
+        if self.global_step < len(self.mpjpe_statistics):
+            self.mpjpe_statistics[self.global_step], self.pampjpe_statistics[self.global_step] = [mpjpe], [pampjpe]
+
+        if o.dynamic_boa:
+            with torch.no_grad():
+                adapted = self.model(image, need_feature=True)[3]
+                sims = self.cal_feature_diff(init_features, adapted)
+            self.feat_sims[self.global_step] = [sims]
+            self.optimized_step = 0
+            while 1 - sims[12]['cos'] > o.cos_sim_threshold:
+                self.optimized_step += 1
+                if self.optimized_step > o.optim_steps:
+                    break
+                upper_loss, adapted = self.upper_level_adaptation(image, kp, None, self.model)
+                self._outer_step(upper_loss)
+                with torch.no_grad():
+                    init_features = adapted
+                    adapted = self.model(image, need_feature=True)[3]
+                    sims = self.cal_feature_diff(init_features, adapted)
+                self.feat_sims[self.global_step].append(sims)
+                mpjpe, pampjpe, pve = self.inference(batch, self.model)
+            self.optim_step_record.append(self.optimized_step)
+        return mpjpe, pampjpe, pve
+
+    # ------------------------------------------------------------------ evaluation (reference :204-262)
+    def predict(self, image, model=None):
+        """rotmat, betas, cam, joints49, vertices for ``image`` (no adaptation)."""
+        model = self.model if model is None else model
+        with torch.no_grad():
+            rot, shape, cam = model(image)
+            out = self.decode_smpl_params(rot, shape)
+        return dict(rotmat=rot, betas=shape, cam=cam, joints=out['s3d'], vertices=out['vts'])
+
+    def inference(self, batch, model, need_feature=False):
+        image, gt_pose, gt_betas, gender = batch['image'], batch['pose'], batch['betas'], batch['gender']
+        model.eval()
+        with torch.no_grad():
+            out = model(image, need_feature)
+            pred_rotmat, pred_shape, pred_cam = out[0], out[1], out[2]
+            pred_vertices = self.decode_smpl_params(pred_rotmat, pred_shape)['vts']
+            J = self.J_regressor.to(self.device)
+            gt_vertices = self.smpl_male(global_orient=gt_pose[:, :3], body_pose=gt_pose[:, 3:], betas=gt_betas).vertices
+            gt_vertices_f = self.smpl_female(global_orient=gt_pose[:, :3], body_pose=gt_pose[:, 3:], betas=gt_betas).vertices
+            gt_vertices = torch.where((gender == 1).view(-1, 1, 1), gt_vertices_f, gt_vertices)
+            gt_k = torch.matmul(J, gt_vertices)
+            gt_k = gt_k[:, self.joint_mapper_h36m] - gt_k[:, [0]]
+            pr_k = torch.matmul(J, pred_vertices)
+            pr_k = pr_k[:, self.joint_mapper_h36m] - pr_k[:, [0]]
+            mpjpe = torch.sqrt(((pr_k - gt_k) ** 2).sum(-1)).mean(-1).cpu().numpy()
+            S1, S2 = pr_k.cpu().numpy(), gt_k.cpu().numpy()
+            S1_hat = compute_similarity_transform_batch(S1, S2)
+            pampjpe = np.sqrt(((S1_hat - S2) ** 2).sum(-1)).mean(-1)
+            gt_neutral = self.smpl_neutral(betas=gt_betas, body_pose=gt_pose[:, 3:], global_orient=gt_pose[:, :3], pose2rot=True).vertices
+            pve = torch.sqrt(((gt_neutral - pred_vertices) ** 2).sum(2)).mean().item()
+        if getattr(self.options, 'cache_results', 0):
+            cam_t = torch.stack([pred_cam[:, 1], pred_cam[:, 2], 2 * 5000. / (constants.IMG_RES * pred_cam[:, 0] + 1e-9)], dim=-1)
+            torch.save({'verts': pred_vertices.cpu().numpy(), 'cam': cam_t.cpu().numpy(), 'rotmat': pred_rotmat.cpu().numpy(),
+                        'beta': pred_shape.cpu().numpy()}, osp.join(self.exppath, 'result', f'Pred_{self.global_step}.pt'))
+        if need_feature:
+            return mpjpe * 1000, pampjpe * 1000, pve * 1000, out[3]
+        return mpjpe * 1000, pampjpe * 1000, pve * 1000
+
+    def adapt(self, batch):
+        from .fused import fused_adapt
+        return fused_adapt(self, batch)

@@ -1,0 +1,213 @@
+// extern "C" surface of libdynaboa_b200 (see include/dynaboa_b200.h for the contract of each entry).
+#include "common.cuh"
+#include "kernels.h"
+#include "losses.h"
+#include "optim.h"
+#include "rotmath.cuh"
+#include "smpl.h"
+
+namespace dboa {
+int hmr_forward(const float* P, const float* init_pose, const float* init_shape, const float* init_cam, const float* image, int B,
+                const float* drop_masks, float* T, float* scratch, float* rotmat, float* shape, float* cam, float* pose6d,
+                cudaStream_t st);
+int hmr_backward(const float* P, const float* T, int B, int masked, const float* d_rotmat, const float* d_shape, const float* d_cam,
+                 float* G, float* scratch, cudaStream_t st);
+int hmr_num_params();
+long long hmr_arena_floats();
+int hmr_param_info(int i, char* name, int cap, long long* off, int* ndim, long long shape[4], long long stride[4]);
+long long hmr_tape_floats(int B);
+long long hmr_scratch_floats(int B);
+int hmr_feature_info(int B, int i, long long* off, int* ndim, long long shape[4], long long stride[4]);
+
+__global__ void r2aa_fwd_kernel(const float* __restrict__ R, float* __restrict__ aa, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float Ri[9], a[3];
+    for (int k = 0; k < 9; ++k) Ri[k] = R[(size_t)i * 9 + k];
+    r2aa_fwd(Ri, a);
+    for (int k = 0; k < 3; ++k) aa[(size_t)i * 3 + k] = a[k];
+}
+__global__ void r2aa_bwd_kernel(const float* __restrict__ R, const float* __restrict__ daa, float* __restrict__ dR, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float Ri[9], d[3], g[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < 9; ++k) Ri[k] = R[(size_t)i * 9 + k];
+    for (int k = 0; k < 3; ++k) d[k] = daa[(size_t)i * 3 + k];
+    r2aa_bwd(Ri, d, g);
+    for (int k = 0; k < 9; ++k) dR[(size_t)i * 9 + k] = g[k];
+}
+}  // namespace dboa
+
+using namespace dboa;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+static ConvDims make_dims(int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad, int Kpitch) {
+    ConvDims d;
+    d.B = B; d.Hi = Hi; d.Wi = Wi; d.Cin = Cin; d.Cout = Cout; d.kh = k; d.kw = k; d.stride = stride; d.pad = pad; d.Kpitch = Kpitch;
+    d.Ho = (Hi + 2 * pad - k) / stride + 1; d.Wo = (Wi + 2 * pad - k) / stride + 1;
+    return d;
+}
+
+extern "C" {
+
+const char* dboa_version(void) { return "dynaboa_b200 0.1 (sm_100a)"; }
+int dboa_last_cuda_error(void) { return g_last_cuda_error; }
+long long dboa_launch_count(void) { return g_launch_count; }
+int dboa_set_tensor_core_conv(int enable) { conv_tc_set_enabled(enable != 0); return DBOA_OK; }
+
+int dboa_hmr_num_params(void) { return hmr_num_params(); }
+long long dboa_hmr_arena_floats(void) { return hmr_arena_floats(); }
+int dboa_hmr_param_info(int i, char* name, int name_cap, long long* offset, int* ndim, long long shape[4], long long stride[4]) {
+    if (!offset || !ndim || !shape || !stride) return DBOA_ERR_ARG;
+    return hmr_param_info(i, name, name_cap, offset, ndim, shape, stride);
+}
+long long dboa_hmr_tape_floats(int B) { return hmr_tape_floats(B); }
+long long dboa_hmr_scratch_floats(int B) { return hmr_scratch_floats(B); }
+int dboa_hmr_feature_info(int B, int i, long long* offset, int* ndim, long long shape[4], long long stride[4]) {
+    if (!offset || !ndim || !shape || !stride) return DBOA_ERR_ARG;
+    return hmr_feature_info(B, i, offset, ndim, shape, stride);
+}
+int dboa_hmr_forward(const float* arena, const float* init_pose, const float* init_shape, const float* init_cam, const float* image,
+                     int B, const float* drop_masks, float* tape, float* scratch, float* rotmat, float* shape, float* cam, float* pose6d,
+                     dboa_stream_t stream) {
+    if (!arena || !init_pose || !init_shape || !init_cam || !image || !tape || !scratch || !rotmat || !shape || !cam) return DBOA_ERR_ARG;
+    return hmr_forward(arena, init_pose, init_shape, init_cam, image, B, drop_masks, tape, scratch, rotmat, shape, cam, pose6d, ST(stream));
+}
+int dboa_hmr_backward(const float* arena, const float* tape, int B, int masked, const float* d_rotmat, const float* d_shape,
+                      const float* d_cam, float* grad_arena, float* scratch, dboa_stream_t stream) {
+    if (!arena || !tape || !grad_arena || !scratch) return DBOA_ERR_ARG;
+    return hmr_backward(arena, tape, B, masked, d_rotmat, d_shape, d_cam, grad_arena, scratch, ST(stream));
+}
+
+int dboa_conv2d_fwd(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad, int Kpitch,
+                    float* ws, long long ws_floats, dboa_stream_t stream) {
+    if (!x || !w || !y) return DBOA_ERR_ARG;
+    return conv_fwd(x, w, y, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), ws, ws ? (size_t)ws_floats : 0, ST(stream));
+}
+int dboa_conv2d_dgrad(const float* dy, const float* w, float* dx, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
+                      int Kpitch, int accumulate, float* ws, long long ws_floats, dboa_stream_t stream) {
+    if (!dy || !w || !dx) return DBOA_ERR_ARG;
+    return conv_dgrad(dy, w, dx, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), accumulate, ws, ws ? (size_t)ws_floats : 0, ST(stream));
+}
+int dboa_conv2d_wgrad(const float* dy, const float* x, float* dw, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
+                      int Kpitch, float* ws, long long ws_floats, dboa_stream_t stream) {
+    if (!dy || !x || !dw) return DBOA_ERR_ARG;
+    return conv_wgrad(dy, x, dw, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), ws, ws ? (size_t)ws_floats : 0, ST(stream));
+}
+long long dboa_gn_partial_floats(int B, int HW, int C) { return (long long)gn_partial_floats(B, HW, C); }
+long long dboa_gn_bwd_partial_floats(int B, int HW, int C) { return (long long)gn_bwd_partial_floats(B, HW, C); }
+int dboa_groupnorm_fwd(const float* y, const float* gamma, const float* beta, const float* residual, float* out, float* stats, float* partial,
+                       int B, int HW, int C, int relu, dboa_stream_t stream) {
+    if (!y || !gamma || !beta || !out || !stats || !partial) return DBOA_ERR_ARG;
+    DBOA_TRY(gn_stats(y, B, HW, C, partial, ST(stream)));
+    return gn_apply(y, partial, gamma, beta, stats, residual, nullptr, nullptr, nullptr, nullptr, nullptr, out, B, HW, C, relu, ST(stream));
+}
+int dboa_groupnorm_bwd(const float* dout, const float* mask_src, const float* y, const float* stats, const float* gamma, float* dy,
+                       float* dgamma, float* dbeta, float* partial, int B, int HW, int C, dboa_stream_t stream) {
+    if (!dout || !y || !stats || !gamma || !dy || !dgamma || !dbeta || !partial) return DBOA_ERR_ARG;
+    return gn_bwd(dout, mask_src, y, stats, gamma, dy, dgamma, dbeta, partial, B, HW, C, ST(stream));
+}
+int dboa_maxpool_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, dboa_stream_t stream) {
+    if (!x || !y || !idx || (H & 1) || (W & 1) || (C & 3)) return DBOA_ERR_ARG;
+    return maxpool3x3s2_fwd(x, y, idx, B, H, W, C, ST(stream));
+}
+int dboa_maxpool_bwd(const float* dy, const unsigned char* idx, float* dx, int B, int H, int W, int C, dboa_stream_t stream) {
+    if (!dy || !idx || !dx || (H & 1) || (W & 1) || (C & 3)) return DBOA_ERR_ARG;
+    return maxpool3x3s2_bwd(dy, idx, dx, B, H, W, C, ST(stream));
+}
+
+int dboa_rot6d_fwd(const float* x6, float* R, int n, dboa_stream_t stream) {
+    if (!x6 || !R || n < 0) return DBOA_ERR_ARG;
+    return n ? rot6d_fwd_launch(x6, R, n, ST(stream)) : DBOA_OK;
+}
+int dboa_rot6d_bwd(const float* x6, const float* dR, float* dx6, int n, dboa_stream_t stream) {
+    if (!x6 || !dR || !dx6 || n < 0) return DBOA_ERR_ARG;
+    return n ? rot6d_bwd_launch(x6, dR, dx6, n, ST(stream)) : DBOA_OK;
+}
+int dboa_rodrigues(const float* aa, float* R, int n, int kind, dboa_stream_t stream) {
+    if (!aa || !R || n < 0 || kind < 0 || kind > 1) return DBOA_ERR_ARG;
+    return n ? rodrigues_launch(aa, R, n, kind, ST(stream)) : DBOA_OK;
+}
+int dboa_rotmat_to_aa_fwd(const float* R, float* aa, int n, dboa_stream_t stream) {
+    if (!R || !aa || n < 0) return DBOA_ERR_ARG;
+    if (!n) return DBOA_OK;
+    r2aa_fwd_kernel<<<ceil_div(n, 128), 128, 0, ST(stream)>>>(R, aa, n);
+    return check_launch();
+}
+int dboa_rotmat_to_aa_bwd(const float* R, const float* daa, float* dR, int n, dboa_stream_t stream) {
+    if (!R || !daa || !dR || n < 0) return DBOA_ERR_ARG;
+    if (!n) return DBOA_OK;
+    r2aa_bwd_kernel<<<ceil_div(n, 128), 128, 0, ST(stream)>>>(R, daa, dR, n);
+    return check_launch();
+}
+
+long long dboa_smpl_tape_floats(int B) { return (long long)SmplTape::floats(B); }
+long long dboa_smpl_scratch_floats(int B) { return (long long)SmplScratch::floats(B); }
+int dboa_smpl_forward(const dboa_smpl_model* m, const float* betas, const float* rotmat, int B, float* vertices, float* joints, float* tape,
+                      dboa_stream_t stream) {
+    if (!m || !betas || !rotmat || !vertices || !joints || !tape || B < 1) return DBOA_ERR_ARG;
+    return smpl_forward(*m, betas, rotmat, B, vertices, joints, tape, ST(stream));
+}
+int dboa_smpl_backward(const dboa_smpl_model* m, const float* rotmat, int B, const float* tape, const float* d_joints, float* scratch,
+                       float* d_rotmat, float* d_betas, int accumulate, dboa_stream_t stream) {
+    if (!m || !rotmat || !tape || !d_joints || !scratch || !d_rotmat || !d_betas || B < 1) return DBOA_ERR_ARG;
+    return smpl_backward(*m, rotmat, B, tape, d_joints, scratch, d_rotmat, d_betas, accumulate, ST(stream));
+}
+
+int dboa_project_fwd(const float* cam, const float* j3d, float* p2d, int B, int NJ, dboa_stream_t stream) {
+    if (!cam || !j3d || !p2d || B < 1 || NJ < 1) return DBOA_ERR_ARG;
+    return project_fwd_launch(cam, j3d, p2d, B, NJ, ST(stream));
+}
+int dboa_project_bwd(const float* cam, const float* j3d, const float* dp2d, float* dj3d, float* dcam, int B, int NJ, int acc_j, int acc_cam,
+                     dboa_stream_t stream) {
+    if (!cam || !j3d || !dp2d || !dj3d || !dcam || B < 1 || NJ < 1) return DBOA_ERR_ARG;
+    return project_bwd_launch(cam, j3d, dp2d, dj3d, dcam, B, NJ, acc_j, acc_cam, ST(stream));
+}
+int dboa_pose_prior(const float* rotmat, const float* means, const float* precisions, const float* neg_log_w, float* prior_b, float* d_rotmat,
+                    float scale, int B, dboa_stream_t stream) {
+    if (!rotmat || !means || !precisions || !neg_log_w || !prior_b || B < 1) return DBOA_ERR_ARG;
+    return pose_prior_launch(rotmat, means, precisions, neg_log_w, prior_b, d_rotmat, scale, B, ST(stream));
+}
+int dboa_gmm_prior(const float* pose69, const float* means, const float* precisions, const float* neg_log_w, float* prior_b, float* d_pose,
+                   float scale, int B, dboa_stream_t stream) {
+    if (!pose69 || !means || !precisions || !neg_log_w || !prior_b || B < 1) return DBOA_ERR_ARG;
+    return gmm_prior_launch(pose69, means, precisions, neg_log_w, prior_b, d_pose, scale, B, ST(stream));
+}
+int dboa_loss_multi(const dboa_loss_args* a, dboa_stream_t stream) {
+    if (!a || !a->p2d || !a->j3d || !a->R || !a->beta || !a->terms) return DBOA_ERR_ARG;
+    if (a->gt_s3d && !a->kp) return DBOA_ERR_ARG;
+    return loss_multi_launch(*a, ST(stream));
+}
+int dboa_loss_motion(const float* p_cur, const float* p_hist, const float* kp_cur, const float* kp_hist, float weight, float* term,
+                     float* dp_cur, float* dp_hist, int B, int accumulate_cur, dboa_stream_t stream) {
+    if (!p_cur || !p_hist || !kp_cur || !kp_hist || !term || !dp_cur || !dp_hist || B < 1) return DBOA_ERR_ARG;
+    return loss_motion_launch(p_cur, p_hist, kp_cur, kp_hist, weight, term, dp_cur, dp_hist, B, accumulate_cur, ST(stream));
+}
+
+int dboa_sgd_update(const float* p, const float* g, float* out, float lr, long long n, dboa_stream_t stream) {
+    if (!p || !g || !out || n < 0) return DBOA_ERR_ARG;
+    return sgd_update(p, g, out, lr, (size_t)n, ST(stream));
+}
+int dboa_adam_ema(float* p, const float* g, float* m, float* v, float* teacher, long long n, float lr, float beta1, float beta2, float eps,
+                  int step, float alpha, dboa_stream_t stream) {
+    if (!p || !g || !m || !v || n < 0) return DBOA_ERR_ARG;
+    return adam_ema(p, g, m, v, teacher, (size_t)n, lr, beta1, beta2, eps, step, alpha, ST(stream));
+}
+int dboa_ema_update(float* teacher, const float* p, long long n, float alpha, dboa_stream_t stream) {
+    if (!teacher || !p || n < 0) return DBOA_ERR_ARG;
+    return ema_update(teacher, p, (size_t)n, alpha, ST(stream));
+}
+int dboa_cosine_pairs(const float* const* a, const float* const* b, const long long* n, int npairs, float* partial, long long partial_floats,
+                      float* out, float eps, dboa_stream_t stream) {
+    if (!a || !b || !n || !partial || !out || npairs < 1 || npairs > 16) return DBOA_ERR_ARG;
+    CosinePairs cp;
+    cp.npairs = npairs;
+    for (int i = 0; i < npairs; ++i) { cp.a[i] = a[i]; cp.b[i] = b[i]; cp.n[i] = n[i]; }
+    return cosine_pairs(cp, partial, (size_t)partial_floats, out, eps, ST(stream));
+}
+int dboa_retrieval_nearest(const float* feat, const float* centers, int K, int D, int* best, float* dists, dboa_stream_t stream) {
+    if (!feat || !centers || !best || !dists) return DBOA_ERR_ARG;
+    return retrieval_nearest(feat, centers, K, D, best, dists, ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,344 @@
+// fp32 implicit-GEMM convolution on CUDA cores: forward, data gradient, weight gradient.
+//
+// Replaces the cuDNN calls behind reference model/hmr.py:29-34,72,113 (53 x nn.Conv2d, bias=False)
+// and their autograd backward.  Activations are NHWC; weights are
+// [Cout][kh][kw][Cin] with a row pitch `Kpitch >= roundup16(kh*kw*Cin)` (zero padded).
+//
+// This is the exact-fp32 path: it is the numerical reference the tcgen05 TF32x3 path
+// (conv_tc.cu) is checked against on the GPU, and it serves the shapes that path does not
+// take (Cin = 3 stem, odd tiles).  Split-K is deterministic: partial tiles go to a workspace
+// and are summed in a fixed order by `splitk_reduce_kernel`.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dboa {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256, PADM = 4;
+
+// One BK-deep slab of the 64x64 tile product; thread (tx,ty) owns a 4x4 micro-tile.
+__device__ __forceinline__ void mma_slab(const float (*As)[BM + PADM], const float (*Bs)[BN + PADM], int tx, int ty,
+                                         float acc[4][4]) {
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+        float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward:  y[m][n] = sum_k xcol[m][k] * w[n][k],   m = (b,ho,wo), k = (r,s,ci)
+// grid (ceil(M/64), Cout/64, nsplit); each z-slice covers k in [z*klen, (z+1)*klen)
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(NT) conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      float* __restrict__ out, ConvDims d, int klen) {
+    __shared__ __align__(16) float As[BK][BM + PADM];
+    __shared__ __align__(16) float Bs[BK][BN + PADM];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int M = d.B * d.Ho * d.Wo, K = d.kh * d.kw * d.Cin;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kbeg = blockIdx.z * klen, kend = min(kbeg + klen, (K + BK - 1) / BK * BK);
+
+    // loader roles: row = tid/4, kv = tid%4 (4 consecutive k)
+    const int lrow = tid >> 2, lkv = (tid & 3) * 4;
+    const int m = m0 + lrow;
+    const bool mvalid = m < M;
+    int hi0 = 0, wi0 = 0;
+    const float* xb = x;
+    if (mvalid) {
+        int b = m / (d.Ho * d.Wo), rem = m - b * d.Ho * d.Wo;
+        int ho = rem / d.Wo, wo = rem - ho * d.Wo;
+        hi0 = ho * d.stride - d.pad; wi0 = wo * d.stride - d.pad;
+        xb = x + (size_t)b * d.Hi * d.Wi * d.Cin;
+    }
+    const float* wrow = w + (size_t)(n0 + lrow) * d.Kpitch;
+
+    float acc[4][4] = {};
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        const int k = k0 + lkv;
+        float av[4] = {0.f, 0.f, 0.f, 0.f};
+        if (mvalid) {
+            if (VEC == 4) {
+                if (k < K) {
+                    int tap = k / d.Cin, ci = k - tap * d.Cin;
+                    int r = tap / d.kw, s = tap - r * d.kw;
+                    int hi = hi0 + r, wi = wi0 + s;
+                    if ((unsigned)hi < (unsigned)d.Hi && (unsigned)wi < (unsigned)d.Wi) {
+                        float4 v = ldg4(xb + ((size_t)hi * d.Wi + wi) * d.Cin + ci);
+                        av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    int kk = k + e;
+                    if (kk < K) {
+                        int tap = kk / d.Cin, ci = kk - tap * d.Cin;
+                        int r = tap / d.kw, s = tap - r * d.kw;
+                        int hi = hi0 + r, wi = wi0 + s;
+                        if ((unsigned)hi < (unsigned)d.Hi && (unsigned)wi < (unsigned)d.Wi)
+                            av[e] = __ldg(xb + ((size_t)hi * d.Wi + wi) * d.Cin + ci);
+                    }
+                }
+            }
+        }
+        float4 bv = ldg4(wrow + k);           // rows are zero padded up to Kpitch >= roundup16(K)
+        __syncthreads();
+        As[lkv + 0][lrow] = av[0]; As[lkv + 1][lrow] = av[1]; As[lkv + 2][lrow] = av[2]; As[lkv + 3][lrow] = av[3];
+        Bs[lkv + 0][lrow] = bv.x; Bs[lkv + 1][lrow] = bv.y; Bs[lkv + 2][lrow] = bv.z; Bs[lkv + 3][lrow] = bv.w;
+        __syncthreads();
+        mma_slab(As, Bs, tx, ty, acc);
+    }
+    float* o = out + (size_t)blockIdx.z * M * d.Cout;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int mm = m0 + ty * 4 + i;
+        if (mm < M)
+            *reinterpret_cast<float4*>(o + (size_t)mm * d.Cout + n0 + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// data gradient:  dx[m][ci] = sum_{r,s,co} dy[b][ho][wo][co] * w[co][r][s][ci]
+//   m = (b,hi,wi);  ho = (hi + pad - r)/stride when divisible and in range
+// GEMM view: M = B*Hi*Wi, N = Cin, K = kh*kw*Cout ordered (r,s,co)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) conv_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                        float* __restrict__ out, ConvDims d, int klen, int accumulate) {
+    __shared__ __align__(16) float As[BK][BM + PADM];
+    __shared__ __align__(16) float Bs[BK][BN + PADM];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int M = d.B * d.Hi * d.Wi, K = d.kh * d.kw * d.Cout;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kbeg = blockIdx.z * klen, kend = min(kbeg + klen, K);
+
+    const int lrow = tid >> 2, lkv = (tid & 3) * 4;       // A loader: 4 consecutive co
+    const int m = m0 + lrow;
+    const bool mvalid = m < M;
+    int hi = 0, wi = 0;
+    const float* dyb = dy;
+    if (mvalid) {
+        int b = m / (d.Hi * d.Wi), rem = m - b * d.Hi * d.Wi;
+        hi = rem / d.Wi; wi = rem - hi * d.Wi;
+        dyb = dy + (size_t)b * d.Ho * d.Wo * d.Cout;
+    }
+    const int bk = tid >> 4, bnv = (tid & 15) * 4;        // B loader: row k, 4 consecutive ci
+
+    float acc[4][4] = {};
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+            const int k = k0 + lkv;
+            if (mvalid && k < kend) {
+                int tap = k / d.Cout, co = k - tap * d.Cout;
+                int r = tap / d.kw, s = tap - r * d.kw;
+                int th = hi + d.pad - r, tw = wi + d.pad - s;
+                if (th >= 0 && tw >= 0) {
+                    int ho = th / d.stride, wo = tw / d.stride;
+                    if (ho * d.stride == th && wo * d.stride == tw && ho < d.Ho && wo < d.Wo)
+                        av = ldg4(dyb + ((size_t)ho * d.Wo + wo) * d.Cout + co);
+                }
+            }
+        }
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+            const int k = k0 + bk;
+            if (k < kend) {
+                int tap = k / d.Cout, co = k - tap * d.Cout;
+                bv = ldg4(w + (size_t)co * d.Kpitch + (size_t)tap * d.Cin + n0 + bnv);
+            }
+        }
+        __syncthreads();
+        As[lkv + 0][lrow] = av.x; As[lkv + 1][lrow] = av.y; As[lkv + 2][lrow] = av.z; As[lkv + 3][lrow] = av.w;
+        *reinterpret_cast<float4*>(&Bs[bk][bnv]) = bv;
+        __syncthreads();
+        mma_slab(As, Bs, tx, ty, acc);
+    }
+    float* o = out + (size_t)blockIdx.z * M * d.Cin;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int mm = m0 + ty * 4 + i;
+        if (mm < M) {
+            float4* p = reinterpret_cast<float4*>(o + (size_t)mm * d.Cin + n0 + tx * 4);
+            float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            if (accumulate) { float4 c = *p; v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w; }
+            *p = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient:  dw[co][(r,s,ci)] (+)= sum_m dy[m][co] * xcol[m][(r,s,ci)]
+// GEMM view: M' = Cout, N' = kh*kw*Cin, K' = B*Ho*Wo (split over blockIdx.z)
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(NT) conv_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                        float* __restrict__ out, ConvDims d, int plen, int direct_accumulate) {
+    __shared__ __align__(16) float As[BK][BM + PADM];
+    __shared__ __align__(16) float Bs[BK][BN + PADM];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int Mpix = d.B * d.Ho * d.Wo, K = d.kh * d.kw * d.Cin;
+    const int m0 = blockIdx.x * BM /* co */, n0 = blockIdx.y * BN /* (r,s,ci) */;
+    const int pbeg = blockIdx.z * plen, pend = min(pbeg + plen, Mpix);
+
+    const int lk = tid >> 4, lv = (tid & 15) * 4;
+    // B loader: this thread's 4 columns n' = n0 + lv .. +3
+    int br[4], bs[4], bc[4]; bool bval[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        int n = n0 + lv + e;
+        bval[e] = n < K;
+        int tap = bval[e] ? n / d.Cin : 0;
+        bc[e] = bval[e] ? n - tap * d.Cin : 0;
+        br[e] = tap / d.kw; bs[e] = tap - br[e] * d.kw;
+    }
+
+    float acc[4][4] = {};
+    for (int p0 = pbeg; p0 < pend; p0 += BK) {
+        const int p = p0 + lk;
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p < pend) {
+            av = ldg4(dy + (size_t)p * d.Cout + m0 + lv);
+            int b = p / (d.Ho * d.Wo), rem = p - b * d.Ho * d.Wo;
+            int ho = rem / d.Wo, wo = rem - ho * d.Wo;
+            const float* xb = x + (size_t)b * d.Hi * d.Wi * d.Cin;
+            if (VEC == 4) {
+                if (bval[0]) {
+                    int hi = ho * d.stride - d.pad + br[0], wi = wo * d.stride - d.pad + bs[0];
+                    if ((unsigned)hi < (unsigned)d.Hi && (unsigned)wi < (unsigned)d.Wi) {
+                        float4 v = ldg4(xb + ((size_t)hi * d.Wi + wi) * d.Cin + bc[0]);
+                        bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (bval[e]) {
+                        int hi = ho * d.stride - d.pad + br[e], wi = wo * d.stride - d.pad + bs[e];
+                        if ((unsigned)hi < (unsigned)d.Hi && (unsigned)wi < (unsigned)d.Wi)
+                            bv[e] = __ldg(xb + ((size_t)hi * d.Wi + wi) * d.Cin + bc[e]);
+                    }
+            }
+        }
+        __syncthreads();
+        *reinterpret_cast<float4*>(&As[lk][lv]) = av;
+        *reinterpret_cast<float4*>(&Bs[lk][lv]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+        __syncthreads();
+        mma_slab(As, Bs, tx, ty, acc);
+    }
+    // rows = co, cols = n'
+    float* o = out + (direct_accumulate ? (size_t)0 : (size_t)blockIdx.z * d.Cout * d.Kpitch);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int co = m0 + ty * 4 + i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tx * 4 + j;
+            if (n < K) {
+                float* p = o + (size_t)co * d.Kpitch + n;
+                *p = direct_accumulate ? (*p + acc[i][j]) : acc[i][j];
+            }
+        }
+    }
+}
+
+// out[i] = (accumulate ? out[i] : 0) + sum_z part[z][i]   (fixed order => deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, size_t n4, int nsplit, int accumulate) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 s = accumulate ? reinterpret_cast<float4*>(out)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < nsplit; ++z) {
+        float4 v = reinterpret_cast<const float4*>(part)[(size_t)z * n4 + i];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static const int kTargetCtas = 296;      // 2 x 148 SMs
+
+static int pick_split(int tiles, int kiters, size_t out_floats, size_t ws_floats) {
+    if (tiles >= kTargetCtas || kiters < 8) return 1;
+    int s = (kTargetCtas + tiles - 1) / tiles;
+    if (s > kiters / 4) s = kiters / 4;
+    while (s > 1 && (size_t)s * out_floats > ws_floats) --s;
+    return s < 1 ? 1 : s;
+}
+
+int conv_fwd(const float* x, const float* w, float* y, const ConvDims& d, float* ws, size_t ws_floats, cudaStream_t st) {
+    if (d.Cout % BN != 0 || d.Kpitch % 4 != 0) return DBOA_ERR_SHAPE;
+    const int M = d.B * d.Ho * d.Wo, K = d.kh * d.kw * d.Cin;
+    if (d.Kpitch < (K + BK - 1) / BK * BK) return DBOA_ERR_SHAPE;
+    const int kiters = (K + BK - 1) / BK;
+    const int tiles = ceil_div(M, BM) * (d.Cout / BN);
+    int ns = pick_split(tiles, kiters, (size_t)M * d.Cout, ws_floats);
+    int klen = ((kiters + ns - 1) / ns) * BK;
+    ns = (kiters * BK + klen - 1) / klen;
+    dim3 grid(ceil_div(M, BM), d.Cout / BN, ns);
+    float* dst = ns > 1 ? ws : y;
+    if (d.Cin % 4 == 0) conv_fwd_kernel<4><<<grid, NT, 0, st>>>(x, w, dst, d, klen);
+    else conv_fwd_kernel<1><<<grid, NT, 0, st>>>(x, w, dst, d, klen);
+    DBOA_TRY(check_launch());
+    if (ns > 1) {
+        size_t n4 = (size_t)M * d.Cout / 4;
+        splitk_reduce_kernel<<<ceil_div(n4, 256), 256, 0, st>>>(ws, y, n4, ns, 0);
+        DBOA_TRY(check_launch());
+    }
+    return DBOA_OK;
+}
+
+int conv_dgrad(const float* dy, const float* w, float* dx, const ConvDims& d, int accumulate, float* ws, size_t ws_floats,
+               cudaStream_t st) {
+    if (d.Cin % BN != 0 || d.Cout % BK != 0) return DBOA_ERR_SHAPE;
+    const int M = d.B * d.Hi * d.Wi, K = d.kh * d.kw * d.Cout;
+    const int kiters = K / BK;
+    const int tiles = ceil_div(M, BM) * (d.Cin / BN);
+    int ns = pick_split(tiles, kiters, (size_t)M * d.Cin, ws_floats);
+    int klen = ((kiters + ns - 1) / ns) * BK;
+    ns = (K + klen - 1) / klen;
+    dim3 grid(ceil_div(M, BM), d.Cin / BN, ns);
+    conv_dgrad_kernel<<<grid, NT, 0, st>>>(dy, w, ns > 1 ? ws : dx, d, klen, ns > 1 ? 0 : accumulate);
+    DBOA_TRY(check_launch());
+    if (ns > 1) {
+        size_t n4 = (size_t)M * d.Cin / 4;
+        splitk_reduce_kernel<<<ceil_div(n4, 256), 256, 0, st>>>(ws, dx, n4, ns, accumulate);
+        DBOA_TRY(check_launch());
+    }
+    return DBOA_OK;
+}
+
+int conv_wgrad(const float* dy, const float* x, float* dw, const ConvDims& d, float* ws, size_t ws_floats, cudaStream_t st) {
+    if (d.Cout % BM != 0) return DBOA_ERR_SHAPE;
+    const int Mpix = d.B * d.Ho * d.Wo, K = d.kh * d.kw * d.Cin;
+    const int piters = ceil_div(Mpix, BK);
+    const int tiles = (d.Cout / BM) * ceil_div(K, BN);
+    size_t wfloats = (size_t)d.Cout * d.Kpitch;
+    int ns = pick_split(tiles, piters, wfloats, ws_floats);
+    int plen = ((piters + ns - 1) / ns) * BK;
+    ns = (Mpix + plen - 1) / plen;
+    dim3 grid(d.Cout / BM, ceil_div(K, BN), ns);
+    if (ns > 1) {
+        // partial slabs must be fully defined where the reduce reads them: clear the padded pitch once
+        if (d.Kpitch != K) { cudaMemsetAsync(ws, 0, (size_t)ns * wfloats * sizeof(float), st); }
+    }
+    float* dst = ns > 1 ? ws : dw;
+    if (d.Cin % 4 == 0) conv_wgrad_kernel<4><<<grid, NT, 0, st>>>(dy, x, dst, d, plen, ns > 1 ? 0 : 1);
+    else conv_wgrad_kernel<1><<<grid, NT, 0, st>>>(dy, x, dst, d, plen, ns > 1 ? 0 : 1);
+    DBOA_TRY(check_launch());
+    if (ns > 1) {
+        size_t n4 = wfloats / 4;
+        splitk_reduce_kernel<<<ceil_div(n4, 256), 256, 0, st>>>(ws, dw, n4, ns, 1);
+        DBOA_TRY(check_launch());
+    }
+    return DBOA_OK;
+}
+
+}  // namespace dboa

@@ -1,0 +1,455 @@
+// Whole-network launch plan of the HMR regressor: parameter arena layout, activation tape layout,
+// forward and hand-written backward (no autograd-through-autograd).
+//
+// Replaces reference model/hmr.py:67-124 (module construction / state_dict contract),
+// :127-181 (HMR.forward, Bottleneck.forward :40-60) and the torch autograd backward that
+// learn2learn's MAML.adapt / loss.backward() run over it (reference dynaboa_benchmark.py:140,150).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dboa {
+
+int g_last_cuda_error = 0;
+int g_launch_count = 0;
+
+// ---------------------------------------------------------------------------------------------
+// static network description
+// ---------------------------------------------------------------------------------------------
+struct ConvLayer {
+    std::string wname, nname;      // state_dict prefixes of the conv and its GroupNorm
+    int cin, cout, k, stride, pad, hin, hout, kpitch;
+    long long w_off, g_off, b_off; // arena offsets (floats)
+};
+struct Block { int c1, c2, c3, cd; };     // conv indices; cd = -1 when the residual is the identity
+
+struct ParamInfo { std::string name; long long off; int ndim; long long shape[4], stride[4]; };
+
+struct Net {
+    std::vector<ConvLayer> convs;
+    std::vector<Block> blocks;
+    std::vector<ParamInfo> params;       // nn.Module.parameters() order of the reference
+    long long arena_floats = 0;
+    long long fc1_w, fc1_b, fc2_w, fc2_b, dec_w, dec_b;
+};
+
+static long long align32(long long x) { return (x + 31) / 32 * 32; }
+
+static const int kBlocks[4] = {3, 4, 6, 3}, kPlanes[4] = {64, 128, 256, 512};
+static const int HEAD_IN = 2205, HEAD_LD = 2208, HID = 1024, NDEC = 157, DEC_LD = 160;
+
+static Net build_net() {
+    Net n;
+    long long off = 0;
+    auto add_conv = [&](const std::string& wname, const std::string& nname, int cin, int cout, int k, int stride, int pad, int hin) {
+        ConvLayer c;
+        c.wname = wname; c.nname = nname; c.cin = cin; c.cout = cout; c.k = k; c.stride = stride; c.pad = pad; c.hin = hin;
+        c.hout = (hin + 2 * pad - k) / stride + 1;
+        int K = k * k * cin;
+        c.kpitch = (K + 15) / 16 * 16;
+        c.w_off = off; off = align32(off + (long long)cout * c.kpitch);
+        c.g_off = off; off = align32(off + cout);
+        c.b_off = off; off = align32(off + cout);
+        ParamInfo w{wname + ".weight", c.w_off, 4, {cout, cin, k, k}, {c.kpitch, 1, (long long)k * cin, cin}};
+        ParamInfo g{nname + ".weight", c.g_off, 1, {cout, 1, 1, 1}, {1, 1, 1, 1}};
+        ParamInfo b{nname + ".bias", c.b_off, 1, {cout, 1, 1, 1}, {1, 1, 1, 1}};
+        n.params.push_back(w); n.params.push_back(g); n.params.push_back(b);
+        n.convs.push_back(c);
+        return (int)n.convs.size() - 1;
+    };
+    add_conv("conv1", "bn1", 3, 64, 7, 2, 3, 224);
+    int inpl = 64, h = 56;
+    for (int li = 0; li < 4; ++li) {
+        for (int bi = 0; bi < kBlocks[li]; ++bi) {
+            int s = (li > 0 && bi == 0) ? 2 : 1, pl = kPlanes[li];
+            char pre[64];
+            snprintf(pre, sizeof pre, "layer%d.%d", li + 1, bi);
+            Block b;
+            b.c1 = add_conv(std::string(pre) + ".conv1", std::string(pre) + ".bn1", inpl, pl, 1, 1, 0, h);
+            b.c2 = add_conv(std::string(pre) + ".conv2", std::string(pre) + ".bn2", pl, pl, 3, s, 1, h);
+            int hout = h / s;
+            b.c3 = add_conv(std::string(pre) + ".conv3", std::string(pre) + ".bn3", pl, pl * 4, 1, 1, 0, hout);
+            b.cd = -1;
+            if (bi == 0) b.cd = add_conv(std::string(pre) + ".downsample.0", std::string(pre) + ".downsample.1", inpl, pl * 4, 1, s, 0, h);
+            n.blocks.push_back(b);
+            inpl = pl * 4; h = hout;
+        }
+    }
+    n.fc1_w = off; off = align32(off + (long long)HID * HEAD_LD);
+    n.fc1_b = off; off = align32(off + HID);
+    n.fc2_w = off; off = align32(off + (long long)HID * HID);
+    n.fc2_b = off; off = align32(off + HID);
+    n.dec_w = off; off = align32(off + (long long)NDEC * HID);
+    n.dec_b = off; off = align32(off + NDEC);
+    n.params.push_back({"fc1.weight", n.fc1_w, 2, {HID, HEAD_IN, 1, 1}, {HEAD_LD, 1, 1, 1}});
+    n.params.push_back({"fc1.bias", n.fc1_b, 1, {HID, 1, 1, 1}, {1, 1, 1, 1}});
+    n.params.push_back({"fc2.weight", n.fc2_w, 2, {HID, HID, 1, 1}, {HID, 1, 1, 1}});
+    n.params.push_back({"fc2.bias", n.fc2_b, 1, {HID, 1, 1, 1}, {1, 1, 1, 1}});
+    n.params.push_back({"decpose.weight", n.dec_w, 2, {144, HID, 1, 1}, {HID, 1, 1, 1}});
+    n.params.push_back({"decpose.bias", n.dec_b, 1, {144, 1, 1, 1}, {1, 1, 1, 1}});
+    n.params.push_back({"decshape.weight", n.dec_w + 144LL * HID, 2, {10, HID, 1, 1}, {HID, 1, 1, 1}});
+    n.params.push_back({"decshape.bias", n.dec_b + 144, 1, {10, 1, 1, 1}, {1, 1, 1, 1}});
+    n.params.push_back({"deccam.weight", n.dec_w + 154LL * HID, 2, {3, HID, 1, 1}, {HID, 1, 1, 1}});
+    n.params.push_back({"deccam.bias", n.dec_b + 154, 1, {3, 1, 1, 1}, {1, 1, 1, 1}});
+    n.arena_floats = off;
+    return n;
+}
+
+static const Net& net() {
+    static Net n = build_net();
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// activation tape
+// ---------------------------------------------------------------------------------------------
+struct ConvTape { long long y, part, stats, a; };   // a == -1: output lives in the block's conv3 slot
+struct Tape {
+    long long x0, p0, p0_idx;
+    std::vector<ConvTape> conv;
+    long long xc, h1pre, h1post, h2pre, h2post, params, masks;
+    long long total;
+};
+
+static Tape build_tape(int B) {
+    const Net& n = net();
+    Tape t;
+    long long off = 0;
+    auto take = [&](long long cnt) { long long o = off; off = align32(off + cnt); return o; };
+    t.x0 = take((long long)B * 224 * 224 * 3);
+    t.conv.resize(n.convs.size());
+    for (size_t i = 0; i < n.convs.size(); ++i) {
+        const ConvLayer& c = n.convs[i];
+        long long sz = (long long)B * c.hout * c.hout * c.cout;
+        t.conv[i].y = take(sz);
+        t.conv[i].part = take((long long)gn_partial_floats(B, c.hout * c.hout, c.cout));
+        t.conv[i].stats = take((long long)B * 8);
+        t.conv[i].a = -1;
+    }
+    // post-activation buffers: stem, conv1/conv2/conv3 of each block (downsample shares conv3's)
+    t.conv[0].a = take((long long)B * 112 * 112 * 64);
+    t.p0 = take((long long)B * 56 * 56 * 64);
+    t.p0_idx = take(((long long)B * 56 * 56 * 64 + 3) / 4);
+    for (const Block& b : n.blocks)
+        for (int ci : {b.c1, b.c2, b.c3}) {
+            const ConvLayer& c = n.convs[ci];
+            t.conv[ci].a = take((long long)B * c.hout * c.hout * c.cout);
+        }
+    t.xc = take(3LL * B * HEAD_LD);
+    t.h1pre = take(3LL * B * HID); t.h1post = take(3LL * B * HID);
+    t.h2pre = take(3LL * B * HID); t.h2post = take(3LL * B * HID);
+    t.params = take(4LL * B * DEC_LD);
+    t.masks = take(6LL * B * HID);
+    t.total = off;
+    return t;
+}
+
+static const Tape& tape_for(int B) {
+    static std::vector<Tape> cache(65);
+    static std::vector<char> ready(65, 0);
+    if (!ready[B]) { cache[B] = build_tape(B); ready[B] = 1; }
+    return cache[B];
+}
+
+static const long long kConvWs = 8LL << 20;    // split-K workspace (floats)
+
+struct Scratch {
+    float *ws, *g0, *g1, *t1, *t2, *t3, *gnp, *dP, *dy_dec, *d_h2, *d_h1, *dxc, *dxf, *tmp1024, *lin_ws;
+    long long total;
+    long long lin_ws_floats;
+    Scratch(float* base, int B) {
+        const long long S = (long long)B * 112 * 112 * 64;
+        long long off = 0;
+        auto take = [&](long long cnt) { float* p = base ? base + off : nullptr; off = align32(off + cnt); return p; };
+        ws = take(kConvWs);
+        g0 = take(S); g1 = take(S); t1 = take(S); t2 = take(S); t3 = take(S);
+        long long gmax = 0;
+        for (const ConvLayer& c : net().convs) {
+            long long v = (long long)gn_bwd_partial_floats(B, c.hout * c.hout, c.cout);
+            gmax = v > gmax ? v : gmax;
+        }
+        gnp = take(gmax);
+        dP = take((long long)B * DEC_LD);
+        dy_dec = take(3LL * B * DEC_LD);
+        d_h2 = take(3LL * B * HID); d_h1 = take(3LL * B * HID);
+        dxc = take((long long)B * HEAD_LD);
+        dxf = take((long long)B * 2048);
+        tmp1024 = take((long long)B * HID);
+        lin_ws_floats = 16LL * B * HEAD_LD;
+        lin_ws = take(lin_ws_floats);
+        total = off;
+    }
+};
+
+static ConvDims dims_of(const ConvLayer& c, int B) {
+    ConvDims d;
+    d.B = B; d.Hi = c.hin; d.Wi = c.hin; d.Cin = c.cin; d.Ho = c.hout; d.Wo = c.hout; d.Cout = c.cout;
+    d.kh = c.k; d.kw = c.k; d.stride = c.stride; d.pad = c.pad; d.Kpitch = c.kpitch;
+    return d;
+}
+
+// conv forward with the tensor-core path for plain GEMM shapes (1x1, stride 1) when enabled
+static int conv_forward(const ConvLayer& c, int B, const float* x, const float* w, float* y, float* ws, cudaStream_t st) {
+    if (c.k == 1 && c.stride == 1 && conv_tc_enabled()) {
+        int s = conv1x1_tc_fwd(x, w, y, B * c.hout * c.hout, c.cin, c.cout, st);
+        if (s != DBOA_ERR_UNSUPPORTED) return s;
+    }
+    return conv_fwd(x, w, y, dims_of(c, B), ws, (size_t)kConvWs, st);
+}
+
+__global__ void head_init_kernel(const float* __restrict__ ip, const float* __restrict__ is, const float* __restrict__ ic,
+                                 float* __restrict__ params0, float* __restrict__ xc0, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * NDEC) return;
+    int b = i / NDEC, j = i - b * NDEC;
+    float v = j < 144 ? ip[j] : (j < 154 ? is[j - 144] : ic[j - 154]);
+    params0[(size_t)b * DEC_LD + j] = v;
+    xc0[(size_t)b * HEAD_LD + 2048 + j] = v;
+}
+__global__ void head_out_kernel(const float* __restrict__ params3, float* __restrict__ shape, float* __restrict__ cam,
+                                float* __restrict__ pose6d, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * NDEC) return;
+    int b = i / NDEC, j = i - b * NDEC;
+    float v = params3[(size_t)b * DEC_LD + j];
+    if (j < 144) { if (pose6d) pose6d[(size_t)b * 144 + j] = v; }
+    else if (j < 154) shape[(size_t)b * 10 + (j - 144)] = v;
+    else cam[(size_t)b * 3 + (j - 154)] = v;
+}
+// dP[b][:] = [rot6d-adjoint (filled separately) | d_shape | d_cam]
+__global__ void head_grad_in_kernel(const float* __restrict__ dshape, const float* __restrict__ dcam, float* __restrict__ dP, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 16) return;
+    int b = i / 16, j = i - b * 16;
+    float v = j < 10 ? (dshape ? dshape[b * 10 + j] : 0.f) : (j < 13 ? (dcam ? dcam[b * 3 + (j - 10)] : 0.f) : 0.f);
+    dP[(size_t)b * DEC_LD + 144 + j] = v;
+}
+// pose6d rows live with a leading dimension (DEC_LD) inside the tape
+__global__ void rot6d_rows_fwd_kernel(const float* __restrict__ params3, float* __restrict__ rotmat, int B);
+__global__ void rot6d_rows_bwd_kernel(const float* __restrict__ params3, const float* __restrict__ drot, float* __restrict__ dP, int B);
+
+}  // namespace dboa
+
+#include "rotmath.cuh"
+namespace dboa {
+
+__global__ void rot6d_rows_fwd_kernel(const float* __restrict__ params3, float* __restrict__ rotmat, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 24) return;
+    int b = i / 24, j = i - b * 24;
+    float x[6], R[9];
+    for (int k = 0; k < 6; ++k) x[k] = params3[(size_t)b * DEC_LD + j * 6 + k];
+    rot6d_fwd(x, R);
+    for (int k = 0; k < 9; ++k) rotmat[(size_t)i * 9 + k] = R[k];
+}
+__global__ void rot6d_rows_bwd_kernel(const float* __restrict__ params3, const float* __restrict__ drot, float* __restrict__ dP, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 24) return;
+    int b = i / 24, j = i - b * 24;
+    float x[6], g[9], d[6];
+    for (int k = 0; k < 6; ++k) x[k] = params3[(size_t)b * DEC_LD + j * 6 + k];
+    for (int k = 0; k < 9; ++k) g[k] = drot ? drot[(size_t)i * 9 + k] : 0.f;
+    rot6d_bwd(x, g, d);
+    for (int k = 0; k < 6; ++k) dP[(size_t)b * DEC_LD + j * 6 + k] = d[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+int hmr_forward(const float* P, const float* init_pose, const float* init_shape, const float* init_cam, const float* image, int B,
+                const float* drop_masks, float* T, float* scratch, float* rotmat, float* shape, float* cam, float* pose6d,
+                cudaStream_t st) {
+    if (B < 1 || B > 64) return DBOA_ERR_SHAPE;
+    const Net& n = net();
+    const Tape& t = tape_for(B);
+    Scratch sc(scratch, B);
+    auto gn_plain = [&](int ci, float* out, int relu, const float* res) {
+        const ConvLayer& c = n.convs[ci];
+        int HW = c.hout * c.hout;
+        DBOA_TRY(gn_stats(T + t.conv[ci].y, B, HW, c.cout, T + t.conv[ci].part, st));
+        return gn_apply(T + t.conv[ci].y, T + t.conv[ci].part, P + c.g_off, P + c.b_off, T + t.conv[ci].stats, res, nullptr, nullptr,
+                        nullptr, nullptr, nullptr, out, B, HW, c.cout, relu, st);
+    };
+    DBOA_TRY(nchw_to_nhwc(image, T + t.x0, B, 3, 224, 224, st));
+    DBOA_TRY(conv_forward(n.convs[0], B, T + t.x0, P + n.convs[0].w_off, T + t.conv[0].y, sc.ws, st));
+    DBOA_TRY(gn_plain(0, T + t.conv[0].a, 1, nullptr));
+    DBOA_TRY(maxpool3x3s2_fwd(T + t.conv[0].a, T + t.p0, reinterpret_cast<unsigned char*>(T + t.p0_idx), B, 112, 112, 64, st));
+    const float* x = T + t.p0;
+    for (const Block& b : n.blocks) {
+        const ConvLayer &c1 = n.convs[b.c1], &c2 = n.convs[b.c2], &c3 = n.convs[b.c3];
+        DBOA_TRY(conv_forward(c1, B, x, P + c1.w_off, T + t.conv[b.c1].y, sc.ws, st));
+        DBOA_TRY(gn_plain(b.c1, T + t.conv[b.c1].a, 1, nullptr));
+        DBOA_TRY(conv_forward(c2, B, T + t.conv[b.c1].a, P + c2.w_off, T + t.conv[b.c2].y, sc.ws, st));
+        DBOA_TRY(gn_plain(b.c2, T + t.conv[b.c2].a, 1, nullptr));
+        DBOA_TRY(conv_forward(c3, B, T + t.conv[b.c2].a, P + c3.w_off, T + t.conv[b.c3].y, sc.ws, st));
+        const int HW = c3.hout * c3.hout;
+        if (b.cd >= 0) {
+            const ConvLayer& cd = n.convs[b.cd];
+            DBOA_TRY(conv_forward(cd, B, x, P + cd.w_off, T + t.conv[b.cd].y, sc.ws, st));
+            DBOA_TRY(gn_stats(T + t.conv[b.c3].y, B, HW, c3.cout, T + t.conv[b.c3].part, st));
+            DBOA_TRY(gn_stats(T + t.conv[b.cd].y, B, HW, cd.cout, T + t.conv[b.cd].part, st));
+            DBOA_TRY(gn_apply(T + t.conv[b.c3].y, T + t.conv[b.c3].part, P + c3.g_off, P + c3.b_off, T + t.conv[b.c3].stats, nullptr,
+                              T + t.conv[b.cd].y, T + t.conv[b.cd].part, P + cd.g_off, P + cd.b_off, T + t.conv[b.cd].stats,
+                              T + t.conv[b.c3].a, B, HW, c3.cout, 1, st));
+        } else {
+            DBOA_TRY(gn_plain(b.c3, T + t.conv[b.c3].a, 1, x));
+        }
+        x = T + t.conv[b.c3].a;
+    }
+    // pooled feature goes straight into the three regressor input rows
+    DBOA_TRY(avgpool_fwd(x, T + t.xc, B, 49, 2048, HEAD_LD, 3, (size_t)B * HEAD_LD, st));
+    head_init_kernel<<<ceil_div(B * NDEC, 128), 128, 0, st>>>(init_pose, init_shape, init_cam, T + t.params, T + t.xc, B);
+    DBOA_TRY(check_launch());
+    if (drop_masks) cudaMemcpyAsync(T + t.masks, drop_masks, 6ULL * B * HID * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    for (int it = 0; it < 3; ++it) {
+        const float* m1 = drop_masks ? T + t.masks + (size_t)(it * 2 + 0) * B * HID : nullptr;
+        const float* m2 = drop_masks ? T + t.masks + (size_t)(it * 2 + 1) * B * HID : nullptr;
+        float* xc = T + t.xc + (size_t)it * B * HEAD_LD;
+        float* h1pre = T + t.h1pre + (size_t)it * B * HID; float* h1post = T + t.h1post + (size_t)it * B * HID;
+        float* h2pre = T + t.h2pre + (size_t)it * B * HID; float* h2post = T + t.h2post + (size_t)it * B * HID;
+        DBOA_TRY(linear_fwd(xc, HEAD_LD, P + n.fc1_w, HEAD_LD, P + n.fc1_b, nullptr, 0, m1, h1pre, h1post, HID, nullptr, 0, B, HID, HEAD_IN, st));
+        DBOA_TRY(linear_fwd(h1post, HID, P + n.fc2_w, HID, P + n.fc2_b, nullptr, 0, m2, h2pre, h2post, HID, nullptr, 0, B, HID, HID, st));
+        float* pin = T + t.params + (size_t)it * B * DEC_LD;
+        float* pout = T + t.params + (size_t)(it + 1) * B * DEC_LD;
+        float* xnext = it < 2 ? T + t.xc + (size_t)(it + 1) * B * HEAD_LD + 2048 : nullptr;
+        DBOA_TRY(linear_fwd(h2post, HID, P + n.dec_w, HID, P + n.dec_b, pin, DEC_LD, nullptr, nullptr, pout, DEC_LD, xnext, HEAD_LD, B, NDEC,
+                            HID, st));
+    }
+    const float* p3 = T + t.params + 3ULL * B * DEC_LD;
+    rot6d_rows_fwd_kernel<<<ceil_div(B * 24, 128), 128, 0, st>>>(p3, rotmat, B);
+    DBOA_TRY(check_launch());
+    head_out_kernel<<<ceil_div(B * NDEC, 128), 128, 0, st>>>(p3, shape, cam, pose6d, B);
+    return check_launch();
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward (accumulates into the flat gradient arena G, same layout as P)
+// ---------------------------------------------------------------------------------------------
+int hmr_backward(const float* P, const float* T, int B, int masked_in, const float* d_rotmat, const float* d_shape, const float* d_cam,
+                 float* G, float* scratch, cudaStream_t st) {
+    if (B < 1 || B > 64) return DBOA_ERR_SHAPE;
+    const Net& n = net();
+    const Tape& t = tape_for(B);
+    Scratch sc(scratch, B);
+    const bool masked = masked_in != 0;     // the forward ran with dropout keep-masks (saved in the tape)
+
+    // ---- head
+    const float* p3 = T + t.params + 3ULL * B * DEC_LD;
+    cudaMemsetAsync(sc.dP, 0, (size_t)B * DEC_LD * sizeof(float), st);
+    rot6d_rows_bwd_kernel<<<ceil_div(B * 24, 128), 128, 0, st>>>(p3, d_rotmat, sc.dP, B);
+    DBOA_TRY(check_launch());
+    head_grad_in_kernel<<<ceil_div(B * 16, 128), 128, 0, st>>>(d_shape, d_cam, sc.dP, B);
+    DBOA_TRY(check_launch());
+    cudaMemsetAsync(sc.dxf, 0, (size_t)B * 2048 * sizeof(float), st);
+    for (int it = 2; it >= 0; --it) {
+        float* dy_dec = sc.dy_dec + (size_t)it * B * DEC_LD;
+        float* d_h2 = sc.d_h2 + (size_t)it * B * HID;
+        float* d_h1 = sc.d_h1 + (size_t)it * B * HID;
+        cudaMemcpyAsync(dy_dec, sc.dP, (size_t)B * DEC_LD * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        if (masked) {
+            DBOA_TRY(linear_dgrad(dy_dec, DEC_LD, P + n.dec_w, HID, sc.tmp1024, HID, B, NDEC, HID, sc.lin_ws, sc.lin_ws_floats, st));
+            DBOA_TRY(ew_mul(sc.tmp1024, T + t.masks + (size_t)(it * 2 + 1) * B * HID, d_h2, (size_t)B * HID, st));
+            DBOA_TRY(linear_dgrad(d_h2, HID, P + n.fc2_w, HID, sc.tmp1024, HID, B, HID, HID, sc.lin_ws, sc.lin_ws_floats, st));
+            DBOA_TRY(ew_mul(sc.tmp1024, T + t.masks + (size_t)(it * 2 + 0) * B * HID, d_h1, (size_t)B * HID, st));
+        } else {
+            DBOA_TRY(linear_dgrad(dy_dec, DEC_LD, P + n.dec_w, HID, d_h2, HID, B, NDEC, HID, sc.lin_ws, sc.lin_ws_floats, st));
+            DBOA_TRY(linear_dgrad(d_h2, HID, P + n.fc2_w, HID, d_h1, HID, B, HID, HID, sc.lin_ws, sc.lin_ws_floats, st));
+        }
+        DBOA_TRY(linear_dgrad(d_h1, HID, P + n.fc1_w, HEAD_LD, sc.dxc, HEAD_LD, B, HID, HEAD_IN, sc.lin_ws, sc.lin_ws_floats, st));
+        DBOA_TRY(ew_add_rows(sc.dxf, 2048, sc.dxf, 2048, sc.dxc, HEAD_LD, B, 2048, st));
+        DBOA_TRY(ew_add_rows(sc.dP, DEC_LD, sc.dP, DEC_LD, sc.dxc + 2048, HEAD_LD, B, NDEC, st));
+    }
+    DBOA_TRY(linear_wgrad(sc.dy_dec, DEC_LD, T + t.h2post, HID, G + n.dec_w, HID, G + n.dec_b, 3 * B, NDEC, HID, st));
+    DBOA_TRY(linear_wgrad(sc.d_h2, HID, T + t.h1post, HID, G + n.fc2_w, HID, G + n.fc2_b, 3 * B, HID, HID, st));
+    DBOA_TRY(linear_wgrad(sc.d_h1, HID, T + t.xc, HEAD_LD, G + n.fc1_w, HEAD_LD, G + n.fc1_b, 3 * B, HID, HEAD_IN, st));
+
+    // ---- backbone
+    float* dOut = sc.g0;
+    float* dIn = sc.g1;
+    DBOA_TRY(avgpool_bwd(sc.dxf, 2048, dOut, B, 49, 2048, st));
+    auto gnb = [&](int ci, const float* dout, const float* mask_src, float* dy) {
+        const ConvLayer& c = n.convs[ci];
+        return gn_bwd(dout, mask_src, T + t.conv[ci].y, T + t.conv[ci].stats, P + c.g_off, dy, G + c.g_off, G + c.b_off, sc.gnp, B,
+                      c.hout * c.hout, c.cout, st);
+    };
+    for (int bi = (int)n.blocks.size() - 1; bi >= 0; --bi) {
+        const Block& b = n.blocks[bi];
+        const ConvLayer &c1 = n.convs[b.c1], &c2 = n.convs[b.c2], &c3 = n.convs[b.c3];
+        const float* xin = bi == 0 ? T + t.p0 : T + t.conv[n.blocks[bi - 1].c3].a;
+        const float* a3 = T + t.conv[b.c3].a;
+        DBOA_TRY(gnb(b.c3, dOut, a3, sc.t1));
+        if (b.cd >= 0) {
+            const ConvLayer& cd = n.convs[b.cd];
+            DBOA_TRY(gnb(b.cd, dOut, a3, sc.t2));
+            DBOA_TRY(conv_wgrad(sc.t2, xin, G + cd.w_off, dims_of(cd, B), sc.ws, (size_t)kConvWs, st));
+            DBOA_TRY(conv_dgrad(sc.t2, P + cd.w_off, dIn, dims_of(cd, B), 0, sc.ws, (size_t)kConvWs, st));
+        } else {
+            DBOA_TRY(relu_mask(dOut, a3, dIn, (size_t)B * c3.hout * c3.hout * c3.cout, st));
+        }
+        DBOA_TRY(conv_wgrad(sc.t1, T + t.conv[b.c2].a, G + c3.w_off, dims_of(c3, B), sc.ws, (size_t)kConvWs, st));
+        DBOA_TRY(conv_dgrad(sc.t1, P + c3.w_off, sc.t3, dims_of(c3, B), 0, sc.ws, (size_t)kConvWs, st));
+        DBOA_TRY(gnb(b.c2, sc.t3, T + t.conv[b.c2].a, sc.t1));
+        DBOA_TRY(conv_wgrad(sc.t1, T + t.conv[b.c1].a, G + c2.w_off, dims_of(c2, B), sc.ws, (size_t)kConvWs, st));
+        DBOA_TRY(conv_dgrad(sc.t1, P + c2.w_off, sc.t2, dims_of(c2, B), 0, sc.ws, (size_t)kConvWs, st));
+        DBOA_TRY(gnb(b.c1, sc.t2, T + t.conv[b.c1].a, sc.t3));
+        DBOA_TRY(conv_wgrad(sc.t3, xin, G + c1.w_off, dims_of(c1, B), sc.ws, (size_t)kConvWs, st));
+        DBOA_TRY(conv_dgrad(sc.t3, P + c1.w_off, dIn, dims_of(c1, B), 1, sc.ws, (size_t)kConvWs, st));
+        float* tmp = dOut; dOut = dIn; dIn = tmp;
+    }
+    // ---- stem: maxpool, GroupNorm+ReLU, conv (weight gradient only; the image needs none)
+    DBOA_TRY(maxpool3x3s2_bwd(dOut, reinterpret_cast<const unsigned char*>(T + t.p0_idx), dIn, B, 112, 112, 64, st));
+    DBOA_TRY(gnb(0, dIn, T + t.conv[0].a, sc.t1));
+    return conv_wgrad(sc.t1, T + t.x0, G + n.convs[0].w_off, dims_of(n.convs[0], B), sc.ws, (size_t)kConvWs, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout queries
+// ---------------------------------------------------------------------------------------------
+int hmr_num_params() { return (int)net().params.size(); }
+long long hmr_arena_floats() { return net().arena_floats; }
+int hmr_param_info(int i, char* name, int cap, long long* off, int* ndim, long long shape[4], long long stride[4]) {
+    const Net& n = net();
+    if (i < 0 || i >= (int)n.params.size()) return DBOA_ERR_ARG;
+    const ParamInfo& p = n.params[i];
+    if (name && cap > 0) { strncpy(name, p.name.c_str(), cap - 1); name[cap - 1] = 0; }
+    *off = p.off; *ndim = p.ndim;
+    for (int k = 0; k < 4; ++k) { shape[k] = p.shape[k]; stride[k] = p.stride[k]; }
+    return DBOA_OK;
+}
+long long hmr_tape_floats(int B) { return (B < 1 || B > 64) ? -1 : tape_for(B).total; }
+long long hmr_scratch_floats(int B) { return (B < 1 || B > 64) ? -1 : Scratch(nullptr, B).total; }
+int hmr_feature_info(int B, int i, long long* off, int* ndim, long long shape[4], long long stride[4]) {
+    if (B < 1 || B > 64 || i < 0 || i > 14) return DBOA_ERR_ARG;
+    const Net& n = net();
+    const Tape& t = tape_for(B);
+    for (int k = 0; k < 4; ++k) { shape[k] = 1; stride[k] = 1; }
+    if (i <= 4) {
+        int ci = 0;
+        bool post = i > 0;
+        if (i > 0) {
+            int blk = -1;
+            for (int l = 0; l < i; ++l) blk += kBlocks[l];
+            ci = n.blocks[blk].c3;
+        }
+        const ConvLayer& c = n.convs[ci];
+        *off = post ? t.conv[ci].a : t.conv[ci].y;
+        *ndim = 4;
+        long long H = c.hout, C = c.cout;
+        shape[0] = B; shape[1] = C; shape[2] = H; shape[3] = H;
+        stride[0] = H * H * C; stride[1] = 1; stride[2] = H * C; stride[3] = C;
+    } else if (i == 5) {
+        *off = t.xc; *ndim = 2; shape[0] = B; shape[1] = 2048; stride[0] = HEAD_LD; stride[1] = 1;
+    } else {
+        int it = (i - 6) / 3, which = (i - 6) % 3;
+        long long base = which == 0 ? t.h1pre : (which == 1 ? t.h1post : t.h2pre);
+        *off = base + (long long)it * B * HID; *ndim = 2; shape[0] = B; shape[1] = HID; stride[0] = HID; stride[1] = 1;
+    }
+    return DBOA_OK;
+}
+
+}  // namespace dboa

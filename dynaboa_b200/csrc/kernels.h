@@ -1,0 +1,58 @@
+// Internal launcher prototypes shared between the kernel translation units, the per-op C-ABI
+// wrappers (cabi.cu) and the whole-network plan (hmr_plan.cu).  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace dboa {
+
+struct ConvDims {
+    int B, Hi, Wi, Cin, Ho, Wo, Cout, kh, kw, stride, pad, Kpitch;
+};
+
+// ---- conv.cu (fp32 CUDA-core implicit GEMM)
+int conv_fwd(const float* x, const float* w, float* y, const ConvDims& d, float* ws, size_t ws_floats, cudaStream_t st);
+int conv_dgrad(const float* dy, const float* w, float* dx, const ConvDims& d, int accumulate, float* ws, size_t ws_floats, cudaStream_t st);
+int conv_wgrad(const float* dy, const float* x, float* dw, const ConvDims& d, float* ws, size_t ws_floats, cudaStream_t st);
+
+// ---- conv_tc.cu (tcgen05 TF32x3 GEMM for 1x1 / stride-1 convolutions); returns DBOA_ERR_UNSUPPORTED when the shape is not taken
+int conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin, int Cout, cudaStream_t st);
+bool conv_tc_enabled();
+void conv_tc_set_enabled(bool on);
+
+// ---- norm_pool.cu
+int gn_chunks(int HW, int C);                       // number of row chunks the statistics kernels use
+size_t gn_partial_floats(int B, int HW, int C);     // floats for [B][4][chunks][3]
+int gn_stats(const float* y, int B, int HW, int C, float* partial, cudaStream_t st);
+// out = relu?( gn(y) [+ res] [+ gn(y2)] ); writes final (mean, rstd) to stats[B][4][2] (and stats2)
+int gn_apply(const float* y, const float* partial, const float* gamma, const float* beta, float* stats,
+             const float* res, const float* y2, const float* partial2, const float* gamma2, const float* beta2, float* stats2,
+             float* out, int B, int HW, int C, int relu, cudaStream_t st);
+size_t gn_bwd_partial_floats(int B, int HW, int C);
+// dz = dout * (mask_src > 0 if mask_src else 1); dy = GN backward; dgamma/dbeta accumulate (+=)
+int gn_bwd(const float* dout, const float* mask_src, const float* y, const float* stats, const float* gamma,
+           float* dy, float* dgamma, float* dbeta, float* partial, int B, int HW, int C, cudaStream_t st);
+int relu_mask(const float* dout, const float* mask_src, float* dz, size_t n, cudaStream_t st);
+int nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, cudaStream_t st);
+int maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, cudaStream_t st);
+int maxpool3x3s2_bwd(const float* dy, const unsigned char* idx, float* dx, int B, int H, int W, int C, cudaStream_t st);
+// mean over HW -> out rows with leading dimension ld, replicated `ncopy` times `copy_stride` floats apart
+int avgpool_fwd(const float* x, float* out, int B, int HW, int C, int ld, int ncopy, size_t copy_stride, cudaStream_t st);
+int avgpool_bwd(const float* dxf, int ld, float* dx, int B, int HW, int C, cudaStream_t st);
+
+// ---- head.cu
+// y[b][n] = (addend ? addend[b][n] : 0) + bias[n] + sum_k x[b][k] W[n][k];  pre <- y (before mask), post <- y*mask
+int linear_fwd(const float* x, int ldx, const float* W, int ldw, const float* bias, const float* addend, int ld_add,
+               const float* mask, float* pre, float* post, int ld_out, float* post2, int ld_out2,
+               int B, int N, int K, cudaStream_t st);
+// dx[b][k] = sum_n dy[b][n] W[n][k] (k < K)
+int linear_dgrad(const float* dy, int ldy, const float* W, int ldw, float* dx, int ldx, int B, int N, int K,
+                 float* ws, size_t ws_floats, cudaStream_t st);
+// dW[n][k] += sum_r dy[r][n] x[r][k];  db[n] += sum_r dy[r][n]
+int linear_wgrad(const float* dy, int ldy, const float* x, int ldx, float* dW, int ldw, float* db, int R, int N, int K, cudaStream_t st);
+int rot6d_fwd_launch(const float* pose6d, float* rotmat, int n, cudaStream_t st);
+int rot6d_bwd_launch(const float* pose6d, const float* drot, float* dpose, int n, cudaStream_t st);
+int ew_mul(const float* a, const float* b, float* out, size_t n, cudaStream_t st);
+int ew_add_rows(float* dst, int ld_dst, const float* a, int lda, const float* b, int ldb, int B, int n, cudaStream_t st);
+
+}  // namespace dboa

@@ -1,0 +1,22 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace dboa {
+
+struct CosinePairs {
+    const float* a[16];
+    const float* b[16];
+    long long n[16];
+    int blk_off[17];
+    int npairs;
+};
+
+int sgd_update(const float* p, const float* g, float* out, float lr, size_t n, cudaStream_t st);
+int adam_ema(float* p, const float* g, float* m, float* v, float* teacher, size_t n, float lr, float beta1, float beta2, float eps, int step,
+             float alpha, cudaStream_t st);
+int ema_update(float* teacher, const float* p, size_t n, float alpha, cudaStream_t st);
+int cosine_pairs(const CosinePairs& cp, float* partial, size_t partial_floats, float* out, float eps, cudaStream_t st);
+int retrieval_nearest(const float* feat, const float* centers, int K, int D, int* best, float* dists, cudaStream_t st);
+
+}  // namespace dboa

@@ -1,0 +1,219 @@
+"""Autograd-free bilevel adaptation step: the arithmetic of reference dynaboa_benchmark.py:126-201
+(``Adaptor.adaptation``) driven by direct C-ABI calls.
+
+What changes relative to the autograd path (``Adaptor.adaptation``), none of it numerically:
+
+* gradients of every forward graph of a level (frame, history frame, exemplar minibatch) are accumulated by
+  ``dboa_hmr_backward`` straight into ONE flat arena -- no per-tensor ``.grad`` accumulation, no 169-way splits;
+* inner step 0 reuses the no-grad probe forward (the fast weights equal theta before the first update), and
+  each dynamic iteration reuses the feature-test forward as its upper-level forward (same weights, same image);
+* the first-order MAML adjoint is the identity, so the outer gradient w.r.t. the fast weights IS the gradient
+  applied to theta (SURVEY.md "facts": ``first_order=True``);
+* Adam and the mean-teacher EMA run as one fused sweep; frame and teacher-consistency terms share one loss-head
+  launch; the only host syncs are retrieval's cluster index and the ``dynamic_boa`` decision.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib, hmr as hmr_mod, losses
+from ._lib import ptr, stream
+
+
+class _Pred:
+    """Everything one forward graph produces (kept for its backward)."""
+    __slots__ = ('image', 'rot', 'shape', 'cam', 'tape', 'verts', 'joints', 'smpl_tape', 'p2d', 'B', 'masked')
+
+
+def _smpl_fwd(smpl, betas, rot):
+    B, dev = betas.shape[0], betas.device
+    verts = torch.empty(B, 6890, 3, dtype=torch.float32, device=dev)
+    joints = torch.empty(B, 49, 3, dtype=torch.float32, device=dev)
+    tape = torch.empty(_lib.load().dboa_smpl_tape_floats(B), dtype=torch.float32, device=dev)
+    _lib.call('dboa_smpl_forward', smpl._struct_ref(), ptr(betas), ptr(rot), B, ptr(verts), ptr(joints), ptr(tape), stream())
+    return verts, joints, tape
+
+
+def forward_graph(ad, arena, buffers, image, masks=None):
+    p = _Pred()
+    p.image, p.B, p.masked = image, image.shape[0], masks is not None
+    p.rot, p.shape, p.cam, _, p.tape = hmr_mod.raw_forward(arena, buffers, image, masks)
+    p.verts, p.joints, p.smpl_tape = _smpl_fwd(ad.smpl_neutral, p.shape, p.rot)
+    p.p2d = torch.empty(p.B, 49, 2, dtype=torch.float32, device=image.device)
+    _lib.call('dboa_project_fwd', ptr(p.cam), ptr(p.joints), ptr(p.p2d), p.B, 49, stream())
+    return p
+
+
+def _loss_head(ad, p, w, kp=None, t_p2d=None, t_j3d=None, t_beta=None, t_R=None, gt_s3d=None):
+    """Runs the (optional) pose prior and the multi-term head; returns (terms[9], dp2d, dj3d, dR, dbeta)."""
+    B, dev = p.B, p.rot.device
+    dp2d, dj3d = torch.empty_like(p.p2d), torch.empty_like(p.joints)
+    dR, dbeta = torch.empty_like(p.rot), torch.empty_like(p.shape)
+    terms = torch.empty(9, dtype=torch.float32, device=dev)
+    prior_b = None
+    if w[2] != 0.0:
+        prior_b = torch.empty(B, dtype=torch.float32, device=dev)
+        g = ad.gmm_f
+        _lib.call('dboa_pose_prior', ptr(p.rot), ptr(g.means), ptr(g.precisions), ptr(g.neg_log_weights), ptr(prior_b), ptr(dR),
+                  float(w[2]) / B, B, stream())
+    a = _lib.LossArgsStruct()
+    a.B = B
+    keep = []
+    for name, t in (('p2d', p.p2d), ('j3d', p.joints), ('R', p.rot), ('beta', p.shape), ('kp', kp), ('prior_b', prior_b), ('t_p2d', t_p2d),
+                    ('t_j3d', t_j3d), ('t_beta', t_beta), ('t_R', t_R), ('gt_s3d', gt_s3d), ('terms', terms), ('dp2d', dp2d),
+                    ('dj3d', dj3d), ('dR', dR), ('dbeta', dbeta)):
+        if t is not None:
+            t = t if (t.is_contiguous() and t.dtype == torch.float32) else t.contiguous().float()
+            keep.append(t)
+        setattr(a, name, None if t is None else t.data_ptr())
+    for i in range(8):
+        a.w[i] = float(w[i])
+    a.dR_accumulate = 1 if prior_b is not None else 0
+    _lib.call('dboa_loss_multi', C.byref(a), stream())
+    return terms, dp2d, dj3d, dR, dbeta
+
+
+def backward_graph(ad, arena, p, dp2d, dj3d, dR, dbeta, grad_arena):
+    """d(loss)/d(p2d, joints, R, beta) -> accumulate d(loss)/d(weights) into ``grad_arena``."""
+    B, dev = p.B, p.rot.device
+    dcam = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    _lib.call('dboa_project_bwd', ptr(p.cam), ptr(p.joints), ptr(dp2d), ptr(dj3d), ptr(dcam), B, 49, 1, 0, stream())
+    scratch = torch.empty(_lib.load().dboa_smpl_scratch_floats(B), dtype=torch.float32, device=dev)
+    _lib.call('dboa_smpl_backward', ad.smpl_neutral._struct_ref(), ptr(p.rot), B, ptr(p.smpl_tape), ptr(dj3d), ptr(scratch), ptr(dR),
+              ptr(dbeta), 1, stream())
+    hmr_mod.raw_backward(arena, p.tape, B, p.masked, dR, dbeta, dcam, grad_arena)
+
+
+def level_backward(ad, arena, buffers, main, kp, lower, grad_arena):
+    """One level of the bilevel problem (reference base_adaptor.py:222-317) on weights ``arena``: evaluates the
+    level's loss on the already computed ``main`` forward (+ history / exemplar forwards) and accumulates its
+    gradient into ``grad_arena``.  Returns the loss as a device scalar."""
+    o = ad.options
+    tag = 'll' if lower else 'ul'
+    image = main.image
+    use_frame = o.use_frame_losses_lower if lower else o.use_frame_losses_upper
+    use_temporal = o.use_temporal_losses_lower if lower else o.use_temporal_losses_upper
+    w = [0.0] * 8
+    targets = {}
+    if use_frame:
+        w[0], w[1], w[2] = o.s2dloss_weight, o.shape_prior_weight, o.pose_prior_weight
+    if use_temporal and o.use_meanteacher:
+        teacher = ad.teacher
+        t = forward_graph(ad, teacher.arena, teacher._buffers, image, teacher._masks(image.shape[0], image.device))
+        tw = o.teacherloss_weight
+        w[3], w[4], w[5], w[6] = 5 * tw, 5 * tw, 0.001 * tw, 1 * tw
+        targets = dict(t_p2d=t.p2d, t_j3d=t.joints, t_beta=t.shape, t_R=t.rot)
+    terms, dp2d, dj3d, dR, dbeta = _loss_head(ad, main, w, kp=kp if use_frame else None, **targets)
+    total = terms[8]
+    if use_frame:
+        ad.fit_losses[f'{tag}/s2dloss'], ad.fit_losses[f'{tag}/shape_prior'], ad.fit_losses[f'{tag}/pose_prior'] = terms[0], terms[1], terms[2]
+        (ad.kp2dlosses_lower.append(terms[0]) if lower else ad.kp2dlosses_upper.__setitem__(ad.global_step, terms[0]))
+    if use_temporal and o.use_motion and (ad.global_step - o.interval) > 0:
+        hist_image, hist_kp = ad.get_hist()
+        h = forward_graph(ad, arena, buffers, hist_image)
+        mterm = torch.empty(1, dtype=torch.float32, device=image.device)
+        dph = torch.empty_like(h.p2d)
+        _lib.call('dboa_loss_motion', ptr(main.p2d), ptr(h.p2d), ptr(kp), ptr(hist_kp.contiguous()), float(o.motionloss_weight), ptr(mterm),
+                  ptr(dp2d), ptr(dph), main.B, 1, stream())
+        z3, zR, zb = torch.zeros_like(h.joints), torch.zeros_like(h.rot), torch.zeros_like(h.shape)
+        backward_graph(ad, arena, h, dph, z3, zR, zb, grad_arena)
+        total = total + mterm[0] * o.motionloss_weight
+        ad.fit_losses['ul/motion_loss'] = mterm[0]
+    backward_graph(ad, arena, main, dp2d, dj3d, dR, dbeta, grad_arena)
+    if o.retrieval:
+        ex = ad.retrieval(hmr_mod._feature_views(main.tape, main.B)[5])
+        if (o.lower_level_mixtrain if lower else o.upper_level_mixtrain):
+            e = forward_graph(ad, arena, buffers, ex['img'])
+            n = e.B
+            gt_R = torch.empty(n, 24, 3, 3, dtype=torch.float32, device=image.device)
+            _lib.call('dboa_rodrigues', ptr(ex['pose'].reshape(-1, 3).contiguous()), ptr(gt_R), n * 24, 0, stream())
+            lw = o.labelloss_weight
+            eterms, a, b, c, d = _loss_head(ad, e, [5 * lw, 0, 0, 0, 0, 0.001 * lw, 1 * lw, 5 * lw], kp=ex['keypoints'], t_beta=ex['betas'],
+                                            t_R=gt_R, gt_s3d=ex['pose_3d'])
+            backward_graph(ad, arena, e, a, b, c, d, grad_arena)
+            total = total + eterms[8]
+            ad.fit_losses[f'{tag}/labled_loss'] = eterms[8]
+    return total
+
+
+def feature_cosines(ad, tape_a, tape_b, B):
+    fa, fb = hmr_mod._feature_views(tape_a, B), hmr_mod._feature_views(tape_b, B)
+    return ad.cal_feature_diff(fa, fb)
+
+
+def fused_adapt(ad, batch):
+    o = ad.options
+    image, kp = batch['image'].contiguous().float(), batch['smpl_j2d'].contiguous().float()
+    ad.save_hist(image, kp)
+    model = getattr(ad.model, 'module', ad.model)
+    theta, buffers = model.arena, model._buffers
+    opt = ad.optimizer
+    G = model.grad_arena()
+    teacher = ad.teacher if o.use_meanteacher else None
+    evaluate = getattr(ad, 'fused_eval', 'final')
+    with torch.no_grad():
+        probe = forward_graph(ad, theta, buffers, image)            # init_features (reference :132-133)
+        if not o.use_boa:
+            G.zero_()
+            ad.last_upper_loss = level_backward(ad, theta, buffers, probe, kp, True, G)
+            opt.step()
+            return ad.inference(batch, ad.model) if evaluate != 'none' else None
+        fast, cur = theta, probe
+        if not hasattr(ad, '_fast_bufs'):
+            ad._fast_bufs = [torch.empty_like(theta), torch.empty_like(theta)]
+            ad._inner_grad = torch.empty_like(theta)
+        for i in range(o.inner_step):
+            if i > 0:
+                cur = forward_graph(ad, fast, buffers, image)
+            ad._inner_grad.zero_()
+            level_backward(ad, fast, buffers, cur, kp, True, ad._inner_grad)
+            nxt = ad._fast_bufs[i % 2]
+            _lib.call('dboa_sgd_update', ptr(fast), ptr(ad._inner_grad), ptr(nxt), float(o.fastlr), theta.numel(), stream())
+            fast = nxt
+            if evaluate == 'all':
+                ad.inference(batch, _ArenaModel(model, fast))
+        upper = forward_graph(ad, fast, buffers, image)
+        G.zero_()
+        ad.last_upper_loss = level_backward(ad, fast, buffers, upper, kp, False, G)
+        opt.step(teacher=teacher, alpha=o.alpha)                    # Adam + EMA teacher, one sweep
+        result = None
+        if evaluate == 'all' or (evaluate == 'final' and not o.dynamic_boa):
+            result = ad.inference(batch, ad.model)
+        if o.dynamic_boa:
+            after = forward_graph(ad, theta, buffers, image)
+            sims = feature_cosines(ad, probe.tape, after.tape, probe.B)
+            ad.feat_sims[ad.global_step] = [sims]
+            steps = 0
+            while 1 - sims[12]['cos'] > o.cos_sim_threshold:
+                steps += 1
+                if steps > o.optim_steps:
+                    break
+                G.zero_()
+                level_backward(ad, theta, buffers, after, kp, False, G)       # 'after' was computed with the current theta
+                opt.step(teacher=teacher, alpha=o.alpha)
+                before, after = after, forward_graph(ad, theta, buffers, image)
+                sims = feature_cosines(ad, before.tape, after.tape, probe.B)
+                ad.feat_sims[ad.global_step].append(sims)
+                if evaluate == 'all':
+                    result = ad.inference(batch, ad.model)
+            ad.optimized_step = steps
+            ad.optim_step_record.append(steps)
+            if evaluate == 'final':
+                result = ad.inference(batch, ad.model)
+        return result
+
+
+class _ArenaModel:
+    """Minimal callable so ``inference`` can evaluate an arbitrary flat weight arena (fast weights)."""
+
+    def __init__(self, model, arena):
+        self.model, self.arena = model, arena
+
+    def eval(self):
+        return self
+
+    def __call__(self, image, need_feature=False):
+        rot, shape, cam, _, tape = hmr_mod.raw_forward(self.arena, self.model._buffers, image)
+        if need_feature:
+            return rot, shape, cam, hmr_mod._feature_views(tape, image.shape[0])
+        return rot, shape, cam

@@ -1,0 +1,146 @@
+/* libdynaboa_b200 -- C ABI of the B200-native DynaBOA hot path.
+ *
+ * The reference (syguan96/DynaBOA) has no FFI/plugin boundary of its own: its hot path is Python
+ * calling stock PyTorch ops.  This header is the boundary the B200 implementation
+ * introduces underneath the reference's Python API; each entry point names the reference code it
+ * replaces.  Conventions:
+ *   - every pointer is a DEVICE pointer to fp32 data unless stated otherwise; buffers are owned by
+ *     the caller (torch-allocated) and must outlive the call;
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and never synchronise;
+ *   - return value: 0 = ok, <0 = error (DBOA_ERR_*); no exceptions cross the ABI;
+ *   - one host thread per device (the reference is single-threaded on this path).
+ * Reference-side binding (ctypes) is shown in INTEGRATION.md.
+ */
+#ifndef DYNABOA_B200_H
+#define DYNABOA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBOA_OK 0
+#define DBOA_ERR_ARG (-1)
+#define DBOA_ERR_SHAPE (-2)
+#define DBOA_ERR_CUDA (-3)
+#define DBOA_ERR_UNSUPPORTED (-4)
+
+typedef void* dboa_stream_t;
+
+/* ---- library state ------------------------------------------------------------------------- */
+const char* dboa_version(void);
+int dboa_last_cuda_error(void);            /* cudaError_t of the last failed launch */
+long long dboa_launch_count(void);         /* kernels launched by this library so far */
+int dboa_set_tensor_core_conv(int enable); /* 1: tcgen05 TF32x3 path for eligible convs (default), 0: fp32 CUDA-core path */
+
+/* ---- HMR regressor: parameter arena and tape layout ----------------------------------------
+ * replaces: model/hmr.py:67-124 (HMR.__init__/_make_layer state_dict contract).
+ * The 169 parameters live in ONE flat fp32 arena; entry i (in nn.Module.parameters() order) is the
+ * strided view (offset, shape, stride) of it.  Conv weights are stored [Cout][kh][kw][Cin]. */
+int dboa_hmr_num_params(void);
+long long dboa_hmr_arena_floats(void);
+int dboa_hmr_param_info(int i, char* name, int name_cap, long long* offset, int* ndim, long long shape[4], long long stride[4]);
+long long dboa_hmr_tape_floats(int B);      /* activations saved by the forward (also holds the features) */
+long long dboa_hmr_scratch_floats(int B);   /* scratch shared by forward (split-K) and backward */
+/* feature i of HMR.forward(need_feature=True) (model/hmr.py:138-168) as a strided view of the tape */
+int dboa_hmr_feature_info(int B, int i, long long* offset, int* ndim, long long shape[4], long long stride[4]);
+
+/* replaces: model/hmr.py:127-181 HMR.forward (+ utils/geometry.py:47-61 rot6d_to_rotmat).
+ * image: (B,3,224,224) NCHW.  drop_masks: NULL (eval) or (3,2,B,1024) keep-masks already scaled by 1/(1-p).
+ * outputs: rotmat (B,24,3,3), shape (B,10), cam (B,3), pose6d (B,144). */
+int dboa_hmr_forward(const float* arena, const float* init_pose, const float* init_shape, const float* init_cam,
+                     const float* image, int B, const float* drop_masks, float* tape, float* scratch,
+                     float* rotmat, float* shape, float* cam, float* pose6d, dboa_stream_t stream);
+/* replaces: autograd backward of the above (torch.autograd.grad in learn2learn MAML.adapt, loss.backward()
+ * at dynaboa_benchmark.py:140,150).  grad_arena is ACCUMULATED into (+=), same layout as the arena. */
+int dboa_hmr_backward(const float* arena, const float* tape, int B, int masked /* forward used drop_masks */,
+                      const float* d_rotmat, const float* d_shape, const float* d_cam, float* grad_arena, float* scratch,
+                      dboa_stream_t stream);
+
+/* ---- single operators (unit-parity surface; same kernels the plan above launches) ----------- */
+/* replaces: nn.Conv2d forward / backward (model/hmr.py:29-34,72,113); NHWC activations, weights [Cout][Kpitch] */
+int dboa_conv2d_fwd(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
+                    int Kpitch, float* ws, long long ws_floats, dboa_stream_t stream);
+int dboa_conv2d_dgrad(const float* dy, const float* w, float* dx, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
+                      int Kpitch, int accumulate, float* ws, long long ws_floats, dboa_stream_t stream);
+int dboa_conv2d_wgrad(const float* dy, const float* x, float* dw, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
+                      int Kpitch, float* ws, long long ws_floats, dboa_stream_t stream);
+/* replaces: nn.GroupNorm(4, C) + ReLU (+ residual) forward / backward (model/hmr.py:14-18,40-60) */
+long long dboa_gn_partial_floats(int B, int HW, int C);
+long long dboa_gn_bwd_partial_floats(int B, int HW, int C);
+int dboa_groupnorm_fwd(const float* y, const float* gamma, const float* beta, const float* residual, float* out, float* stats,
+                       float* partial, int B, int HW, int C, int relu, dboa_stream_t stream);
+int dboa_groupnorm_bwd(const float* dout, const float* mask_src, const float* y, const float* stats, const float* gamma, float* dy,
+                       float* dgamma, float* dbeta, float* partial, int B, int HW, int C, dboa_stream_t stream);
+int dboa_maxpool_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, dboa_stream_t stream);
+int dboa_maxpool_bwd(const float* dy, const unsigned char* idx, float* dx, int B, int H, int W, int C, dboa_stream_t stream);
+
+/* ---- rotations (utils/geometry.py) ---------------------------------------------------------- */
+int dboa_rot6d_fwd(const float* x6, float* R, int n, dboa_stream_t stream);                       /* :47-61 */
+int dboa_rot6d_bwd(const float* x6, const float* dR, float* dx6, int n, dboa_stream_t stream);
+/* kind 0: batch_rodrigues :9-45 (quaternion route); kind 1: smplx lbs.batch_rodrigues (pose2rot=True) */
+int dboa_rodrigues(const float* aa, float* R, int n, int kind, dboa_stream_t stream);
+int dboa_rotmat_to_aa_fwd(const float* R, float* aa, int n, dboa_stream_t stream);              /* :184-306 */
+int dboa_rotmat_to_aa_bwd(const float* R, const float* daa, float* dR, int n, dboa_stream_t stream);
+
+/* ---- SMPL (model/smpl.py:25-37 over smplx lbs) ---------------------------------------------- */
+typedef struct dboa_smpl_model {
+    const float* v_template;   /* (6890,3) */
+    const float* blend_dirs;   /* (217, 20670): rows 0..9 shapedirs as (l, v*3+k), rows 10..216 posedirs */
+    const float* J_template;   /* (24,3)   = J_regressor @ v_template */
+    const float* J_shapedirs;  /* (24,3,10) = J_regressor @ shapedirs */
+    const int* parents;        /* (24,) */
+    const float* lbs_weights;  /* (6890,24) */
+    const float* J_extra;      /* (9,6890) reference config.JOINT_REGRESSOR_TRAIN_EXTRA */
+    const int* joint_map;      /* (49,) into [24 kinematic | 21 vertex picks | 9 extra] */
+    const int* vertex_ids;     /* (21,) smplx vertex_joint_selector picks */
+} dboa_smpl_model;
+long long dboa_smpl_tape_floats(int B);
+long long dboa_smpl_scratch_floats(int B);
+/* betas (B,10), rotmat (B,24,3,3) -> vertices (B,6890,3), joints (B,49,3) */
+int dboa_smpl_forward(const dboa_smpl_model* m, const float* betas, const float* rotmat, int B, float* vertices, float* joints,
+                      float* tape, dboa_stream_t stream);
+/* d(joints) -> d(rotmat), d(betas) (vertices carry no loss on the adaptation path: SURVEY.md Appendix A) */
+int dboa_smpl_backward(const dboa_smpl_model* m, const float* rotmat, int B, const float* tape, const float* d_joints, float* scratch,
+                       float* d_rotmat, float* d_betas, int accumulate, dboa_stream_t stream);
+
+/* ---- projection and losses (base_adaptor.py) ------------------------------------------------ */
+int dboa_project_fwd(const float* cam, const float* j3d, float* p2d, int B, int NJ, dboa_stream_t stream);      /* :160-170 */
+int dboa_project_bwd(const float* cam, const float* j3d, const float* dp2d, float* dj3d, float* dcam, int B, int NJ, int acc_j,
+                     int acc_cam, dboa_stream_t stream);
+/* GMM pose prior (:405-409, utils/smplify/prior.py:181-196): prior_b[b] = min_m NLL; d_rotmat = scale * d prior_b / dR */
+int dboa_pose_prior(const float* rotmat, const float* means, const float* precisions, const float* neg_log_w, float* prior_b,
+                    float* d_rotmat, float scale, int B, dboa_stream_t stream);
+/* MaxMixturePrior.forward(pose, betas) itself (utils/smplify/prior.py:227-231) on a (B,69) axis-angle body pose */
+int dboa_gmm_prior(const float* pose69, const float* means, const float* precisions, const float* neg_log_w, float* prior_b,
+                   float* d_pose, float scale, int B, dboa_stream_t stream);
+typedef struct dboa_loss_args {
+    int B;
+    const float *p2d, *j3d, *R, *beta;      /* predictions: (B,49,2) (B,49,3) (B,24,3,3) (B,10) */
+    const float* kp;                        /* (B,49,3) keypoints + confidence, or NULL */
+    const float* prior_b;                   /* (B,) per-body pose prior values, or NULL */
+    const float *t_p2d, *t_j3d, *t_beta, *t_R; /* consistency / label targets, or NULL each */
+    const float* gt_s3d;                    /* (B,24,4) labelled 3D joints, or NULL (needs kp) */
+    float w[8];                             /* weights: s2d, shape, pose, t_p2d, t_j3d, t_beta, t_R, s3d */
+    float* terms;                           /* (9,) out: the 8 unweighted terms, then the weighted total */
+    float *dp2d, *dj3d, *dR, *dbeta;        /* out: gradients of the weighted total (NULL to skip) */
+    int dR_accumulate;                      /* 1: dR already holds the pose-prior gradient */
+} dboa_loss_args;
+int dboa_loss_multi(const dboa_loss_args* args, dboa_stream_t stream);        /* :234-241,283-291,331-337,360-370,401,412-422 */
+int dboa_loss_motion(const float* p_cur, const float* p_hist, const float* kp_cur, const float* kp_hist, float weight, float* term,
+                     float* dp_cur, float* dp_hist, int B, int accumulate_cur, dboa_stream_t stream);               /* :379-398 */
+
+/* ---- whole-model sweeps, feature test, retrieval -------------------------------------------- */
+int dboa_sgd_update(const float* p, const float* g, float* out, float lr, long long n, dboa_stream_t stream);   /* l2l maml_update */
+int dboa_adam_ema(float* p, const float* g, float* m, float* v, float* teacher /* or NULL */, long long n, float lr, float beta1,
+                  float beta2, float eps, int step, float alpha, dboa_stream_t stream);     /* base_adaptor.py:126,193-201 */
+int dboa_ema_update(float* teacher, const float* p, long long n, float alpha, dboa_stream_t stream);
+/* cal_feature_diff :211-219: cosine similarity of npairs (<=16) flattened tensor pairs; host arrays of device pointers */
+int dboa_cosine_pairs(const float* const* a, const float* const* b, const long long* n, int npairs, float* partial,
+                      long long partial_floats, float* out, float eps, dboa_stream_t stream);
+/* retrieval :82-84: index of the centre with the smallest cosine distance to feat (D,) among centers (K,D) */
+int dboa_retrieval_nearest(const float* feat, const float* centers, int K, int D, int* best, float* dists, dboa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNABOA_B200_H */

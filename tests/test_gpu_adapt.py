@@ -1,0 +1,102 @@
+"""End-to-end bilevel adaptation on the GPU against trajectories recorded from the reference's own
+``BaseAdaptor`` / ``Adaptor`` code (tests/golden/adapt_*.npz, see oracle/make_golden.py): configs C2
+(1 inner step), C3 (3 inner steps + retrieval minibatch) and C5 (dynamic re-adaptation loop)."""
+import ast
+import os
+import random
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def make_options(tmp, golden_options_repr, **extra):
+    o = dict(ast.literal_eval(golden_options_repr))
+    o.update(expdir=str(tmp), expname='run', tensorboard=0, synthetic_frames=8, cache_results=0)
+    o.update(extra)
+    return SimpleNamespace(**o)
+
+
+def build_adaptor(asset_dir, tmp, gd):
+    from dynaboa_b200 import config
+    from dynaboa_b200.adaptor import Adaptor
+    opts = make_options(tmp, str(gd['options']), model_file=config.BASE_MODEL)
+    return Adaptor(opts), opts
+
+
+def run_and_compare(asset_dir, tmp_path, golden, tag, fused):
+    from dynaboa_b200 import synthetic
+    from oracle.make_golden import sample_indices
+    gd = golden(f'adapt_{tag}')
+    ad, opts = build_adaptor(asset_dir, tmp_path, gd)
+    n_frames = gd['upper_loss'].shape[0]
+    stream = synthetic.SyntheticStream(length=n_frames, batch_size=opts.batch_size)
+    names = [str(s) for s in gd['param_names']]
+    masks_all = torch.from_numpy(gd['teacher_masks']).float()
+    n_outer = 0
+    for t in range(n_frames):
+        batch = {k: v.cuda() if torch.is_tensor(v) else v for k, v in stream[t].items()}
+        random.seed(1000 + t)
+        calls = {'i': 0}
+
+        def provider(B, dev, t=t, calls=calls):
+            m = masks_all[t, min(calls['i'], masks_all.shape[1] - 1)]
+            calls['i'] += 1
+            return m.to(dev)
+        ad.teacher.mask_provider = provider
+        ad.global_step, ad.fit_losses = t, {}
+        ad.model.eval()
+        mpjpe, pampjpe, pve = ad.adapt(batch) if fused else ad.adaptation(batch)
+        dyn = int(gd['dyn_steps'][t])
+        n_outer += 1 + min(dyn, opts.optim_steps)
+        tol = 2e-4 if t == 0 else 1e-3
+        assert abs(float(ad.last_upper_loss) - gd['upper_loss'][t]) <= tol * abs(gd['upper_loss'][t]) or dyn > 0, (tag, t)
+        pred = ad.predict(batch['image'])
+        assert rel_err(pred['rotmat'], gd['rotmat'][t]) < 1e-3, (tag, t)
+        assert rel_err(pred['betas'], gd['betas'][t]) < 1e-3 and rel_err(pred['cam'], gd['cam'][t]) < 1e-3, (tag, t)
+        assert rel_err(pred['joints'], gd['joints'][t]) < 1e-3, (tag, t)
+        assert rel_err(pred['vertices'][:, ::10], gd['verts_sub'][t]) < 1e-3, (tag, t)
+        assert abs(np.mean(mpjpe) - gd['metrics'][t][0].mean()) <= 1e-3 * gd['metrics'][t][0].mean(), (tag, t)
+        assert abs(np.mean(pampjpe) - gd['metrics'][t][1].mean()) <= 2e-3 * gd['metrics'][t][1].mean(), (tag, t)
+        if 'cos12' in gd and opts.dynamic_boa:
+            assert ad.optim_step_record[-1] == dyn, (tag, t)
+        params = dict(ad.model.module.named_parameters())
+        bound = 4 * opts.lr * n_outer
+        gnorm = gd['grad_norms'][t]
+        bad = 0
+        for i, name in enumerate(names):
+            p = params[name]
+            idx = sample_indices(name, p.numel())
+            th = p.detach().contiguous().flatten()[idx].double().cpu().numpy()
+            assert np.abs(th - gd['theta_samples'][t][i]).max() <= bound, (tag, t, name)
+            if t == 0 and not fused or t == 0:
+                gs = ad.optimizer.model.grad_arena()
+                gr = p.grad.contiguous().flatten()[idx].double().cpu().numpy()
+                scale = max(gnorm[i] / p.numel() ** 0.5, 1e-12)
+                if np.abs(gr - gd['grad_samples'][t][i]).max() > 2e-3 * max(scale, np.abs(gd['grad_samples'][t][i]).max()):
+                    bad += 1
+        assert bad <= 2, (tag, t, f'{bad} tensors with outer-gradient samples off')
+    return ad
+
+
+@pytest.mark.parametrize('tag', ['c2', 'c3', 'c5'])
+def test_autograd_path_follows_reference_trajectory(asset_dir, tmp_path, golden, tag):
+    run_and_compare(asset_dir, tmp_path, golden, tag, fused=False)
+
+
+@pytest.mark.parametrize('tag', ['c2', 'c3', 'c5'])
+def test_fused_path_follows_reference_trajectory(asset_dir, tmp_path, golden, tag):
+    run_and_compare(asset_dir, tmp_path, golden, tag, fused=True)
+
+
+def test_excute_loop_runs(asset_dir, tmp_path, golden):
+    gd = golden('adapt_c2')
+    ad, _ = build_adaptor(asset_dir, tmp_path, gd)
+    ad.teacher.eval()
+    out = ad.excute(max_frames=3)
+    assert np.isfinite(out['mpjpe']) and np.isfinite(out['pampjpe']) and os.path.exists(os.path.join(ad.exppath, 'res.txt'))

@@ -1,0 +1,139 @@
+"""HMR regressor on the GPU against the golden vectors produced by the reference's own model/hmr.py
+(tests/golden/hmr_forward.npz) and against the oracle: forward, features, backward, state_dict contract,
+MAML clone/adapt semantics."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def model():
+    from dynaboa_b200 import synthetic
+    from dynaboa_b200.hmr import hmr
+    from oracle import hmr_ref
+    m = hmr(synthetic.make_mean_params()).cuda()
+    sd = hmr_ref.strip_prefix(synthetic.make_basemodel()['model'])
+    missing = m.load_state_dict(sd, strict=True)
+    m.eval()
+    return m, sd
+
+
+def golden_input():
+    g = torch.Generator().manual_seed(24)
+    return torch.randn(2, 3, 224, 224, generator=g)
+
+
+def test_state_dict_contract(model):
+    from dynaboa_b200 import layout
+    m, sd = model
+    keys = list(m.state_dict().keys())
+    assert set(keys) == set(layout.param_shapes()) | set(layout.buffer_shapes())
+    assert [n for n, _ in m.named_parameters()] == list(layout.param_shapes())
+    for k, v in m.state_dict().items():
+        assert torch.equal(v.cpu().contiguous(), sd[k]), k
+    assert sum(p.numel() for p in m.parameters()) == 26977501
+
+
+def test_forward_matches_reference_golden(model, golden):
+    m, _ = model
+    gd = golden('hmr_forward')
+    with torch.no_grad():
+        rot, shape, cam, feats = m(golden_input().cuda(), need_feature=True)
+    assert rel_err(rot, gd['rotmat']) < 1e-4 and rel_err(shape, gd['shape']) < 1e-4 and rel_err(cam, gd['cam']) < 1e-4
+    assert len(feats) == 15
+    shapes = [(2, 64, 112, 112), (2, 256, 56, 56), (2, 512, 28, 28), (2, 1024, 14, 14), (2, 2048, 7, 7), (2, 2048)] + [(2, 1024)] * 9
+    for i, f in enumerate(feats):
+        assert tuple(f.shape) == shapes[i]
+        fc = f.contiguous().double().cpu()
+        ref_sum, ref_abs = gd['feat_digest'][i]
+        assert abs(fc.abs().sum().item() - ref_abs) <= 1e-4 * ref_abs, i
+        assert abs(fc.sum().item() - ref_sum) <= 1e-4 * ref_abs, i
+        assert rel_err(fc.flatten()[:32], gd['feat_head'][i]) < 2e-4 or np.abs(gd['feat_head'][i]).max() < 1e-3, i
+    for i in range(5, 15):
+        assert rel_err(feats[i], gd[f'feat{i}']) < 1e-4, i
+
+
+def test_backward_matches_reference_golden(model, golden):
+    m, _ = model
+    gd = golden('hmr_forward')
+    x = golden_input()[:1].cuda()
+    for p in m.parameters():
+        p.grad = None
+    object.__setattr__(m, '_grad_arena', None)
+    rot, shape, cam = m(x)
+    loss = (rot * torch.from_numpy(gd['w_r']).cuda()).sum() + (shape * torch.from_numpy(gd['w_s']).cuda()).sum() \
+        + (cam * torch.from_numpy(gd['w_c']).cuda()).sum()
+    loss.backward()
+    params = dict(m.named_parameters())
+    for key in gd:
+        if not key.startswith('grad_'):
+            continue
+        name = key[5:]
+        g = params[name].grad.contiguous().flatten().double().cpu()
+        ref_norm, ref_head = gd[key][0], gd[key][1:]
+        assert abs(g.norm().item() - ref_norm) <= 1e-3 * ref_norm, name
+        assert (g[:64] - torch.from_numpy(ref_head)).abs().max().item() <= 1e-3 * max(np.abs(ref_head).max(), ref_norm / g.numel() ** 0.5), name
+
+
+def test_batch_invariance_and_determinism(model):
+    m, _ = model
+    x = golden_input().cuda()
+    with torch.no_grad():
+        a = m(x)
+        b = m(x)
+        c0, c1 = m(x[:1]), m(x[1:])
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    for k in range(3):
+        assert rel_err(torch.cat([c0[k], c1[k]]), a[k]) < 1e-5
+
+
+def test_teacher_dropout_masks(model):
+    from oracle import hmr_ref
+    m, sd = model
+    x = golden_input()[:1]
+    g = torch.Generator().manual_seed(5)
+    masks = (torch.rand(3, 2, 1, 1024, generator=g) >= 0.5).float() * 2
+    m.train()
+    m.mask_provider = lambda B, dev: masks.to(dev)
+    try:
+        with torch.no_grad():
+            rot, shape, cam = m(x.cuda())
+    finally:
+        m.eval()
+        m.mask_provider = None
+    ref = hmr_ref.forward(x, sd, masks=[(masks[i, 0], masks[i, 1]) for i in range(3)])
+    assert rel_err(rot, ref[0]) < 1e-4 and rel_err(cam, ref[2]) < 1e-4
+
+
+def test_maml_clone_adapt_first_order(model):
+    from dynaboa_b200.maml import MAML
+    m, sd = model
+    maml = MAML(m, lr=8e-6, first_order=True)
+    assert all(k.startswith('module.') for k in maml.state_dict())
+    x = golden_input()[:1].cuda()
+    for p in m.parameters():
+        p.grad = None
+    object.__setattr__(m, '_grad_arena', None)
+    learner = maml.clone()
+    theta0 = m.arena.clone()
+    rot, shape, cam = learner(x)
+    inner = (rot ** 2).sum() + (shape ** 2).sum() + cam.sum()
+    (g_inner,) = torch.autograd.grad(inner, [learner.module._fast], retain_graph=True)
+    learner.adapt(inner)
+    fast = learner.module._fast
+    assert torch.equal(fast.detach(), theta0 + (-8e-6 * g_inner))          # p + (-lr * g), elementwise exact
+    assert torch.equal(m.arena, theta0)                                     # the original weights are untouched
+    rot2, shape2, cam2 = learner(x)
+    outer = rot2.sum() + (shape2 * 3).sum() + (cam2 ** 2).sum()
+    outer.backward()
+    # first-order: d outer / d theta == d outer / d fast (identity adjoint of the inner update)
+    (g_fast,) = torch.autograd.grad((lambda r: r[0].sum() + (r[1] * 3).sum() + (r[2] ** 2).sum())(learner(x)), [fast])
+    got = torch.cat([p.grad.contiguous().flatten() for p in m.parameters()])
+    from dynaboa_b200.hmr import layout
+    want = torch.cat([v.contiguous().flatten() for v in layout().views(g_fast)])
+    assert rel_err(got, want) < 1e-6
