@@ -105,9 +105,32 @@ def build_oracle(workload, n_frames):
     return ora, synthetic.SyntheticStream(length=n_frames, batch_size=1)
 
 
+def pick_threads():
+    """Thread count for the CPU arm: the fastest of a few candidates on a short HMR forward+backward probe
+    (a 128-thread oneDNN pool on a shared box can be slower than 32 threads)."""
+    from dynaboa_b200 import synthetic
+    from oracle import hmr_ref
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    sd = {k: v.clone().requires_grad_(v.dim() > 0 and 'init_' not in k) for k, v in hmr_ref.strip_prefix(synthetic.make_basemodel()['model']).items()}
+    x = torch.randn(1, 3, 224, 224)
+    best = (float('inf'), 1)
+    for n in sorted({min(c, avail) for c in (8, 16, 32, 64, avail)}):
+        torch.set_num_threads(n)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            r, s_, c = hmr_ref.forward(x, sd)
+            (r.sum() + s_.sum() + c.sum()).backward()
+            ts.append(time.perf_counter() - t0)
+        sys.stderr.write(f'[bench] cpu probe: {n} threads -> {min(ts) * 1e3:.0f} ms fwd+bwd\n')
+        best = min(best, (min(ts), n))
+    torch.set_num_threads(best[1])
+    return best[1]
+
+
 def time_oracle(workload, steps, warmup):
-    """Reference CPU path (oracle port), S-adapt scope, all host threads.  Returns frames/s (median-based)."""
-    torch.set_num_threads(os.cpu_count())
+    """Reference CPU path (oracle port), S-adapt scope, best host thread count.  Returns frames/s (median-based)."""
+    pick_threads()
     PRELUDE = 7
     warmup = warmup + PRELUDE
     ora, stream = build_oracle(workload, steps + warmup)
@@ -118,6 +141,7 @@ def time_oracle(workload, steps, warmup):
         ora.adaptation(stream[t], with_inference=False)
         ora.predict(stream[t]['image'])
         dt = time.perf_counter() - t0
+        sys.stderr.write(f'[bench] cpu frame {t}: {dt:.2f} s\n')
         if t >= warmup:
             times.append(dt)
     return 1.0 / float(np.median(times)), float(np.sum(times))
@@ -222,7 +246,9 @@ def run_ours(args, rank, world, local):
         ad.model.module.arena.copy_(snapshot[0]); ad.teacher.arena.copy_(snapshot[1])
         ad.optimizer.m.zero_(); ad.optimizer.v.zero_(); ad.optimizer.step_count = 0
 
+    sys.stderr.write('[bench] setup done\n')
     ms_dev, launches, clocks = timed(False)
+    sys.stderr.write(f'[bench] device-resident: {ms_dev / args.steps:.2f} ms/frame\n')
     restore()
     ms_e2e, _, clocks_e2e = timed(True)
     value = world * args.steps / (ms_dev / 1000.0)

@@ -23,6 +23,7 @@ from .pose_utils import compute_similarity_transform_batch
 class Adaptor(BaseAdaptor):
     def __init__(self, options):
         super().__init__(options)
+        self.model.eval()        # the reference driver does this before every frame (dynaboa_benchmark.py:89)
         self.reset_records()
 
     def reset_records(self):

@@ -81,6 +81,7 @@ def run_and_compare(asset_dir, tmp_path, golden, tag, fused):
                 if np.abs(gr - gd['grad_samples'][t][i]).max() > 2e-3 * max(scale, np.abs(gd['grad_samples'][t][i]).max()):
                     bad += 1
         assert bad <= 2, (tag, t, f'{bad} tensors with outer-gradient samples off')
+        print(f'[{tag}{"/fused" if fused else ""}] frame {t}: upper {float(ad.last_upper_loss):.6f} (golden {gd["upper_loss"][t]:.6f})')
     return ad
 
 

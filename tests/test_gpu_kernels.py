@@ -98,16 +98,17 @@ def test_groupnorm_fwd_bwd(L, shape, with_res):
     HW = H * H
     yd = dev(y.permute(0, 2, 3, 1))
     resd = dev(res.permute(0, 2, 3, 1)) if with_res else None
+    gammad, betad, doutd = dev(gamma), dev(beta), dev(dout.permute(0, 2, 3, 1))
     outd = torch.empty_like(yd)
     stats = torch.empty(B * 8, device='cuda')
     part = torch.empty(L.load().dboa_gn_partial_floats(B, HW, Cc), device='cuda')
-    L.call('dboa_groupnorm_fwd', L.ptr(yd), L.ptr(dev(gamma)), L.ptr(dev(beta)), L.ptr(resd), L.ptr(outd), L.ptr(stats), L.ptr(part),
+    L.call('dboa_groupnorm_fwd', L.ptr(yd), L.ptr(gammad), L.ptr(betad), L.ptr(resd), L.ptr(outd), L.ptr(stats), L.ptr(part),
            B, HW, Cc, 1, L.stream())
     assert rel_err(outd.permute(0, 3, 1, 2), out.detach()) < 2e-5
     dyd = torch.empty_like(yd)
     dgam, dbet = torch.ones(Cc, device='cuda'), torch.ones(Cc, device='cuda')       # accumulate semantics
     bpart = torch.empty(L.load().dboa_gn_bwd_partial_floats(B, HW, Cc), device='cuda')
-    L.call('dboa_groupnorm_bwd', L.ptr(dev(dout.permute(0, 2, 3, 1))), L.ptr(outd), L.ptr(yd), L.ptr(stats), L.ptr(dev(gamma)),
+    L.call('dboa_groupnorm_bwd', L.ptr(doutd), L.ptr(outd), L.ptr(yd), L.ptr(stats), L.ptr(gammad),
            L.ptr(dyd), L.ptr(dgam), L.ptr(dbet), L.ptr(bpart), B, HW, Cc, L.stream())
     assert rel_err(dyd.permute(0, 3, 1, 2), yr.grad) < 1e-4
     assert rel_err(dgam.cpu() - 1, gr.grad) < 1e-4 and rel_err(dbet.cpu() - 1, br.grad) < 1e-4
@@ -126,7 +127,8 @@ def test_maxpool(L):
     L.call('dboa_maxpool_fwd', L.ptr(xd), L.ptr(yd), L.ptr(idx), 2, 112, 112, 64, L.stream())
     assert torch.equal(yd.permute(0, 3, 1, 2).cpu(), y.detach())
     dxd = torch.empty_like(xd)
-    L.call('dboa_maxpool_bwd', L.ptr(dev(dy.permute(0, 2, 3, 1))), L.ptr(idx), L.ptr(dxd), 2, 112, 112, 64, L.stream())
+    dyd = dev(dy.permute(0, 2, 3, 1))
+    L.call('dboa_maxpool_bwd', L.ptr(dyd), L.ptr(idx), L.ptr(dxd), 2, 112, 112, 64, L.stream())
     # ties only occur between zeros, whose gradient the preceding ReLU discards: compare where x > 0
     m = (x > 0)
     assert rel_err(dxd.permute(0, 3, 1, 2).cpu() * m, xr.grad * m) < 1e-6
@@ -135,23 +137,26 @@ def test_maxpool(L):
 def test_rotations_against_golden(L, golden):
     gd = golden('geometry')
     x6 = torch.from_numpy(gd['rot6d_in'])
+    x6d = dev(x6)
     R = torch.empty(x6.shape[0], 3, 3, device='cuda')
-    L.call('dboa_rot6d_fwd', L.ptr(dev(x6)), L.ptr(R), x6.shape[0], L.stream())
+    L.call('dboa_rot6d_fwd', L.ptr(x6d), L.ptr(R), x6.shape[0], L.stream())
     assert rel_err(R, gd['rot6d_out']) < 1e-6
     aa = torch.from_numpy(gd['rodrigues_in'])
     R = torch.empty(aa.shape[0], 3, 3, device='cuda')
-    L.call('dboa_rodrigues', L.ptr(dev(aa)), L.ptr(R), aa.shape[0], 0, L.stream())
+    aad = dev(aa)
+    L.call('dboa_rodrigues', L.ptr(aad), L.ptr(R), aa.shape[0], 0, L.stream())
     assert rel_err(R, gd['rodrigues_out']) < 2e-6
     Rin = torch.from_numpy(gd['r2aa_in'])
     out = torch.empty(Rin.shape[0], 3, device='cuda')
-    L.call('dboa_rotmat_to_aa_fwd', L.ptr(dev(Rin)), L.ptr(out), Rin.shape[0], L.stream())
+    Rind, wd = dev(Rin), dev(torch.from_numpy(gd['r2aa_w']))
+    L.call('dboa_rotmat_to_aa_fwd', L.ptr(Rind), L.ptr(out), Rin.shape[0], L.stream())
     assert rel_err(out, gd['r2aa_out']) < 2e-6
     dR = torch.empty(Rin.shape[0], 3, 3, device='cuda')
-    L.call('dboa_rotmat_to_aa_bwd', L.ptr(dev(Rin)), L.ptr(dev(torch.from_numpy(gd['r2aa_w']))), L.ptr(dR), Rin.shape[0], L.stream())
+    L.call('dboa_rotmat_to_aa_bwd', L.ptr(Rind), L.ptr(wd), L.ptr(dR), Rin.shape[0], L.stream())
     assert rel_err(dR, gd['r2aa_grad']) < 1e-5
     p = torch.empty(4, 49, 2, device='cuda')
-    L.call('dboa_project_fwd', L.ptr(dev(torch.from_numpy(gd['proj_cam']))), L.ptr(dev(torch.from_numpy(gd['proj_pts']))), L.ptr(p), 4, 49,
-           L.stream())
+    camd, ptsd = dev(torch.from_numpy(gd['proj_cam'])), dev(torch.from_numpy(gd['proj_pts']))
+    L.call('dboa_project_fwd', L.ptr(camd), L.ptr(ptsd), L.ptr(p), 4, 49, L.stream())
     assert rel_err(p, gd['proj_out']) < 1e-6
 
 
@@ -291,7 +296,8 @@ def test_sweeps_match_torch_optimisers(L):
     grad[:1000] = 0
     # inner SGD step: p + (-lr * g)
     out = torch.empty(n, device='cuda')
-    L.call('dboa_sgd_update', L.ptr(dev(p0)), L.ptr(dev(grad)), L.ptr(out), 8e-6, n, L.stream())
+    p0d, gradd = dev(p0), dev(grad)
+    L.call('dboa_sgd_update', L.ptr(p0d), L.ptr(gradd), L.ptr(out), 8e-6, n, L.stream())
     assert torch.equal(out.cpu(), p0 + (-8e-6 * grad))
     # Adam(lr 3e-6, betas (0.5, 0.9)) x 3 steps + EMA teacher, against torch.optim.Adam on CPU
     pc = p0.clone().requires_grad_(True)
@@ -303,7 +309,8 @@ def test_sweeps_match_torch_optimisers(L):
         pc.grad = gstep.clone()
         opt.step()
         teacher_c.mul_(0.1).add_(pc.data, alpha=0.9)
-        L.call('dboa_adam_ema', L.ptr(pd), L.ptr(dev(gstep)), L.ptr(m), L.ptr(v), L.ptr(td), n, 3e-6, 0.5, 0.9, 1e-8, step, 0.1, L.stream())
+        gstepd = dev(gstep)
+        L.call('dboa_adam_ema', L.ptr(pd), L.ptr(gstepd), L.ptr(m), L.ptr(v), L.ptr(td), n, 3e-6, 0.5, 0.9, 1e-8, step, 0.1, L.stream())
     assert (pd.cpu() - pc.data).abs().max().item() < 1e-9 + 1e-7 * pc.data.abs().max().item()
     assert (td.cpu() - teacher_c).abs().max().item() < 1e-9 + 1e-7 * teacher_c.abs().max().item()
     t2 = dev(p0)
@@ -331,7 +338,8 @@ def test_cosine_and_retrieval(L):
     centers[6] = feat * 1.3 + 0.01 * torch.rand(2048, generator=g)
     best = torch.zeros(1, dtype=torch.int32, device='cuda')
     d = torch.zeros(10, device='cuda')
-    L.call('dboa_retrieval_nearest', L.ptr(dev(feat)), L.ptr(dev(centers)), 10, 2048, L.ptr(best), L.ptr(d), L.stream())
+    featd, centersd = dev(feat), dev(centers)
+    L.call('dboa_retrieval_nearest', L.ptr(featd), L.ptr(centersd), 10, 2048, L.ptr(best), L.ptr(d), L.stream())
     refd = 1 - F.cosine_similarity(feat.unsqueeze(0), centers)
     assert int(best.item()) == int(torch.argsort(refd)[0]) == 6
     assert rel_err(d, refd) < 1e-5
