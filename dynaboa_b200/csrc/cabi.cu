@@ -53,7 +53,7 @@ extern "C" {
 const char* dboa_version(void) { return "dynaboa_b200 0.1 (sm_100a)"; }
 int dboa_last_cuda_error(void) { return g_last_cuda_error; }
 long long dboa_launch_count(void) { return g_launch_count; }
-int dboa_set_tensor_core_conv(int enable) { conv_tc_set_enabled(enable != 0); return DBOA_OK; }
+int dboa_set_tensor_core_conv(int enable) { conv_tc_set_mode(enable); return DBOA_OK; }
 
 int dboa_hmr_num_params(void) { return hmr_num_params(); }
 long long dboa_hmr_arena_floats(void) { return hmr_arena_floats(); }
@@ -93,6 +93,12 @@ int dboa_conv2d_wgrad(const float* dy, const float* x, float* dw, int B, int Hi,
                       int Kpitch, float* ws, long long ws_floats, dboa_stream_t stream) {
     if (!dy || !x || !dw) return DBOA_ERR_ARG;
     return conv_wgrad(dy, x, dw, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), ws, ws ? (size_t)ws_floats : 0, ST(stream));
+}
+int dboa_conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin, int Cout, float* ws, long long ws_floats,
+                        dboa_stream_t stream) {
+    if (!x || !w || !y) return DBOA_ERR_ARG;
+    conv_tc_set_workspace(ws, ws ? (size_t)ws_floats : 0);
+    return conv1x1_tc_fwd(x, w, y, M, Cin, Cout, ST(stream));
 }
 long long dboa_gn_partial_floats(int B, int HW, int C) { return (long long)gn_partial_floats(B, HW, C); }
 long long dboa_gn_bwd_partial_floats(int B, int HW, int C) { return (long long)gn_bwd_partial_floats(B, HW, C); }

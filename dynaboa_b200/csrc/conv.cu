@@ -260,6 +260,12 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
     reinterpret_cast<float4*>(out)[i] = s;
 }
 
+int splitk_reduce(const float* part, float* out, size_t n, int nsplit, int accumulate, cudaStream_t st) {
+    size_t n4 = n / 4;
+    splitk_reduce_kernel<<<ceil_div(n4, 256), 256, 0, st>>>(part, out, n4, nsplit, accumulate);
+    return check_launch();
+}
+
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------

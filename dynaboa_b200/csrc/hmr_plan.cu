@@ -275,6 +275,7 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
         return gn_apply(T + t.conv[ci].y, T + t.conv[ci].part, P + c.g_off, P + c.b_off, T + t.conv[ci].stats, res, nullptr, nullptr,
                         nullptr, nullptr, nullptr, out, B, HW, c.cout, relu, st);
     };
+    conv_tc_set_workspace(sc.ws, (size_t)kConvWs);
     DBOA_TRY(nchw_to_nhwc(image, T + t.x0, B, 3, 224, 224, st));
     DBOA_TRY(conv_forward(n.convs[0], B, T + t.x0, P + n.convs[0].w_off, T + t.conv[0].y, sc.ws, st));
     DBOA_TRY(gn_plain(0, T + t.conv[0].a, 1, nullptr));

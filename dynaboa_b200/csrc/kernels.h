@@ -19,6 +19,9 @@ int conv_wgrad(const float* dy, const float* x, float* dw, const ConvDims& d, fl
 int conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin, int Cout, cudaStream_t st);
 bool conv_tc_enabled();
 void conv_tc_set_enabled(bool on);
+void conv_tc_set_mode(int mode);                      // 0 off, 1 on, 2 on with LBO/SBO swapped (bring-up aid)
+void conv_tc_set_workspace(float* ws, size_t floats);
+int splitk_reduce(const float* part, float* out, size_t n, int nsplit, int accumulate, cudaStream_t st);
 
 // ---- norm_pool.cu
 int gn_chunks(int HW, int C);                       // number of row chunks the statistics kernels use

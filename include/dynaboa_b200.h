@@ -64,6 +64,10 @@ int dboa_conv2d_dgrad(const float* dy, const float* w, float* dx, int B, int Hi,
                       int Kpitch, int accumulate, float* ws, long long ws_floats, dboa_stream_t stream);
 int dboa_conv2d_wgrad(const float* dy, const float* x, float* dw, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
                       int Kpitch, float* ws, long long ws_floats, dboa_stream_t stream);
+/* 1x1 / stride-1 convolution as a tcgen05 TF32x3 GEMM: y[M][Cout] = x[M][Cin] * w[Cout][Cin]^T (fp32-accurate);
+ * needs dboa_set_tensor_core_conv(1); returns DBOA_ERR_UNSUPPORTED for shapes it does not take (Cin % 32, Cout % 64) */
+int dboa_conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin, int Cout, float* ws, long long ws_floats,
+                        dboa_stream_t stream);
 /* replaces: nn.GroupNorm(4, C) + ReLU (+ residual) forward / backward (model/hmr.py:14-18,40-60) */
 long long dboa_gn_partial_floats(int B, int HW, int C);
 long long dboa_gn_bwd_partial_floats(int B, int HW, int C);

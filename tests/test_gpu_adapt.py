@@ -74,12 +74,13 @@ def run_and_compare(asset_dir, tmp_path, golden, tag, fused):
             idx = sample_indices(name, p.numel())
             th = p.detach().contiguous().flatten()[idx].double().cpu().numpy()
             assert np.abs(th - gd['theta_samples'][t][i]).max() <= bound, (tag, t, name)
-            if t == 0 and not fused or t == 0:
-                gs = ad.optimizer.model.grad_arena()
+            if t == 0 and not opts.dynamic_boa:     # one outer step from identical weights: the sensitive gradient check
                 gr = p.grad.contiguous().flatten()[idx].double().cpu().numpy()
                 scale = max(gnorm[i] / p.numel() ** 0.5, 1e-12)
-                if np.abs(gr - gd['grad_samples'][t][i]).max() > 2e-3 * max(scale, np.abs(gd['grad_samples'][t][i]).max()):
+                err = np.abs(gr - gd['grad_samples'][t][i]).max()
+                if err > 2e-3 * max(scale, np.abs(gd['grad_samples'][t][i]).max()):
                     bad += 1
+                    print(f'  grad off: {name} err {err:.3e} rms {scale:.3e} golden-max {np.abs(gd["grad_samples"][t][i]).max():.3e}')
         assert bad <= 2, (tag, t, f'{bad} tensors with outer-gradient samples off')
         print(f'[{tag}{"/fused" if fused else ""}] frame {t}: upper {float(ad.last_upper_loss):.6f} (golden {gd["upper_loss"][t]:.6f})')
     return ad

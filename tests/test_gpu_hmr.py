@@ -79,6 +79,33 @@ def test_backward_matches_reference_golden(model, golden):
         assert (g[:64] - torch.from_numpy(ref_head)).abs().max().item() <= 1e-3 * max(np.abs(ref_head).max(), ref_norm / g.numel() ** 0.5), name
 
 
+@pytest.mark.parametrize('B', [1, 2, 3])
+def test_full_gradient_matches_oracle_autograd(model, B):
+    """Every one of the 169 gradient tensors against torch autograd of the oracle on the CPU, batch 1..3."""
+    from oracle import hmr_ref
+    m, sd = model
+    g = torch.Generator().manual_seed(77 + B)
+    x = torch.randn(B, 3, 224, 224, generator=g)
+    w_r, w_s, w_c = torch.randn(B, 24, 3, 3, generator=g), torch.randn(B, 10, generator=g), torch.randn(B, 3, generator=g)
+    pc = {k: v.clone().requires_grad_(True) for k, v in sd.items() if not k.startswith('init_')}
+    full = dict(pc)
+    full.update({k: sd[k] for k in ('init_pose', 'init_shape', 'init_cam')})
+    r, s_, c = hmr_ref.forward(x, full)
+    ((r * w_r).sum() + (s_ * w_s).sum() + (c * w_c).sum()).backward()
+    for p in m.parameters():
+        p.grad = None
+    object.__setattr__(m, '_grad_arena', None)
+    rot, shape, cam = m(x.cuda())
+    ((rot * w_r.cuda()).sum() + (shape * w_s.cuda()).sum() + (cam * w_c.cuda()).sum()).backward()
+    worst = []
+    for name, p in m.named_parameters():
+        ref = pc[name].grad
+        worst.append((rel_err(p.grad.contiguous(), ref), name))
+    worst.sort(reverse=True)
+    print(f'B={B} worst gradient tensors:', [(f'{e:.1e}', n) for e, n in worst[:5]])
+    assert worst[0][0] < 5e-4, worst[:8]
+
+
 def test_batch_invariance_and_determinism(model):
     m, _ = model
     x = golden_input().cuda()
