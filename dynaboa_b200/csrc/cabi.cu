@@ -105,13 +105,12 @@ long long dboa_gn_bwd_partial_floats(int B, int HW, int C) { return (long long)g
 int dboa_groupnorm_fwd(const float* y, const float* gamma, const float* beta, const float* residual, float* out, float* stats, float* partial,
                        int B, int HW, int C, int relu, dboa_stream_t stream) {
     if (!y || !gamma || !beta || !out || !stats || !partial) return DBOA_ERR_ARG;
-    DBOA_TRY(gn_stats(y, B, HW, C, partial, ST(stream)));
-    return gn_apply(y, partial, gamma, beta, stats, residual, nullptr, nullptr, nullptr, nullptr, nullptr, out, B, HW, C, relu, ST(stream));
+    return gn_fwd_fused(y, gamma, beta, residual, out, stats, partial, B, HW, C, relu, ST(stream));
 }
 int dboa_groupnorm_bwd(const float* dout, const float* mask_src, const float* y, const float* stats, const float* gamma, float* dy,
                        float* dgamma, float* dbeta, float* partial, int B, int HW, int C, dboa_stream_t stream) {
     if (!dout || !y || !stats || !gamma || !dy || !dgamma || !dbeta || !partial) return DBOA_ERR_ARG;
-    return gn_bwd(dout, mask_src, y, stats, gamma, dy, dgamma, dbeta, partial, B, HW, C, ST(stream));
+    return gn_bwd_fused(dout, mask_src, y, stats, gamma, dy, dgamma, dbeta, partial, B, HW, C, ST(stream));
 }
 int dboa_maxpool_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, dboa_stream_t stream) {
     if (!x || !y || !idx || (H & 1) || (W & 1) || (C & 3)) return DBOA_ERR_ARG;

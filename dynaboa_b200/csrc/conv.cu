@@ -30,13 +30,73 @@ __device__ __forceinline__ void mma_slab(const float (*As)[BM + PADM], const flo
     }
 }
 
+// Split-K fix-up inside the kernel: every z-slice stores its partial tile, takes a ticket, and the LAST slice to
+// arrive sums the partials in the fixed order z = 0..nz-1 (deterministic) and writes the final tile.
+__device__ __forceinline__ bool splitk_last_arriver(unsigned* counters) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned tile = blockIdx.y * gridDim.x + blockIdx.x;
+        const unsigned t = atomicAdd(&counters[tile], 1u);
+        s_last = (t == gridDim.z - 1);
+        if (s_last) counters[tile] = 0;          // self-resetting: every other slice of this tile has already arrived
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+// rows x 4-float epilogue of a [M][ld] row-major output (forward / data gradient)
+__device__ __forceinline__ void store_rows(const float acc[4][4], float* __restrict__ final_out, float* __restrict__ ws,
+                                           unsigned* counters, int M, int ld, int m0, int n0, int tx, int ty, int accumulate) {
+    const int nz = gridDim.z;
+    if (nz == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int mm = m0 + ty * 4 + i;
+            if (mm < M) {
+                float4* p = reinterpret_cast<float4*>(final_out + (size_t)mm * ld + n0 + tx * 4);
+                float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                if (accumulate) { float4 c = *p; v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w; }
+                *p = v;
+            }
+        }
+        return;
+    }
+    const size_t slab = (size_t)M * ld;
+    float* mine = ws + (size_t)blockIdx.z * slab;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int mm = m0 + ty * 4 + i;
+        if (mm < M)
+            *reinterpret_cast<float4*>(mine + (size_t)mm * ld + n0 + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+    if (!splitk_last_arriver(counters)) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int mm = m0 + ty * 4 + i;
+        if (mm < M) {
+            const size_t off = (size_t)mm * ld + n0 + tx * 4;
+            float4* p = reinterpret_cast<float4*>(final_out + off);
+            float4 sacc = accumulate ? *p : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int z = 0; z < nz; ++z) {
+                float4 v = __ldcg(reinterpret_cast<const float4*>(ws + (size_t)z * slab + off));
+                sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w;
+            }
+            *p = sacc;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward:  y[m][n] = sum_k xcol[m][k] * w[n][k],   m = (b,ho,wo), k = (r,s,ci)
 // grid (ceil(M/64), Cout/64, nsplit); each z-slice covers k in [z*klen, (z+1)*klen)
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(NT) conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                      float* __restrict__ out, ConvDims d, int klen) {
+                                                      float* __restrict__ out, float* __restrict__ ws, unsigned* counters,
+                                                      ConvDims d, int klen) {
     __shared__ __align__(16) float As[BK][BM + PADM];
     __shared__ __align__(16) float Bs[BK][BN + PADM];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -58,10 +118,10 @@ __global__ void __launch_bounds__(NT) conv_fwd_kernel(const float* __restrict__ 
     }
     const float* wrow = w + (size_t)(n0 + lrow) * d.Kpitch;
 
-    float acc[4][4] = {};
-    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    // operand fetch for the k-slab starting at k0 (registers; issued one slab ahead of the math)
+    auto fetch = [&](int k0, float (&av)[4], float4& bv) {
         const int k = k0 + lkv;
-        float av[4] = {0.f, 0.f, 0.f, 0.f};
+        av[0] = av[1] = av[2] = av[3] = 0.f;
         if (mvalid) {
             if (VEC == 4) {
                 if (k < K) {
@@ -87,20 +147,21 @@ __global__ void __launch_bounds__(NT) conv_fwd_kernel(const float* __restrict__ 
                 }
             }
         }
-        float4 bv = ldg4(wrow + k);           // rows are zero padded up to Kpitch >= roundup16(K)
+        bv = ldg4(wrow + k);                  // rows are zero padded up to Kpitch >= roundup16(K)
+    };
+    float acc[4][4] = {};
+    float av[4];
+    float4 bv;
+    if (kbeg < kend) fetch(kbeg, av, bv);
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
         __syncthreads();
         As[lkv + 0][lrow] = av[0]; As[lkv + 1][lrow] = av[1]; As[lkv + 2][lrow] = av[2]; As[lkv + 3][lrow] = av[3];
         Bs[lkv + 0][lrow] = bv.x; Bs[lkv + 1][lrow] = bv.y; Bs[lkv + 2][lrow] = bv.z; Bs[lkv + 3][lrow] = bv.w;
         __syncthreads();
+        if (k0 + BK < kend) fetch(k0 + BK, av, bv);       // in flight while the slab below is multiplied
         mma_slab(As, Bs, tx, ty, acc);
     }
-    float* o = out + (size_t)blockIdx.z * M * d.Cout;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int mm = m0 + ty * 4 + i;
-        if (mm < M)
-            *reinterpret_cast<float4*>(o + (size_t)mm * d.Cout + n0 + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    }
+    store_rows(acc, out, ws, counters, M, d.Cout, m0, n0, tx, ty, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -109,7 +170,8 @@ __global__ void __launch_bounds__(NT) conv_fwd_kernel(const float* __restrict__ 
 // GEMM view: M = B*Hi*Wi, N = Cin, K = kh*kw*Cout ordered (r,s,co)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) conv_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                                        float* __restrict__ out, ConvDims d, int klen, int accumulate) {
+                                                        float* __restrict__ out, float* __restrict__ ws, unsigned* counters,
+                                                        ConvDims d, int klen, int accumulate) {
     __shared__ __align__(16) float As[BK][BM + PADM];
     __shared__ __align__(16) float Bs[BK][BN + PADM];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -129,9 +191,9 @@ __global__ void __launch_bounds__(NT) conv_dgrad_kernel(const float* __restrict_
     }
     const int bk = tid >> 4, bnv = (tid & 15) * 4;        // B loader: row k, 4 consecutive ci
 
-    float acc[4][4] = {};
-    for (int k0 = kbeg; k0 < kend; k0 += BK) {
-        float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fetch = [&](int k0, float4& av, float4& bv) {
+        av = make_float4(0.f, 0.f, 0.f, 0.f);
+        bv = make_float4(0.f, 0.f, 0.f, 0.f);
         {
             const int k = k0 + lkv;
             if (mvalid && k < kend) {
@@ -145,7 +207,6 @@ __global__ void __launch_bounds__(NT) conv_dgrad_kernel(const float* __restrict_
                 }
             }
         }
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         {
             const int k = k0 + bk;
             if (k < kend) {
@@ -153,23 +214,19 @@ __global__ void __launch_bounds__(NT) conv_dgrad_kernel(const float* __restrict_
                 bv = ldg4(w + (size_t)co * d.Kpitch + (size_t)tap * d.Cin + n0 + bnv);
             }
         }
+    };
+    float acc[4][4] = {};
+    float4 av, bv;
+    if (kbeg < kend) fetch(kbeg, av, bv);
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
         __syncthreads();
         As[lkv + 0][lrow] = av.x; As[lkv + 1][lrow] = av.y; As[lkv + 2][lrow] = av.z; As[lkv + 3][lrow] = av.w;
         *reinterpret_cast<float4*>(&Bs[bk][bnv]) = bv;
         __syncthreads();
+        if (k0 + BK < kend) fetch(k0 + BK, av, bv);
         mma_slab(As, Bs, tx, ty, acc);
     }
-    float* o = out + (size_t)blockIdx.z * M * d.Cin;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int mm = m0 + ty * 4 + i;
-        if (mm < M) {
-            float4* p = reinterpret_cast<float4*>(o + (size_t)mm * d.Cin + n0 + tx * 4);
-            float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-            if (accumulate) { float4 c = *p; v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w; }
-            *p = v;
-        }
-    }
+    store_rows(acc, out, ws, counters, M, d.Cin, m0, n0, tx, ty, accumulate);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -178,7 +235,8 @@ __global__ void __launch_bounds__(NT) conv_dgrad_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                                        float* __restrict__ out, ConvDims d, int plen, int direct_accumulate) {
+                                                        float* __restrict__ out, float* __restrict__ ws, unsigned* counters,
+                                                        ConvDims d, int plen) {
     __shared__ __align__(16) float As[BK][BM + PADM];
     __shared__ __align__(16) float Bs[BK][BN + PADM];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -198,11 +256,10 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const float* __restrict_
         br[e] = tap / d.kw; bs[e] = tap - br[e] * d.kw;
     }
 
-    float acc[4][4] = {};
-    for (int p0 = pbeg; p0 < pend; p0 += BK) {
+    auto fetch = [&](int p0, float4& av, float (&bv)[4]) {
         const int p = p0 + lk;
-        float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        av = make_float4(0.f, 0.f, 0.f, 0.f);
+        bv[0] = bv[1] = bv[2] = bv[3] = 0.f;
         if (p < pend) {
             av = ldg4(dy + (size_t)p * d.Cout + m0 + lv);
             int b = p / (d.Ho * d.Wo), rem = p - b * d.Ho * d.Wo;
@@ -226,14 +283,33 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const float* __restrict_
                     }
             }
         }
+    };
+    float acc[4][4] = {};
+    float4 av;
+    float bv[4];
+    if (pbeg < pend) fetch(pbeg, av, bv);
+    for (int p0 = pbeg; p0 < pend; p0 += BK) {
         __syncthreads();
         *reinterpret_cast<float4*>(&As[lk][lv]) = av;
         *reinterpret_cast<float4*>(&Bs[lk][lv]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
         __syncthreads();
+        if (p0 + BK < pend) fetch(p0 + BK, av, bv);
         mma_slab(As, Bs, tx, ty, acc);
     }
-    // rows = co, cols = n'
-    float* o = out + (direct_accumulate ? (size_t)0 : (size_t)blockIdx.z * d.Cout * d.Kpitch);
+    // rows = co, cols = n'; the weight gradient always accumulates (+=) into the gradient arena
+    const int nz = gridDim.z;
+    const size_t slab = (size_t)d.Cout * d.Kpitch;
+    if (nz > 1) {
+        float* mine = ws + (size_t)blockIdx.z * slab;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int n = n0 + tx * 4 + j;
+                if (n < K) mine[(size_t)(m0 + ty * 4 + i) * d.Kpitch + n] = acc[i][j];
+            }
+        if (!splitk_last_arriver(counters)) return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         int co = m0 + ty * 4 + i;
@@ -241,8 +317,11 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const float* __restrict_
         for (int j = 0; j < 4; ++j) {
             int n = n0 + tx * 4 + j;
             if (n < K) {
-                float* p = o + (size_t)co * d.Kpitch + n;
-                *p = direct_accumulate ? (*p + acc[i][j]) : acc[i][j];
+                const size_t off = (size_t)co * d.Kpitch + n;
+                float sacc = out[off];
+                if (nz > 1) { for (int z = 0; z < nz; ++z) sacc += __ldcg(ws + (size_t)z * slab + off); }
+                else sacc += acc[i][j];
+                out[off] = sacc;
             }
         }
     }
@@ -270,9 +349,12 @@ int splitk_reduce(const float* part, float* out, size_t n, int nsplit, int accum
 // launchers
 // ---------------------------------------------------------------------------------------------
 static const int kTargetCtas = 296;      // 2 x 148 SMs
+static const int kMaxTiles = 1 << 16;
+
+unsigned* sync_words(int which);         // library-owned zero-initialised sync storage (norm_pool.cu)
 
 static int pick_split(int tiles, int kiters, size_t out_floats, size_t ws_floats) {
-    if (tiles >= kTargetCtas || kiters < 8) return 1;
+    if (tiles >= kTargetCtas || kiters < 8 || tiles > kMaxTiles) return 1;
     int s = (kTargetCtas + tiles - 1) / tiles;
     if (s > kiters / 4) s = kiters / 4;
     while (s > 1 && (size_t)s * out_floats > ws_floats) --s;
@@ -289,16 +371,11 @@ int conv_fwd(const float* x, const float* w, float* y, const ConvDims& d, float*
     int klen = ((kiters + ns - 1) / ns) * BK;
     ns = (kiters * BK + klen - 1) / klen;
     dim3 grid(ceil_div(M, BM), d.Cout / BN, ns);
-    float* dst = ns > 1 ? ws : y;
-    if (d.Cin % 4 == 0) conv_fwd_kernel<4><<<grid, NT, 0, st>>>(x, w, dst, d, klen);
-    else conv_fwd_kernel<1><<<grid, NT, 0, st>>>(x, w, dst, d, klen);
-    DBOA_TRY(check_launch());
-    if (ns > 1) {
-        size_t n4 = (size_t)M * d.Cout / 4;
-        splitk_reduce_kernel<<<ceil_div(n4, 256), 256, 0, st>>>(ws, y, n4, ns, 0);
-        DBOA_TRY(check_launch());
-    }
-    return DBOA_OK;
+    unsigned* cnt = sync_words(0);
+    if (cnt == nullptr) return DBOA_ERR_CUDA;
+    if (d.Cin % 4 == 0) conv_fwd_kernel<4><<<grid, NT, 0, st>>>(x, w, y, ws, cnt, d, klen);
+    else conv_fwd_kernel<1><<<grid, NT, 0, st>>>(x, w, y, ws, cnt, d, klen);
+    return check_launch();
 }
 
 int conv_dgrad(const float* dy, const float* w, float* dx, const ConvDims& d, int accumulate, float* ws, size_t ws_floats,
@@ -311,14 +388,10 @@ int conv_dgrad(const float* dy, const float* w, float* dx, const ConvDims& d, in
     int klen = ((kiters + ns - 1) / ns) * BK;
     ns = (K + klen - 1) / klen;
     dim3 grid(ceil_div(M, BM), d.Cin / BN, ns);
-    conv_dgrad_kernel<<<grid, NT, 0, st>>>(dy, w, ns > 1 ? ws : dx, d, klen, ns > 1 ? 0 : accumulate);
-    DBOA_TRY(check_launch());
-    if (ns > 1) {
-        size_t n4 = (size_t)M * d.Cin / 4;
-        splitk_reduce_kernel<<<ceil_div(n4, 256), 256, 0, st>>>(ws, dx, n4, ns, accumulate);
-        DBOA_TRY(check_launch());
-    }
-    return DBOA_OK;
+    unsigned* cnt = sync_words(0);
+    if (cnt == nullptr) return DBOA_ERR_CUDA;
+    conv_dgrad_kernel<<<grid, NT, 0, st>>>(dy, w, dx, ws, cnt, d, klen, accumulate);
+    return check_launch();
 }
 
 int conv_wgrad(const float* dy, const float* x, float* dw, const ConvDims& d, float* ws, size_t ws_floats, cudaStream_t st) {
@@ -331,20 +404,11 @@ int conv_wgrad(const float* dy, const float* x, float* dw, const ConvDims& d, fl
     int plen = ((piters + ns - 1) / ns) * BK;
     ns = (Mpix + plen - 1) / plen;
     dim3 grid(d.Cout / BM, ceil_div(K, BN), ns);
-    if (ns > 1) {
-        // partial slabs must be fully defined where the reduce reads them: clear the padded pitch once
-        if (d.Kpitch != K) { cudaMemsetAsync(ws, 0, (size_t)ns * wfloats * sizeof(float), st); }
-    }
-    float* dst = ns > 1 ? ws : dw;
-    if (d.Cin % 4 == 0) conv_wgrad_kernel<4><<<grid, NT, 0, st>>>(dy, x, dst, d, plen, ns > 1 ? 0 : 1);
-    else conv_wgrad_kernel<1><<<grid, NT, 0, st>>>(dy, x, dst, d, plen, ns > 1 ? 0 : 1);
-    DBOA_TRY(check_launch());
-    if (ns > 1) {
-        size_t n4 = wfloats / 4;
-        splitk_reduce_kernel<<<ceil_div(n4, 256), 256, 0, st>>>(ws, dw, n4, ns, 1);
-        DBOA_TRY(check_launch());
-    }
-    return DBOA_OK;
+    unsigned* cnt = sync_words(0);
+    if (cnt == nullptr) return DBOA_ERR_CUDA;
+    if (d.Cin % 4 == 0) conv_wgrad_kernel<4><<<grid, NT, 0, st>>>(dy, x, dw, ws, cnt, d, plen);
+    else conv_wgrad_kernel<1><<<grid, NT, 0, st>>>(dy, x, dw, ws, cnt, d, plen);
+    return check_launch();
 }
 
 }  // namespace dboa

@@ -271,9 +271,8 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
     auto gn_plain = [&](int ci, float* out, int relu, const float* res) {
         const ConvLayer& c = n.convs[ci];
         int HW = c.hout * c.hout;
-        DBOA_TRY(gn_stats(T + t.conv[ci].y, B, HW, c.cout, T + t.conv[ci].part, st));
-        return gn_apply(T + t.conv[ci].y, T + t.conv[ci].part, P + c.g_off, P + c.b_off, T + t.conv[ci].stats, res, nullptr, nullptr,
-                        nullptr, nullptr, nullptr, out, B, HW, c.cout, relu, st);
+        return gn_fwd_fused(T + t.conv[ci].y, P + c.g_off, P + c.b_off, res, out, T + t.conv[ci].stats, T + t.conv[ci].part, B, HW,
+                            c.cout, relu, st);
     };
     conv_tc_set_workspace(sc.ws, (size_t)kConvWs);
     DBOA_TRY(nchw_to_nhwc(image, T + t.x0, B, 3, 224, 224, st));
@@ -292,11 +291,9 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
         if (b.cd >= 0) {
             const ConvLayer& cd = n.convs[b.cd];
             DBOA_TRY(conv_forward(cd, B, x, P + cd.w_off, T + t.conv[b.cd].y, sc.ws, st));
-            DBOA_TRY(gn_stats(T + t.conv[b.c3].y, B, HW, c3.cout, T + t.conv[b.c3].part, st));
-            DBOA_TRY(gn_stats(T + t.conv[b.cd].y, B, HW, cd.cout, T + t.conv[b.cd].part, st));
-            DBOA_TRY(gn_apply(T + t.conv[b.c3].y, T + t.conv[b.c3].part, P + c3.g_off, P + c3.b_off, T + t.conv[b.c3].stats, nullptr,
-                              T + t.conv[b.cd].y, T + t.conv[b.cd].part, P + cd.g_off, P + cd.b_off, T + t.conv[b.cd].stats,
-                              T + t.conv[b.c3].a, B, HW, c3.cout, 1, st));
+            (void)HW;
+            DBOA_TRY(gn_plain(b.cd, sc.t1, 0, nullptr));                 // normalised shortcut -> scratch
+            DBOA_TRY(gn_plain(b.c3, T + t.conv[b.c3].a, 1, sc.t1));      // relu(gn(y3) + shortcut)
         } else {
             DBOA_TRY(gn_plain(b.c3, T + t.conv[b.c3].a, 1, x));
         }
@@ -375,7 +372,7 @@ int hmr_backward(const float* P, const float* T, int B, int masked_in, const flo
     DBOA_TRY(avgpool_bwd(sc.dxf, 2048, dOut, B, 49, 2048, st));
     auto gnb = [&](int ci, const float* dout, const float* mask_src, float* dy) {
         const ConvLayer& c = n.convs[ci];
-        return gn_bwd(dout, mask_src, T + t.conv[ci].y, T + t.conv[ci].stats, P + c.g_off, dy, G + c.g_off, G + c.b_off, sc.gnp, B,
+        return gn_bwd_fused(dout, mask_src, T + t.conv[ci].y, T + t.conv[ci].stats, P + c.g_off, dy, G + c.g_off, G + c.b_off, sc.gnp, B,
                       c.hout * c.hout, c.cout, st);
     };
     for (int bi = (int)n.blocks.size() - 1; bi >= 0; --bi) {

@@ -35,6 +35,11 @@ size_t gn_bwd_partial_floats(int B, int HW, int C);
 // dz = dout * (mask_src > 0 if mask_src else 1); dy = GN backward; dgamma/dbeta accumulate (+=)
 int gn_bwd(const float* dout, const float* mask_src, const float* y, const float* stats, const float* gamma,
            float* dy, float* dgamma, float* dbeta, float* partial, int B, int HW, int C, cudaStream_t st);
+// single-launch variants (statistics + apply, and the whole backward) -- the ones the network plan uses
+int gn_fwd_fused(const float* y, const float* gamma, const float* beta, const float* res, float* out, float* stats, float* partial,
+                 int B, int HW, int C, int relu, cudaStream_t st);
+int gn_bwd_fused(const float* dout, const float* mask_src, const float* y, const float* stats, const float* gamma, float* dy,
+                 float* dgamma, float* dbeta, float* partial, int B, int HW, int C, cudaStream_t st);
 int relu_mask(const float* dout, const float* mask_src, float* dz, size_t n, cudaStream_t st);
 int nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, cudaStream_t st);
 int maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, cudaStream_t st);

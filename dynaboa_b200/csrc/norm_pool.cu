@@ -269,6 +269,254 @@ int gn_bwd(const float* dout, const float* mask_src, const float* y, const float
     return check_launch();
 }
 
+// =============================================================================================
+// Single-launch GroupNorm forward / backward.
+//
+// At batch 1 every layer is a few-microsecond problem, so launches -- not bytes -- set the time
+// (profiles/r01_summary.md).  These kernels merge statistics + apply (forward) and the three
+// backward passes into ONE launch each and read every tensor once: a CTA keeps its chunk in
+// registers, publishes its partial sums, and the CTAs of one (sample, group) rendezvous through a
+// ticket counter + generation flag in library-owned memory.  The last CTA to arrive combines the
+// partials in chunk order (deterministic) and releases the others.  CTAs of a group have
+// consecutive block ids, and the hardware dispatches blocks in id order, so every waiting group is
+// fully resident or about to be: the spin cannot deadlock (same argument as decoupled look-back).
+// =============================================================================================
+static unsigned* g_sync_base = nullptr;
+enum { SYNC_TILE = 0, SYNC_GN_CNT, SYNC_GN_FLAG, SYNC_GNB_CNT, SYNC_GNB_FLAG, SYNC_GNB_PCNT, SYNC_GNB_SUMS, SYNC_REGIONS };
+static const size_t kSyncOff[SYNC_REGIONS + 1] = {0, 65536, 65536 + 256, 65536 + 512, 65536 + 768, 65536 + 1024, 65536 + 1280, 65536 + 2048};
+
+unsigned* sync_words(int which) {
+    if (g_sync_base == nullptr) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, kSyncOff[SYNC_REGIONS] * sizeof(unsigned)) != cudaSuccess) return nullptr;
+        if (cudaMemset(p, 0, kSyncOff[SYNC_REGIONS] * sizeof(unsigned)) != cudaSuccess) return nullptr;
+        g_sync_base = static_cast<unsigned*>(p);
+    }
+    return g_sync_base + kSyncOff[which];
+}
+static unsigned g_generation = 0;
+
+__device__ __forceinline__ void spin_until(const unsigned* flag, unsigned gen) {
+    while (*reinterpret_cast<const volatile unsigned*>(flag) != gen) __nanosleep(40);
+}
+
+__global__ void __launch_bounds__(GN_NT) gn_fwd_fused_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const float* __restrict__ res,
+                                                             float* __restrict__ out, float* __restrict__ stats,
+                                                             float* __restrict__ partial, unsigned* counters, unsigned* flags, int HW,
+                                                             int C, int R, int relu, unsigned gen) {
+    __shared__ float red[32];
+    __shared__ float sm[2];
+    const int chunk = blockIdx.x, g = blockIdx.y, b = blockIdx.z, chunks = gridDim.x, slot = b * GN_G + g;
+    const int cg = C / GN_G, cg4 = cg / 4;
+    const int r0 = chunk * R, rows = min(R, HW - r0);
+    const int nvec = rows * cg4;
+    const size_t base = ((size_t)b * HW + r0) * C + g * cg;
+    float4 v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int idx = threadIdx.x + i * GN_NT;
+        if (idx < nvec) {
+            int row = idx / cg4, cv = idx - row * cg4;
+            v[i] = ldg4(y + base + (size_t)row * C + cv * 4);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float cnt = (float)(rows * cg);
+    const float cmean = block_sum(s, red) / cnt;
+    float m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int idx = threadIdx.x + i * GN_NT;
+        if (idx < nvec) {
+            float a = v[i].x - cmean, c = v[i].y - cmean, e = v[i].z - cmean, f = v[i].w - cmean;
+            m2 += (a * a + c * c) + (e * e + f * f);
+        }
+    }
+    m2 = block_sum(m2, red);
+    if (threadIdx.x == 0) {
+        float* p = partial + ((size_t)slot * chunks + chunk) * 3;
+        p[0] = cnt; p[1] = cmean; p[2] = m2;
+        __threadfence();
+        const unsigned t = atomicAdd(&counters[slot], 1u);
+        if (t == (unsigned)chunks - 1) {
+            counters[slot] = 0;
+            __threadfence();
+            const float* q = partial + (size_t)slot * chunks * 3;
+            float n = 0.f, mu = 0.f, M2 = 0.f;
+            for (int c = 0; c < chunks; ++c) {
+                float nb = __ldcg(q + c * 3), mb = __ldcg(q + c * 3 + 1), Mb = __ldcg(q + c * 3 + 2);
+                float tot = n + nb, delta = mb - mu;
+                mu += delta * (nb / tot);
+                M2 += Mb + delta * delta * (n * nb / tot);
+                n = tot;
+            }
+            const float rstd = 1.0f / sqrtf(M2 / n + GN_EPS);
+            stats[slot * 2] = mu; stats[slot * 2 + 1] = rstd;
+            __threadfence();
+            atomicExch(&flags[slot], gen);
+        } else {
+            spin_until(&flags[slot], gen);
+            __threadfence();
+        }
+        sm[0] = __ldcg(stats + slot * 2); sm[1] = __ldcg(stats + slot * 2 + 1);
+    }
+    __syncthreads();
+    const float mean = sm[0], rstd = sm[1];
+    const int cvf = threadIdx.x % cg4;                     // 256 % cg4 == 0: the channel vector is fixed per thread
+    const float4 ga = ldg4(gamma + g * cg + cvf * 4), be = ldg4(beta + g * cg + cvf * 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int idx = threadIdx.x + i * GN_NT;
+        if (idx < nvec) {
+            int row = idx / cg4;
+            const size_t e = base + (size_t)row * C + cvf * 4;
+            float4 o;
+            o.x = (v[i].x - mean) * rstd * ga.x + be.x; o.y = (v[i].y - mean) * rstd * ga.y + be.y;
+            o.z = (v[i].z - mean) * rstd * ga.z + be.z; o.w = (v[i].w - mean) * rstd * ga.w + be.w;
+            if (res != nullptr) { float4 r = ldg4(res + e); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4*>(out + e) = o;
+        }
+    }
+}
+
+int gn_fwd_fused(const float* y, const float* gamma, const float* beta, const float* res, float* out, float* stats, float* partial,
+                 int B, int HW, int C, int relu, cudaStream_t st) {
+    if (C % 16 != 0 || 256 % (C / 16) != 0 || C / GN_G > GN_BUDGET || B * GN_G > 256) return DBOA_ERR_SHAPE;
+    unsigned* cnt = sync_words(SYNC_GN_CNT);
+    unsigned* flg = sync_words(SYNC_GN_FLAG);
+    if (!cnt || !flg) return DBOA_ERR_CUDA;
+    dim3 grid(gn_chunks(HW, C), GN_G, B);
+    gn_fwd_fused_kernel<<<grid, GN_NT, 0, st>>>(y, gamma, beta, res, out, stats, partial, cnt, flg, HW, C, gn_rows(C), relu, ++g_generation);
+    return check_launch();
+}
+
+__global__ void __launch_bounds__(GN_NT) gn_bwd_fused_kernel(const float* __restrict__ dout, const float* __restrict__ mask_src,
+                                                             const float* __restrict__ y, const float* __restrict__ stats,
+                                                             const float* __restrict__ gamma, float* __restrict__ dy,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                             float* __restrict__ spart, float* __restrict__ dgpart,
+                                                             float* __restrict__ dbpart, float* sums, unsigned* counters, unsigned* flags,
+                                                             unsigned* pcounters, int HW, int C, int R, unsigned gen) {
+    __shared__ float red[32];
+    __shared__ float sm[2];
+    __shared__ int s_plast;
+    __shared__ __align__(16) float smg[GN_NT * 4], smb[GN_NT * 4];
+    const int chunk = blockIdx.x, g = blockIdx.y, b = blockIdx.z, chunks = gridDim.x, B = gridDim.z, slot = b * GN_G + g;
+    const int cg = C / GN_G, cg4 = cg / 4;
+    const int r0 = chunk * R, rows = min(R, HW - r0);
+    const int nvec = rows * cg4;
+    const size_t base = ((size_t)b * HW + r0) * C + g * cg;
+    const float mean = stats[slot * 2], rstd = stats[slot * 2 + 1];
+    const int cv = threadIdx.x % cg4;
+    const float4 ga = ldg4(gamma + g * cg + cv * 4);
+    float4 gq[8], xh[8];
+    float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int idx = threadIdx.x + i * GN_NT;
+        if (idx < nvec) {
+            int row = idx / cg4;
+            const size_t e = base + (size_t)row * C + cv * 4;
+            float4 d = ldg4(dout + e), v = ldg4(y + e);
+            if (mask_src != nullptr) {
+                float4 m = ldg4(mask_src + e);
+                d.x = m.x > 0.f ? d.x : 0.f; d.y = m.y > 0.f ? d.y : 0.f; d.z = m.z > 0.f ? d.z : 0.f; d.w = m.w > 0.f ? d.w : 0.f;
+            }
+            xh[i] = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
+            gq[i] = make_float4(d.x * ga.x, d.y * ga.y, d.z * ga.z, d.w * ga.w);
+            dg.x += d.x * xh[i].x; dg.y += d.y * xh[i].y; dg.z += d.z * xh[i].z; dg.w += d.w * xh[i].w;
+            db.x += d.x; db.y += d.y; db.z += d.z; db.w += d.w;
+            s1 += (gq[i].x + gq[i].y) + (gq[i].z + gq[i].w);
+            s2 += (gq[i].x * xh[i].x + gq[i].y * xh[i].y) + (gq[i].z * xh[i].z + gq[i].w * xh[i].w);
+        }
+    }
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    if (threadIdx.x == 0) {
+        float* p = spart + ((size_t)slot * chunks + chunk) * 2;
+        p[0] = s1; p[1] = s2;
+        __threadfence();
+        const unsigned t = atomicAdd(&counters[slot], 1u);
+        if (t == (unsigned)chunks - 1) {
+            counters[slot] = 0;
+            __threadfence();
+            const float* q = spart + (size_t)slot * chunks * 2;
+            float a = 0.f, c = 0.f;
+            for (int k = 0; k < chunks; ++k) { a += __ldcg(q + k * 2); c += __ldcg(q + k * 2 + 1); }
+            sums[slot * 2] = a; sums[slot * 2 + 1] = c;
+            __threadfence();
+            atomicExch(&flags[slot], gen);
+        } else {
+            spin_until(&flags[slot], gen);
+            __threadfence();
+        }
+        sm[0] = __ldcg(sums + slot * 2); sm[1] = __ldcg(sums + slot * 2 + 1);
+    }
+    // per-channel partial sums of this chunk (fixed-order smem reduction)
+    *reinterpret_cast<float4*>(&smg[threadIdx.x * 4]) = dg;
+    *reinterpret_cast<float4*>(&smb[threadIdx.x * 4]) = db;
+    __syncthreads();
+    for (int c = threadIdx.x; c < cg; c += GN_NT) {
+        const int ccv = c >> 2, comp = c & 3, rp = GN_NT / cg4;
+        float a = 0.f, bsum = 0.f;
+        for (int j = 0; j < rp; ++j) { a += smg[(j * cg4 + ccv) * 4 + comp]; bsum += smb[(j * cg4 + ccv) * 4 + comp]; }
+        const size_t o = ((size_t)b * chunks + chunk) * C + g * cg + c;
+        dgpart[o] = a; dbpart[o] = bsum;
+    }
+    const float invN = 1.0f / ((float)HW * (float)cg);
+    const float m1 = sm[0] * invN, m2 = sm[1] * invN;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int idx = threadIdx.x + i * GN_NT;
+        if (idx < nvec) {
+            int row = idx / cg4;
+            const size_t e = base + (size_t)row * C + cv * 4;
+            float4 o;
+            o.x = rstd * (gq[i].x - m1 - xh[i].x * m2); o.y = rstd * (gq[i].y - m1 - xh[i].y * m2);
+            o.z = rstd * (gq[i].z - m1 - xh[i].z * m2); o.w = rstd * (gq[i].w - m1 - xh[i].w * m2);
+            *reinterpret_cast<float4*>(dy + e) = o;
+        }
+    }
+    // affine-parameter gradients: the last CTA of group g (over all samples and chunks) sums the rows in order
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&pcounters[g], 1u);
+        s_plast = (t == (unsigned)(B * chunks) - 1);
+        if (s_plast) pcounters[g] = 0;
+    }
+    __syncthreads();
+    if (s_plast) {
+        __threadfence();
+        const int nrows = B * chunks;
+        for (int c = threadIdx.x; c < cg; c += GN_NT) {
+            float a = 0.f, bsum = 0.f;
+            for (int r = 0; r < nrows; ++r) { a += __ldcg(dgpart + (size_t)r * C + g * cg + c); bsum += __ldcg(dbpart + (size_t)r * C + g * cg + c); }
+            dgamma[g * cg + c] += a; dbeta[g * cg + c] += bsum;
+        }
+    }
+}
+
+int gn_bwd_fused(const float* dout, const float* mask_src, const float* y, const float* stats, const float* gamma, float* dy,
+                 float* dgamma, float* dbeta, float* partial, int B, int HW, int C, cudaStream_t st) {
+    if (C % 16 != 0 || 256 % (C / 16) != 0 || C / GN_G > GN_BUDGET || B * GN_G > 256) return DBOA_ERR_SHAPE;
+    const int chunks = gn_chunks(HW, C);
+    float* spart = partial;
+    float* dgpart = partial + (size_t)B * GN_G * chunks * 2;
+    float* dbpart = dgpart + (size_t)B * chunks * C;
+    unsigned* cnt = sync_words(SYNC_GNB_CNT);
+    if (!cnt) return DBOA_ERR_CUDA;
+    dim3 grid(chunks, GN_G, B);
+    gn_bwd_fused_kernel<<<grid, GN_NT, 0, st>>>(dout, mask_src, y, stats, gamma, dy, dgamma, dbeta, spart, dgpart, dbpart,
+                                                reinterpret_cast<float*>(sync_words(SYNC_GNB_SUMS)), cnt, sync_words(SYNC_GNB_FLAG),
+                                                sync_words(SYNC_GNB_PCNT), HW, C, gn_rows(C), ++g_generation);
+    return check_launch();
+}
+
 // ---------------------------------------------------------------------------------------------
 __global__ void relu_mask_kernel(const float* __restrict__ dout, const float* __restrict__ mask_src, float* __restrict__ dz, size_t n4) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -44,11 +44,16 @@ def forward_graph(ad, arena, buffers, image, masks=None):
     return p
 
 
-def _loss_head(ad, p, w, kp=None, t_p2d=None, t_j3d=None, t_beta=None, t_R=None, gt_s3d=None):
-    """Runs the (optional) pose prior and the multi-term head; returns (terms[9], dp2d, dj3d, dR, dbeta)."""
-    B, dev = p.B, p.rot.device
-    dp2d, dj3d = torch.empty_like(p.p2d), torch.empty_like(p.joints)
-    dR, dbeta = torch.empty_like(p.rot), torch.empty_like(p.shape)
+def _loss_head(ad, p, w, kp=None, t_p2d=None, t_j3d=None, t_beta=None, t_R=None, gt_s3d=None, grads=None, nb=None):
+    """Runs the (optional) pose prior and the multi-term head on the first ``nb`` samples of ``p``; returns
+    (terms[9], dp2d, dj3d, dR, dbeta).  ``grads``: preallocated (possibly larger-batch) gradient buffers whose leading
+    ``nb`` rows are written."""
+    B, dev = (p.B if nb is None else nb), p.rot.device
+    if grads is None:
+        dp2d, dj3d = torch.empty_like(p.p2d), torch.empty_like(p.joints)
+        dR, dbeta = torch.empty_like(p.rot), torch.empty_like(p.shape)
+    else:
+        dp2d, dj3d, dR, dbeta = grads
     terms = torch.empty(9, dtype=torch.float32, device=dev)
     prior_b = None
     if w[2] != 0.0:
@@ -84,44 +89,59 @@ def backward_graph(ad, arena, p, dp2d, dj3d, dR, dbeta, grad_arena):
     hmr_mod.raw_backward(arena, p.tape, B, p.masked, dR, dbeta, dcam, grad_arena)
 
 
-def level_backward(ad, arena, buffers, main, kp, lower, grad_arena):
+def level_backward(ad, arena, buffers, image, kp, lower, grad_arena, main=None):
     """One level of the bilevel problem (reference base_adaptor.py:222-317) on weights ``arena``: evaluates the
-    level's loss on the already computed ``main`` forward (+ history / exemplar forwards) and accumulates its
-    gradient into ``grad_arena``.  Returns the loss as a device scalar."""
+    level's loss and accumulates its gradient into ``grad_arena``.  ``main`` is an already computed forward of
+    ``image`` with these weights (re-used when given).  When the motion loss is live and no forward is supplied,
+    the current and the history frame go through ONE batched forward / backward (same weights, independent
+    samples).  Returns (loss as a device scalar, the forward whose first rows belong to ``image``)."""
     o = ad.options
     tag = 'll' if lower else 'ul'
-    image = main.image
+    nb = image.shape[0]
     use_frame = o.use_frame_losses_lower if lower else o.use_frame_losses_upper
     use_temporal = o.use_temporal_losses_lower if lower else o.use_temporal_losses_upper
+    motion = bool(use_temporal and o.use_motion and (ad.global_step - o.interval) > 0)
+    hist = None
+    if motion:
+        hist_image, hist_kp = ad.get_hist()
+        if main is None:
+            main = forward_graph(ad, arena, buffers, torch.cat([image, hist_image], 0))      # rows [nb:] = history frame
+        else:
+            hist = forward_graph(ad, arena, buffers, hist_image)
+    elif main is None:
+        main = forward_graph(ad, arena, buffers, image)
     w = [0.0] * 8
     targets = {}
     if use_frame:
         w[0], w[1], w[2] = o.s2dloss_weight, o.shape_prior_weight, o.pose_prior_weight
     if use_temporal and o.use_meanteacher:
         teacher = ad.teacher
-        t = forward_graph(ad, teacher.arena, teacher._buffers, image, teacher._masks(image.shape[0], image.device))
+        t = forward_graph(ad, teacher.arena, teacher._buffers, image, teacher._masks(nb, image.device))
         tw = o.teacherloss_weight
         w[3], w[4], w[5], w[6] = 5 * tw, 5 * tw, 0.001 * tw, 1 * tw
         targets = dict(t_p2d=t.p2d, t_j3d=t.joints, t_beta=t.shape, t_R=t.rot)
-    terms, dp2d, dj3d, dR, dbeta = _loss_head(ad, main, w, kp=kp if use_frame else None, **targets)
+    batched = main.B > nb
+    grads = (torch.zeros_like(main.p2d), torch.zeros_like(main.joints), torch.zeros_like(main.rot), torch.zeros_like(main.shape)) \
+        if batched else None
+    terms, dp2d, dj3d, dR, dbeta = _loss_head(ad, main, w, kp=kp if use_frame else None, grads=grads, nb=nb, **targets)
     total = terms[8]
     if use_frame:
         ad.fit_losses[f'{tag}/s2dloss'], ad.fit_losses[f'{tag}/shape_prior'], ad.fit_losses[f'{tag}/pose_prior'] = terms[0], terms[1], terms[2]
         (ad.kp2dlosses_lower.append(terms[0]) if lower else ad.kp2dlosses_upper.__setitem__(ad.global_step, terms[0]))
-    if use_temporal and o.use_motion and (ad.global_step - o.interval) > 0:
-        hist_image, hist_kp = ad.get_hist()
-        h = forward_graph(ad, arena, buffers, hist_image)
+    if motion:
         mterm = torch.empty(1, dtype=torch.float32, device=image.device)
-        dph = torch.empty_like(h.p2d)
-        _lib.call('dboa_loss_motion', ptr(main.p2d), ptr(h.p2d), ptr(kp), ptr(hist_kp.contiguous()), float(o.motionloss_weight), ptr(mterm),
-                  ptr(dp2d), ptr(dph), main.B, 1, stream())
-        z3, zR, zb = torch.zeros_like(h.joints), torch.zeros_like(h.rot), torch.zeros_like(h.shape)
-        backward_graph(ad, arena, h, dph, z3, zR, zb, grad_arena)
+        p_hist = main.p2d[nb:] if batched else hist.p2d
+        dph = dp2d[nb:] if batched else torch.empty_like(hist.p2d)
+        _lib.call('dboa_loss_motion', ptr(main.p2d), ptr(p_hist), ptr(kp), ptr(hist_kp.contiguous()), float(o.motionloss_weight), ptr(mterm),
+                  ptr(dp2d), ptr(dph), nb, 1, stream())
+        if not batched:
+            backward_graph(ad, arena, hist, dph, torch.zeros_like(hist.joints), torch.zeros_like(hist.rot), torch.zeros_like(hist.shape),
+                           grad_arena)
         total = total + mterm[0] * o.motionloss_weight
         ad.fit_losses['ul/motion_loss'] = mterm[0]
     backward_graph(ad, arena, main, dp2d, dj3d, dR, dbeta, grad_arena)
     if o.retrieval:
-        ex = ad.retrieval(hmr_mod._feature_views(main.tape, main.B)[5])
+        ex = ad.retrieval(hmr_mod._feature_views(main.tape, main.B)[5][:nb])
         if (o.lower_level_mixtrain if lower else o.upper_level_mixtrain):
             e = forward_graph(ad, arena, buffers, ex['img'])
             n = e.B
@@ -133,7 +153,7 @@ def level_backward(ad, arena, buffers, main, kp, lower, grad_arena):
             backward_graph(ad, arena, e, a, b, c, d, grad_arena)
             total = total + eterms[8]
             ad.fit_losses[f'{tag}/labled_loss'] = eterms[8]
-    return total
+    return total, main
 
 
 def feature_cosines(ad, tape_a, tape_b, B):
@@ -155,7 +175,7 @@ def fused_adapt(ad, batch):
         probe = forward_graph(ad, theta, buffers, image)            # init_features (reference :132-133)
         if not o.use_boa:
             G.zero_()
-            ad.last_upper_loss = level_backward(ad, theta, buffers, probe, kp, True, G)
+            ad.last_upper_loss, _ = level_backward(ad, theta, buffers, image, kp, True, G, main=probe)
             opt.step()
             return ad.inference(batch, ad.model) if evaluate != 'none' else None
         fast, cur = theta, probe
@@ -163,18 +183,15 @@ def fused_adapt(ad, batch):
             ad._fast_bufs = [torch.empty_like(theta), torch.empty_like(theta)]
             ad._inner_grad = torch.empty_like(theta)
         for i in range(o.inner_step):
-            if i > 0:
-                cur = forward_graph(ad, fast, buffers, image)
             ad._inner_grad.zero_()
-            level_backward(ad, fast, buffers, cur, kp, True, ad._inner_grad)
+            level_backward(ad, fast, buffers, image, kp, True, ad._inner_grad, main=cur if i == 0 else None)
             nxt = ad._fast_bufs[i % 2]
             _lib.call('dboa_sgd_update', ptr(fast), ptr(ad._inner_grad), ptr(nxt), float(o.fastlr), theta.numel(), stream())
             fast = nxt
             if evaluate == 'all':
                 ad.inference(batch, _ArenaModel(model, fast))
-        upper = forward_graph(ad, fast, buffers, image)
         G.zero_()
-        ad.last_upper_loss = level_backward(ad, fast, buffers, upper, kp, False, G)
+        ad.last_upper_loss, _ = level_backward(ad, fast, buffers, image, kp, False, G)
         opt.step(teacher=teacher, alpha=o.alpha)                    # Adam + EMA teacher, one sweep
         result = None
         if evaluate == 'all' or (evaluate == 'final' and not o.dynamic_boa):
@@ -189,7 +206,7 @@ def fused_adapt(ad, batch):
                 if steps > o.optim_steps:
                     break
                 G.zero_()
-                level_backward(ad, theta, buffers, after, kp, False, G)       # 'after' was computed with the current theta
+                level_backward(ad, theta, buffers, image, kp, False, G, main=after)   # 'after' was computed with the current theta
                 opt.step(teacher=teacher, alpha=o.alpha)
                 before, after = after, forward_graph(ad, theta, buffers, image)
                 sims = feature_cosines(ad, before.tape, after.tape, probe.B)
