@@ -8,8 +8,12 @@
 // (conv_tc.cu) is checked against on the GPU, and it serves the shapes that path does not
 // take (Cin = 3 stem, odd tiles).  Split-K is deterministic: partial tiles go to a workspace
 // and are summed in a fixed order by `splitk_reduce_kernel`.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace dboa {
 
@@ -30,63 +34,59 @@ __device__ __forceinline__ void mma_slab(const float (*As)[BM + PADM], const flo
     }
 }
 
-// Split-K fix-up inside the kernel: every z-slice stores its partial tile, takes a ticket, and the LAST slice to
-// arrive sums the partials in the fixed order z = 0..nz-1 (deterministic) and writes the final tile.
-__device__ __forceinline__ bool splitk_last_arriver(unsigned* counters) {
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned tile = blockIdx.y * gridDim.x + blockIdx.x;
-        const unsigned t = atomicAdd(&counters[tile], 1u);
-        s_last = (t == gridDim.z - 1);
-        if (s_last) counters[tile] = 0;          // self-resetting: every other slice of this tile has already arrived
-    }
-    __syncthreads();
-    if (s_last) __threadfence();
-    return s_last != 0;
-}
-
-// rows x 4-float epilogue of a [M][ld] row-major output (forward / data gradient)
-__device__ __forceinline__ void store_rows(const float acc[4][4], float* __restrict__ final_out, float* __restrict__ ws,
-                                           unsigned* counters, int M, int ld, int m0, int n0, int tx, int ty, int accumulate) {
+// Split-K across a thread-block cluster (cluster dims (1,1,nz), nz <= 16): every K-slice parks its 64x64 partial
+// tile in its own shared memory, the cluster synchronises in hardware, and each CTA then sums a band of 64/nz rows over
+// all peers through distributed shared memory in the fixed order z = 0..nz-1 (deterministic) and writes that band.
+// No global partials, no atomics, no second launch.  `ncols` bounds the columns (weight gradient of the 7x7 stem).
+__device__ __forceinline__ void cluster_reduce_store(const float acc[4][4], float* red, float* __restrict__ out, int nrows, int ld,
+                                                     int r0, int c0, int ncols, int tx, int ty, int accumulate) {
     const int nz = gridDim.z;
     if (nz == 1) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            int mm = m0 + ty * 4 + i;
-            if (mm < M) {
-                float4* p = reinterpret_cast<float4*>(final_out + (size_t)mm * ld + n0 + tx * 4);
+            const int row = r0 + ty * 4 + i;
+            if (row >= nrows) continue;
+            float* p = out + (size_t)row * ld + c0 + tx * 4;
+            if (c0 + tx * 4 + 3 < ncols) {
                 float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-                if (accumulate) { float4 c = *p; v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w; }
-                *p = v;
+                if (accumulate) { float4 c = *reinterpret_cast<float4*>(p); v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w; }
+                *reinterpret_cast<float4*>(p) = v;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c0 + tx * 4 + j < ncols) p[j] = accumulate ? p[j] + acc[i][j] : acc[i][j];
             }
         }
         return;
     }
-    const size_t slab = (size_t)M * ld;
-    float* mine = ws + (size_t)blockIdx.z * slab;
+    cg::cluster_group cluster = cg::this_cluster();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int mm = m0 + ty * 4 + i;
-        if (mm < M)
-            *reinterpret_cast<float4*>(mine + (size_t)mm * ld + n0 + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    }
-    if (!splitk_last_arriver(counters)) return;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int mm = m0 + ty * 4 + i;
-        if (mm < M) {
-            const size_t off = (size_t)mm * ld + n0 + tx * 4;
-            float4* p = reinterpret_cast<float4*>(final_out + off);
-            float4 sacc = accumulate ? *p : make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int z = 0; z < nz; ++z) {
-                float4 v = __ldcg(reinterpret_cast<const float4*>(ws + (size_t)z * slab + off));
-                sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w;
-            }
-            *p = sacc;
+    for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(red + (ty * 4 + i) * BN + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    cluster.sync();
+    const int rank = (int)cluster.block_rank();
+    const int rows_per = BM / nz;                         // nz is a power of two <= 16
+    for (int v = threadIdx.x; v < rows_per * (BN / 4); v += NT) {
+        const int lr = rank * rows_per + v / (BN / 4), c4 = (v % (BN / 4)) * 4;
+        const int row = r0 + lr;
+        if (row >= nrows) continue;
+        float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < nz; ++z) {
+            const float* peer = cluster.map_shared_rank(red, z);
+            const float4 q = *reinterpret_cast<const float4*>(peer + lr * BN + c4);
+            sacc.x += q.x; sacc.y += q.y; sacc.z += q.z; sacc.w += q.w;
+        }
+        float* p = out + (size_t)row * ld + c0 + c4;
+        if (c0 + c4 + 3 < ncols) {
+            if (accumulate) { float4 c = *reinterpret_cast<float4*>(p); sacc.x += c.x; sacc.y += c.y; sacc.z += c.z; sacc.w += c.w; }
+            *reinterpret_cast<float4*>(p) = sacc;
+        } else {
+            const float sv[4] = {sacc.x, sacc.y, sacc.z, sacc.w};
+            for (int j = 0; j < 4; ++j)
+                if (c0 + c4 + j < ncols) p[j] = accumulate ? p[j] + sv[j] : sv[j];
         }
     }
+    cluster.sync();                                        // peers may still be reading this CTA's tile
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -95,10 +95,10 @@ __device__ __forceinline__ void store_rows(const float acc[4][4], float* __restr
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(NT) conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                      float* __restrict__ out, float* __restrict__ ws, unsigned* counters,
-                                                      ConvDims d, int klen) {
+                                                      float* __restrict__ out, ConvDims d, int klen) {
     __shared__ __align__(16) float As[BK][BM + PADM];
     __shared__ __align__(16) float Bs[BK][BN + PADM];
+    __shared__ __align__(16) float red[BM * BN];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int M = d.B * d.Ho * d.Wo, K = d.kh * d.kw * d.Cin;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(NT) conv_fwd_kernel(const float* __restrict__ 
         if (k0 + BK < kend) fetch(k0 + BK, av, bv);       // in flight while the slab below is multiplied
         mma_slab(As, Bs, tx, ty, acc);
     }
-    store_rows(acc, out, ws, counters, M, d.Cout, m0, n0, tx, ty, 0);
+    cluster_reduce_store(acc, red, out, M, d.Cout, m0, n0, d.Cout, tx, ty, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -170,10 +170,10 @@ __global__ void __launch_bounds__(NT) conv_fwd_kernel(const float* __restrict__ 
 // GEMM view: M = B*Hi*Wi, N = Cin, K = kh*kw*Cout ordered (r,s,co)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) conv_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                                        float* __restrict__ out, float* __restrict__ ws, unsigned* counters,
-                                                        ConvDims d, int klen, int accumulate) {
+                                                        float* __restrict__ out, ConvDims d, int klen, int accumulate) {
     __shared__ __align__(16) float As[BK][BM + PADM];
     __shared__ __align__(16) float Bs[BK][BN + PADM];
+    __shared__ __align__(16) float red[BM * BN];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int M = d.B * d.Hi * d.Wi, K = d.kh * d.kw * d.Cout;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(NT) conv_dgrad_kernel(const float* __restrict_
         if (k0 + BK < kend) fetch(k0 + BK, av, bv);
         mma_slab(As, Bs, tx, ty, acc);
     }
-    store_rows(acc, out, ws, counters, M, d.Cin, m0, n0, tx, ty, accumulate);
+    cluster_reduce_store(acc, red, out, M, d.Cin, m0, n0, d.Cin, tx, ty, accumulate);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -235,10 +235,10 @@ __global__ void __launch_bounds__(NT) conv_dgrad_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                                        float* __restrict__ out, float* __restrict__ ws, unsigned* counters,
-                                                        ConvDims d, int plen) {
+                                                        float* __restrict__ out, ConvDims d, int plen) {
     __shared__ __align__(16) float As[BK][BM + PADM];
     __shared__ __align__(16) float Bs[BK][BN + PADM];
+    __shared__ __align__(16) float red[BM * BN];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int Mpix = d.B * d.Ho * d.Wo, K = d.kh * d.kw * d.Cin;
     const int m0 = blockIdx.x * BM /* co */, n0 = blockIdx.y * BN /* (r,s,ci) */;
@@ -297,34 +297,7 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const float* __restrict_
         mma_slab(As, Bs, tx, ty, acc);
     }
     // rows = co, cols = n'; the weight gradient always accumulates (+=) into the gradient arena
-    const int nz = gridDim.z;
-    const size_t slab = (size_t)d.Cout * d.Kpitch;
-    if (nz > 1) {
-        float* mine = ws + (size_t)blockIdx.z * slab;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int n = n0 + tx * 4 + j;
-                if (n < K) mine[(size_t)(m0 + ty * 4 + i) * d.Kpitch + n] = acc[i][j];
-            }
-        if (!splitk_last_arriver(counters)) return;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int co = m0 + ty * 4 + i;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int n = n0 + tx * 4 + j;
-            if (n < K) {
-                const size_t off = (size_t)co * d.Kpitch + n;
-                float sacc = out[off];
-                if (nz > 1) { for (int z = 0; z < nz; ++z) sacc += __ldcg(ws + (size_t)z * slab + off); }
-                else sacc += acc[i][j];
-                out[off] = sacc;
-            }
-        }
-    }
+    cluster_reduce_store(acc, red, out, d.Cout, d.Kpitch, m0, n0, K, tx, ty, 1);
 }
 
 // out[i] = (accumulate ? out[i] : 0) + sum_z part[z][i]   (fixed order => deterministic)
@@ -349,66 +322,74 @@ int splitk_reduce(const float* part, float* out, size_t n, int nsplit, int accum
 // launchers
 // ---------------------------------------------------------------------------------------------
 static const int kTargetCtas = 296;      // 2 x 148 SMs
-static const int kMaxTiles = 1 << 16;
 
-unsigned* sync_words(int which);         // library-owned zero-initialised sync storage (norm_pool.cu)
+// K-slices per tile: a power of two <= 16 (the non-portable cluster limit) that fills ~2 waves and leaves >= 4 iterations
+static int pick_split(int tiles, int kiters) {
+    int ns = 1;
+    while (ns < 16 && tiles * ns * 2 <= kTargetCtas + tiles && kiters / (ns * 2) >= 4) ns *= 2;
+    return ns;
+}
 
-static int pick_split(int tiles, int kiters, size_t out_floats, size_t ws_floats) {
-    if (tiles >= kTargetCtas || kiters < 8 || tiles > kMaxTiles) return 1;
-    int s = (kTargetCtas + tiles - 1) / tiles;
-    if (s > kiters / 4) s = kiters / 4;
-    while (s > 1 && (size_t)s * out_floats > ws_floats) --s;
-    return s < 1 ? 1 : s;
+template <typename K, typename... Args>
+static int launch_z_cluster(K kernel, dim3 grid, cudaStream_t st, Args... args) {
+    if (grid.z > 8) {
+        static bool allowed = false;       // per kernel instantiation
+        if (!allowed) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) { g_last_cuda_error = (int)e; return DBOA_ERR_CUDA; }
+            allowed = true;
+        }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = grid.z;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    ++g_launch_count;
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return DBOA_ERR_CUDA; }
+    return DBOA_OK;
 }
 
 int conv_fwd(const float* x, const float* w, float* y, const ConvDims& d, float* ws, size_t ws_floats, cudaStream_t st) {
+    (void)ws; (void)ws_floats;
     if (d.Cout % BN != 0 || d.Kpitch % 4 != 0) return DBOA_ERR_SHAPE;
     const int M = d.B * d.Ho * d.Wo, K = d.kh * d.kw * d.Cin;
     if (d.Kpitch < (K + BK - 1) / BK * BK) return DBOA_ERR_SHAPE;
     const int kiters = (K + BK - 1) / BK;
     const int tiles = ceil_div(M, BM) * (d.Cout / BN);
-    int ns = pick_split(tiles, kiters, (size_t)M * d.Cout, ws_floats);
-    int klen = ((kiters + ns - 1) / ns) * BK;
-    ns = (kiters * BK + klen - 1) / klen;
+    const int ns = pick_split(tiles, kiters);
+    const int klen = ((kiters + ns - 1) / ns) * BK;
     dim3 grid(ceil_div(M, BM), d.Cout / BN, ns);
-    unsigned* cnt = sync_words(0);
-    if (cnt == nullptr) return DBOA_ERR_CUDA;
-    if (d.Cin % 4 == 0) conv_fwd_kernel<4><<<grid, NT, 0, st>>>(x, w, y, ws, cnt, d, klen);
-    else conv_fwd_kernel<1><<<grid, NT, 0, st>>>(x, w, y, ws, cnt, d, klen);
-    return check_launch();
+    if (d.Cin % 4 == 0) return launch_z_cluster(conv_fwd_kernel<4>, grid, st, x, w, y, d, klen);
+    return launch_z_cluster(conv_fwd_kernel<1>, grid, st, x, w, y, d, klen);
 }
 
 int conv_dgrad(const float* dy, const float* w, float* dx, const ConvDims& d, int accumulate, float* ws, size_t ws_floats,
                cudaStream_t st) {
+    (void)ws; (void)ws_floats;
     if (d.Cin % BN != 0 || d.Cout % BK != 0) return DBOA_ERR_SHAPE;
     const int M = d.B * d.Hi * d.Wi, K = d.kh * d.kw * d.Cout;
     const int kiters = K / BK;
     const int tiles = ceil_div(M, BM) * (d.Cin / BN);
-    int ns = pick_split(tiles, kiters, (size_t)M * d.Cin, ws_floats);
-    int klen = ((kiters + ns - 1) / ns) * BK;
-    ns = (K + klen - 1) / klen;
+    const int ns = pick_split(tiles, kiters);
+    const int klen = ((kiters + ns - 1) / ns) * BK;
     dim3 grid(ceil_div(M, BM), d.Cin / BN, ns);
-    unsigned* cnt = sync_words(0);
-    if (cnt == nullptr) return DBOA_ERR_CUDA;
-    conv_dgrad_kernel<<<grid, NT, 0, st>>>(dy, w, dx, ws, cnt, d, klen, accumulate);
-    return check_launch();
+    return launch_z_cluster(conv_dgrad_kernel, grid, st, dy, w, dx, d, klen, accumulate);
 }
 
 int conv_wgrad(const float* dy, const float* x, float* dw, const ConvDims& d, float* ws, size_t ws_floats, cudaStream_t st) {
+    (void)ws; (void)ws_floats;
     if (d.Cout % BM != 0) return DBOA_ERR_SHAPE;
     const int Mpix = d.B * d.Ho * d.Wo, K = d.kh * d.kw * d.Cin;
     const int piters = ceil_div(Mpix, BK);
     const int tiles = (d.Cout / BM) * ceil_div(K, BN);
-    size_t wfloats = (size_t)d.Cout * d.Kpitch;
-    int ns = pick_split(tiles, piters, wfloats, ws_floats);
-    int plen = ((piters + ns - 1) / ns) * BK;
-    ns = (Mpix + plen - 1) / plen;
+    const int ns = pick_split(tiles, piters);
+    const int plen = ((piters + ns - 1) / ns) * BK;
     dim3 grid(d.Cout / BM, ceil_div(K, BN), ns);
-    unsigned* cnt = sync_words(0);
-    if (cnt == nullptr) return DBOA_ERR_CUDA;
-    if (d.Cin % 4 == 0) conv_wgrad_kernel<4><<<grid, NT, 0, st>>>(dy, x, dw, ws, cnt, d, plen);
-    else conv_wgrad_kernel<1><<<grid, NT, 0, st>>>(dy, x, dw, ws, cnt, d, plen);
-    return check_launch();
+    if (d.Cin % 4 == 0) return launch_z_cluster(conv_wgrad_kernel<4>, grid, st, dy, x, dw, d, plen);
+    return launch_z_cluster(conv_wgrad_kernel<1>, grid, st, dy, x, dw, d, plen);
 }
 
 }  // namespace dboa

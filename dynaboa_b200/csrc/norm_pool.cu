@@ -5,8 +5,12 @@
 // eps 1e-5, affine), :36/57-58 (ReLU, residual add), :75 (MaxPool2d(3,2,1)), :80 (AvgPool2d(7))
 // -- SURVEY.md §2.1 K2/K3.  Statistics use a chunked two-pass (count, mean, M2) scheme merged
 // with Chan's formula in a fixed order, so results are deterministic and robust to large means.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace dboa {
 
@@ -19,8 +23,10 @@ static inline int gn_rows(int C) { int cg = C / GN_G; int r = GN_BUDGET / cg; re
 int gn_chunks(int HW, int C) { return ceil_div(HW, gn_rows(C)); }
 size_t gn_partial_floats(int B, int HW, int C) { return (size_t)B * GN_G * gn_chunks(HW, C) * 3; }
 size_t gn_bwd_partial_floats(int B, int HW, int C) {
-    size_t ch = gn_chunks(HW, C);
-    return (size_t)B * GN_G * ch * 2 + 2 * (size_t)B * ch * C;
+    size_t ch = gn_chunks(HW, C);            // legacy 3-pass layout; also >= the cluster plan's 2*B*16*C? no: take the max
+    size_t legacy = (size_t)B * GN_G * ch * 2 + 2 * (size_t)B * ch * C;
+    size_t cluster = 2 * (size_t)B * 16 * C;
+    return legacy > cluster ? legacy : cluster;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -270,52 +276,84 @@ int gn_bwd(const float* dout, const float* mask_src, const float* y, const float
 }
 
 // =============================================================================================
-// Single-launch GroupNorm forward / backward.
+// Single-launch GroupNorm forward / backward on thread-block clusters.
 //
-// At batch 1 every layer is a few-microsecond problem, so launches -- not bytes -- set the time
-// (profiles/r01_summary.md).  These kernels merge statistics + apply (forward) and the three
-// backward passes into ONE launch each and read every tensor once: a CTA keeps its chunk in
-// registers, publishes its partial sums, and the CTAs of one (sample, group) rendezvous through a
-// ticket counter + generation flag in library-owned memory.  The last CTA to arrive combines the
-// partials in chunk order (deterministic) and releases the others.  CTAs of a group have
-// consecutive block ids, and the hardware dispatches blocks in id order, so every waiting group is
-// fully resident or about to be: the spin cannot deadlock (same argument as decoupled look-back).
+// At batch 1 every layer is a few-microsecond problem, so the dependent phases inside and between
+// kernels -- not bytes -- set the time (profiles/r01_summary.md).  One (sample, group) is handled by
+// ONE cluster of <= 16 CTAs: each CTA keeps its slab of the group in registers (<= 13 float4 per
+// thread), publishes its partial sums in its own shared memory, the cluster synchronises in
+// hardware (barrier.cluster), every CTA reads all partials through distributed shared memory and
+// combines them in chunk order (deterministic), then normalises its registers.  Every tensor is
+// read exactly once; there are no global partials, atomics or second launches on the data path.
 // =============================================================================================
-static unsigned* g_sync_base = nullptr;
-enum { SYNC_TILE = 0, SYNC_GN_CNT, SYNC_GN_FLAG, SYNC_GNB_CNT, SYNC_GNB_FLAG, SYNC_GNB_PCNT, SYNC_GNB_SUMS, SYNC_REGIONS };
-static const size_t kSyncOff[SYNC_REGIONS + 1] = {0, 65536, 65536 + 256, 65536 + 512, 65536 + 768, 65536 + 1024, 65536 + 1280, 65536 + 2048};
+constexpr int GN_VMAX = 13;                      // float4 per thread held in registers
+constexpr int GN_MAXCL = 16;                     // CTAs per cluster (non-portable limit)
 
+struct GnPlan { int chunks, rows; };
+static GnPlan gn_plan(int HW, int C) {
+    const int cg4 = C / GN_G / 4, cap = GN_NT * GN_VMAX;
+    int chunks = ceil_div((long long)HW * cg4, cap);
+    if (chunks < 1) chunks = 1;
+    int rows = ceil_div(HW, chunks);
+    while (rows * cg4 > cap) { ++chunks; rows = ceil_div(HW, chunks); }
+    chunks = ceil_div(HW, rows);
+    return {chunks, rows};
+}
+
+static unsigned* g_sync_base = nullptr;
+enum { SYNC_GNB_PCNT = 0, SYNC_REGIONS };
 unsigned* sync_words(int which) {
+    (void)which;
     if (g_sync_base == nullptr) {
         void* p = nullptr;
-        if (cudaMalloc(&p, kSyncOff[SYNC_REGIONS] * sizeof(unsigned)) != cudaSuccess) return nullptr;
-        if (cudaMemset(p, 0, kSyncOff[SYNC_REGIONS] * sizeof(unsigned)) != cudaSuccess) return nullptr;
+        if (cudaMalloc(&p, 256 * sizeof(unsigned)) != cudaSuccess) return nullptr;
+        if (cudaMemset(p, 0, 256 * sizeof(unsigned)) != cudaSuccess) return nullptr;
         g_sync_base = static_cast<unsigned*>(p);
     }
-    return g_sync_base + kSyncOff[which];
-}
-static unsigned g_generation = 0;
-
-__device__ __forceinline__ void spin_until(const unsigned* flag, unsigned gen) {
-    while (*reinterpret_cast<const volatile unsigned*>(flag) != gen) __nanosleep(40);
+    return g_sync_base;
 }
 
+template <typename K, typename... Args>
+static int launch_x_cluster(K kernel, dim3 grid, cudaStream_t st, Args... args) {
+    if (grid.x > 8) {
+        static bool allowed = false;
+        if (!allowed) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) { g_last_cuda_error = (int)e; return DBOA_ERR_CUDA; }
+            allowed = true;
+        }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(GN_NT); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = grid.x; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    ++g_launch_count;
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return DBOA_ERR_CUDA; }
+    return DBOA_OK;
+}
+
+// grid (chunks, 4, B), cluster (chunks, 1, 1)
 __global__ void __launch_bounds__(GN_NT) gn_fwd_fused_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const float* __restrict__ res,
-                                                             float* __restrict__ out, float* __restrict__ stats,
-                                                             float* __restrict__ partial, unsigned* counters, unsigned* flags, int HW,
-                                                             int C, int R, int relu, unsigned gen) {
+                                                             float* __restrict__ out, float* __restrict__ stats, int HW, int C, int R,
+                                                             int relu) {
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ float red[32];
+    __shared__ float part[4];                 // this CTA's (count, mean, M2)
+    __shared__ float all[GN_MAXCL][3];
     __shared__ float sm[2];
     const int chunk = blockIdx.x, g = blockIdx.y, b = blockIdx.z, chunks = gridDim.x, slot = b * GN_G + g;
     const int cg = C / GN_G, cg4 = cg / 4;
     const int r0 = chunk * R, rows = min(R, HW - r0);
     const int nvec = rows * cg4;
     const size_t base = ((size_t)b * HW + r0) * C + g * cg;
-    float4 v[8];
+    float4 v[GN_VMAX];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < GN_VMAX; ++i) {
         int idx = threadIdx.x + i * GN_NT;
         if (idx < nvec) {
             int row = idx / cg4, cv = idx - row * cg4;
@@ -327,7 +365,7 @@ __global__ void __launch_bounds__(GN_NT) gn_fwd_fused_kernel(const float* __rest
     const float cmean = block_sum(s, red) / cnt;
     float m2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < GN_VMAX; ++i) {
         int idx = threadIdx.x + i * GN_NT;
         if (idx < nvec) {
             float a = v[i].x - cmean, c = v[i].y - cmean, e = v[i].z - cmean, f = v[i].w - cmean;
@@ -335,39 +373,31 @@ __global__ void __launch_bounds__(GN_NT) gn_fwd_fused_kernel(const float* __rest
         }
     }
     m2 = block_sum(m2, red);
+    if (threadIdx.x == 0) { part[0] = cnt; part[1] = cmean; part[2] = m2; }
+    cluster.sync();
+    if (threadIdx.x < chunks * 3) {
+        const int c = threadIdx.x / 3, k = threadIdx.x - c * 3;
+        all[c][k] = cluster.map_shared_rank(part, c)[k];
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        float* p = partial + ((size_t)slot * chunks + chunk) * 3;
-        p[0] = cnt; p[1] = cmean; p[2] = m2;
-        __threadfence();
-        const unsigned t = atomicAdd(&counters[slot], 1u);
-        if (t == (unsigned)chunks - 1) {
-            counters[slot] = 0;
-            __threadfence();
-            const float* q = partial + (size_t)slot * chunks * 3;
-            float n = 0.f, mu = 0.f, M2 = 0.f;
-            for (int c = 0; c < chunks; ++c) {
-                float nb = __ldcg(q + c * 3), mb = __ldcg(q + c * 3 + 1), Mb = __ldcg(q + c * 3 + 2);
-                float tot = n + nb, delta = mb - mu;
-                mu += delta * (nb / tot);
-                M2 += Mb + delta * delta * (n * nb / tot);
-                n = tot;
-            }
-            const float rstd = 1.0f / sqrtf(M2 / n + GN_EPS);
-            stats[slot * 2] = mu; stats[slot * 2 + 1] = rstd;
-            __threadfence();
-            atomicExch(&flags[slot], gen);
-        } else {
-            spin_until(&flags[slot], gen);
-            __threadfence();
+        float n = 0.f, mu = 0.f, M2 = 0.f;
+        for (int c = 0; c < chunks; ++c) {          // Chan's merge in chunk order
+            float nb = all[c][0], mb = all[c][1], Mb = all[c][2];
+            float tot = n + nb, delta = mb - mu;
+            mu += delta * (nb / tot);
+            M2 += Mb + delta * delta * (n * nb / tot);
+            n = tot;
         }
-        sm[0] = __ldcg(stats + slot * 2); sm[1] = __ldcg(stats + slot * 2 + 1);
+        sm[0] = mu; sm[1] = 1.0f / sqrtf(M2 / n + GN_EPS);
+        if (chunk == 0) { stats[slot * 2] = sm[0]; stats[slot * 2 + 1] = sm[1]; }
     }
     __syncthreads();
     const float mean = sm[0], rstd = sm[1];
     const int cvf = threadIdx.x % cg4;                     // 256 % cg4 == 0: the channel vector is fixed per thread
     const float4 ga = ldg4(gamma + g * cg + cvf * 4), be = ldg4(beta + g * cg + cvf * 4);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < GN_VMAX; ++i) {
         int idx = threadIdx.x + i * GN_NT;
         if (idx < nvec) {
             int row = idx / cg4;
@@ -380,27 +410,30 @@ __global__ void __launch_bounds__(GN_NT) gn_fwd_fused_kernel(const float* __rest
             *reinterpret_cast<float4*>(out + e) = o;
         }
     }
+    cluster.sync();                                        // peers may still be reading `part`
 }
 
 int gn_fwd_fused(const float* y, const float* gamma, const float* beta, const float* res, float* out, float* stats, float* partial,
                  int B, int HW, int C, int relu, cudaStream_t st) {
-    if (C % 16 != 0 || 256 % (C / 16) != 0 || C / GN_G > GN_BUDGET || B * GN_G > 256) return DBOA_ERR_SHAPE;
-    unsigned* cnt = sync_words(SYNC_GN_CNT);
-    unsigned* flg = sync_words(SYNC_GN_FLAG);
-    if (!cnt || !flg) return DBOA_ERR_CUDA;
-    dim3 grid(gn_chunks(HW, C), GN_G, B);
-    gn_fwd_fused_kernel<<<grid, GN_NT, 0, st>>>(y, gamma, beta, res, out, stats, partial, cnt, flg, HW, C, gn_rows(C), relu, ++g_generation);
-    return check_launch();
+    (void)partial;
+    if (C % 16 != 0 || 256 % (C / 16) != 0) return DBOA_ERR_SHAPE;
+    const GnPlan pl = gn_plan(HW, C);
+    if (pl.chunks > GN_MAXCL) return DBOA_ERR_SHAPE;
+    dim3 grid(pl.chunks, GN_G, B);
+    return launch_x_cluster(gn_fwd_fused_kernel, grid, st, y, gamma, beta, res, out, stats, HW, C, pl.rows, relu);
 }
 
+// backward: grid (chunks, 4, B), cluster (chunks, 1, 1)
 __global__ void __launch_bounds__(GN_NT) gn_bwd_fused_kernel(const float* __restrict__ dout, const float* __restrict__ mask_src,
                                                              const float* __restrict__ y, const float* __restrict__ stats,
                                                              const float* __restrict__ gamma, float* __restrict__ dy,
                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                             float* __restrict__ spart, float* __restrict__ dgpart,
-                                                             float* __restrict__ dbpart, float* sums, unsigned* counters, unsigned* flags,
-                                                             unsigned* pcounters, int HW, int C, int R, unsigned gen) {
+                                                             float* __restrict__ dgpart, float* __restrict__ dbpart, unsigned* pcounters,
+                                                             int HW, int C, int R) {
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ float red[32];
+    __shared__ float part[2];
+    __shared__ float all[GN_MAXCL][2];
     __shared__ float sm[2];
     __shared__ int s_plast;
     __shared__ __align__(16) float smg[GN_NT * 4], smb[GN_NT * 4];
@@ -412,11 +445,11 @@ __global__ void __launch_bounds__(GN_NT) gn_bwd_fused_kernel(const float* __rest
     const float mean = stats[slot * 2], rstd = stats[slot * 2 + 1];
     const int cv = threadIdx.x % cg4;
     const float4 ga = ldg4(gamma + g * cg + cv * 4);
-    float4 gq[8], xh[8];
+    float4 gq[GN_VMAX], xh[GN_VMAX];
     float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < GN_VMAX; ++i) {
         int idx = threadIdx.x + i * GN_NT;
         if (idx < nvec) {
             int row = idx / cg4;
@@ -436,30 +469,15 @@ __global__ void __launch_bounds__(GN_NT) gn_bwd_fused_kernel(const float* __rest
     }
     s1 = block_sum(s1, red);
     s2 = block_sum(s2, red);
-    if (threadIdx.x == 0) {
-        float* p = spart + ((size_t)slot * chunks + chunk) * 2;
-        p[0] = s1; p[1] = s2;
-        __threadfence();
-        const unsigned t = atomicAdd(&counters[slot], 1u);
-        if (t == (unsigned)chunks - 1) {
-            counters[slot] = 0;
-            __threadfence();
-            const float* q = spart + (size_t)slot * chunks * 2;
-            float a = 0.f, c = 0.f;
-            for (int k = 0; k < chunks; ++k) { a += __ldcg(q + k * 2); c += __ldcg(q + k * 2 + 1); }
-            sums[slot * 2] = a; sums[slot * 2 + 1] = c;
-            __threadfence();
-            atomicExch(&flags[slot], gen);
-        } else {
-            spin_until(&flags[slot], gen);
-            __threadfence();
-        }
-        sm[0] = __ldcg(sums + slot * 2); sm[1] = __ldcg(sums + slot * 2 + 1);
-    }
-    // per-channel partial sums of this chunk (fixed-order smem reduction)
+    if (threadIdx.x == 0) { part[0] = s1; part[1] = s2; }
     *reinterpret_cast<float4*>(&smg[threadIdx.x * 4]) = dg;
     *reinterpret_cast<float4*>(&smb[threadIdx.x * 4]) = db;
-    __syncthreads();
+    cluster.sync();
+    if (threadIdx.x < chunks * 2) {
+        const int c = threadIdx.x >> 1, k = threadIdx.x & 1;
+        all[c][k] = cluster.map_shared_rank(part, c)[k];
+    }
+    // per-channel partial sums of this chunk (fixed-order smem reduction) -> global rows for the affine gradients
     for (int c = threadIdx.x; c < cg; c += GN_NT) {
         const int ccv = c >> 2, comp = c & 3, rp = GN_NT / cg4;
         float a = 0.f, bsum = 0.f;
@@ -467,10 +485,17 @@ __global__ void __launch_bounds__(GN_NT) gn_bwd_fused_kernel(const float* __rest
         const size_t o = ((size_t)b * chunks + chunk) * C + g * cg + c;
         dgpart[o] = a; dbpart[o] = bsum;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, c = 0.f;
+        for (int k = 0; k < chunks; ++k) { a += all[k][0]; c += all[k][1]; }
+        sm[0] = a; sm[1] = c;
+    }
+    __syncthreads();
     const float invN = 1.0f / ((float)HW * (float)cg);
     const float m1 = sm[0] * invN, m2 = sm[1] * invN;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < GN_VMAX; ++i) {
         int idx = threadIdx.x + i * GN_NT;
         if (idx < nvec) {
             int row = idx / cg4;
@@ -495,26 +520,26 @@ __global__ void __launch_bounds__(GN_NT) gn_bwd_fused_kernel(const float* __rest
         const int nrows = B * chunks;
         for (int c = threadIdx.x; c < cg; c += GN_NT) {
             float a = 0.f, bsum = 0.f;
+#pragma unroll 4
             for (int r = 0; r < nrows; ++r) { a += __ldcg(dgpart + (size_t)r * C + g * cg + c); bsum += __ldcg(dbpart + (size_t)r * C + g * cg + c); }
             dgamma[g * cg + c] += a; dbeta[g * cg + c] += bsum;
         }
     }
+    cluster.sync();                                        // peers may still be reading `part`
 }
 
 int gn_bwd_fused(const float* dout, const float* mask_src, const float* y, const float* stats, const float* gamma, float* dy,
                  float* dgamma, float* dbeta, float* partial, int B, int HW, int C, cudaStream_t st) {
-    if (C % 16 != 0 || 256 % (C / 16) != 0 || C / GN_G > GN_BUDGET || B * GN_G > 256) return DBOA_ERR_SHAPE;
-    const int chunks = gn_chunks(HW, C);
-    float* spart = partial;
-    float* dgpart = partial + (size_t)B * GN_G * chunks * 2;
-    float* dbpart = dgpart + (size_t)B * chunks * C;
-    unsigned* cnt = sync_words(SYNC_GNB_CNT);
+    if (C % 16 != 0 || 256 % (C / 16) != 0) return DBOA_ERR_SHAPE;
+    const GnPlan pl = gn_plan(HW, C);
+    if (pl.chunks > GN_MAXCL) return DBOA_ERR_SHAPE;
+    float* dgpart = partial;
+    float* dbpart = partial + (size_t)B * pl.chunks * C;
+    unsigned* cnt = sync_words(SYNC_GNB_PCNT);
     if (!cnt) return DBOA_ERR_CUDA;
-    dim3 grid(chunks, GN_G, B);
-    gn_bwd_fused_kernel<<<grid, GN_NT, 0, st>>>(dout, mask_src, y, stats, gamma, dy, dgamma, dbeta, spart, dgpart, dbpart,
-                                                reinterpret_cast<float*>(sync_words(SYNC_GNB_SUMS)), cnt, sync_words(SYNC_GNB_FLAG),
-                                                sync_words(SYNC_GNB_PCNT), HW, C, gn_rows(C), ++g_generation);
-    return check_launch();
+    dim3 grid(pl.chunks, GN_G, B);
+    return launch_x_cluster(gn_bwd_fused_kernel, grid, st, dout, mask_src, y, stats, gamma, dy, dgamma, dbeta, dgpart, dbpart, cnt, HW, C,
+                            pl.rows);
 }
 
 // ---------------------------------------------------------------------------------------------
