@@ -333,11 +333,15 @@ static int pick_split(int tiles, int kiters) {
 template <typename K, typename... Args>
 static int launch_z_cluster(K kernel, dim3 grid, cudaStream_t st, Args... args) {
     if (grid.z > 8) {
-        static bool allowed = false;       // per kernel instantiation
-        if (!allowed) {
+        // non-portable cluster sizes (9..16) must be enabled per kernel FUNCTION (several kernels share this template's type)
+        static const void* enabled[16];
+        static int n_enabled = 0;
+        bool seen = false;
+        for (int i = 0; i < n_enabled; ++i) seen = seen || (enabled[i] == (const void*)kernel);
+        if (!seen) {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             if (e != cudaSuccess) { g_last_cuda_error = (int)e; return DBOA_ERR_CUDA; }
-            allowed = true;
+            if (n_enabled < 16) enabled[n_enabled++] = (const void*)kernel;
         }
     }
     cudaLaunchConfig_t cfg = {};
