@@ -18,6 +18,7 @@ namespace cg = cooperative_groups;
 namespace dboa {
 
 constexpr int BM = 64, BN = 64, BK = 16, NT = 256, PADM = 4;
+constexpr int PF = 4;      // slabs of operand loads kept in flight per thread
 
 // One BK-deep slab of the 64x64 tile product; thread (tx,ty) owns a 4x4 micro-tile.
 __device__ __forceinline__ void mma_slab(const float (*As)[BM + PADM], const float (*Bs)[BN + PADM], int tx, int ty,
@@ -149,17 +150,27 @@ __global__ void __launch_bounds__(NT) conv_fwd_kernel(const float* __restrict__ 
         }
         bv = ldg4(wrow + k);                  // rows are zero padded up to Kpitch >= roundup16(K)
     };
+    // register pipeline, PF slabs deep: at batch 1 the weight-streaming layers are bound by memory latency per CTA,
+    // so several slabs of loads stay in flight while one slab is multiplied (profiles/r01_summary.md)
     float acc[4][4] = {};
-    float av[4];
-    float4 bv;
-    if (kbeg < kend) fetch(kbeg, av, bv);
-    for (int k0 = kbeg; k0 < kend; k0 += BK) {
-        __syncthreads();
-        As[lkv + 0][lrow] = av[0]; As[lkv + 1][lrow] = av[1]; As[lkv + 2][lrow] = av[2]; As[lkv + 3][lrow] = av[3];
-        Bs[lkv + 0][lrow] = bv.x; Bs[lkv + 1][lrow] = bv.y; Bs[lkv + 2][lrow] = bv.z; Bs[lkv + 3][lrow] = bv.w;
-        __syncthreads();
-        if (k0 + BK < kend) fetch(k0 + BK, av, bv);       // in flight while the slab below is multiplied
-        mma_slab(As, Bs, tx, ty, acc);
+    float av[PF][4];
+    float4 bv[PF];
+#pragma unroll
+    for (int f = 0; f < PF; ++f)
+        if (kbeg + f * BK < kend) fetch(kbeg + f * BK, av[f], bv[f]);
+    for (int k0 = kbeg; k0 < kend; k0 += PF * BK) {
+#pragma unroll
+        for (int f = 0; f < PF; ++f) {
+            const int kk = k0 + f * BK;
+            if (kk < kend) {
+                __syncthreads();
+                As[lkv + 0][lrow] = av[f][0]; As[lkv + 1][lrow] = av[f][1]; As[lkv + 2][lrow] = av[f][2]; As[lkv + 3][lrow] = av[f][3];
+                Bs[lkv + 0][lrow] = bv[f].x; Bs[lkv + 1][lrow] = bv[f].y; Bs[lkv + 2][lrow] = bv[f].z; Bs[lkv + 3][lrow] = bv[f].w;
+                __syncthreads();
+                if (kk + PF * BK < kend) fetch(kk + PF * BK, av[f], bv[f]);
+                mma_slab(As, Bs, tx, ty, acc);
+            }
+        }
     }
     cluster_reduce_store(acc, red, out, M, d.Cout, m0, n0, d.Cout, tx, ty, 0);
 }
@@ -216,15 +227,23 @@ __global__ void __launch_bounds__(NT) conv_dgrad_kernel(const float* __restrict_
         }
     };
     float acc[4][4] = {};
-    float4 av, bv;
-    if (kbeg < kend) fetch(kbeg, av, bv);
-    for (int k0 = kbeg; k0 < kend; k0 += BK) {
-        __syncthreads();
-        As[lkv + 0][lrow] = av.x; As[lkv + 1][lrow] = av.y; As[lkv + 2][lrow] = av.z; As[lkv + 3][lrow] = av.w;
-        *reinterpret_cast<float4*>(&Bs[bk][bnv]) = bv;
-        __syncthreads();
-        if (k0 + BK < kend) fetch(k0 + BK, av, bv);
-        mma_slab(As, Bs, tx, ty, acc);
+    float4 av[PF], bv[PF];
+#pragma unroll
+    for (int f = 0; f < PF; ++f)
+        if (kbeg + f * BK < kend) fetch(kbeg + f * BK, av[f], bv[f]);
+    for (int k0 = kbeg; k0 < kend; k0 += PF * BK) {
+#pragma unroll
+        for (int f = 0; f < PF; ++f) {
+            const int kk = k0 + f * BK;
+            if (kk < kend) {
+                __syncthreads();
+                As[lkv + 0][lrow] = av[f].x; As[lkv + 1][lrow] = av[f].y; As[lkv + 2][lrow] = av[f].z; As[lkv + 3][lrow] = av[f].w;
+                *reinterpret_cast<float4*>(&Bs[bk][bnv]) = bv[f];
+                __syncthreads();
+                if (kk + PF * BK < kend) fetch(kk + PF * BK, av[f], bv[f]);
+                mma_slab(As, Bs, tx, ty, acc);
+            }
+        }
     }
     cluster_reduce_store(acc, red, out, M, d.Cin, m0, n0, d.Cin, tx, ty, accumulate);
 }
@@ -285,16 +304,24 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const float* __restrict_
         }
     };
     float acc[4][4] = {};
-    float4 av;
-    float bv[4];
-    if (pbeg < pend) fetch(pbeg, av, bv);
-    for (int p0 = pbeg; p0 < pend; p0 += BK) {
-        __syncthreads();
-        *reinterpret_cast<float4*>(&As[lk][lv]) = av;
-        *reinterpret_cast<float4*>(&Bs[lk][lv]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
-        __syncthreads();
-        if (p0 + BK < pend) fetch(p0 + BK, av, bv);
-        mma_slab(As, Bs, tx, ty, acc);
+    float4 av[PF];
+    float bv[PF][4];
+#pragma unroll
+    for (int f = 0; f < PF; ++f)
+        if (pbeg + f * BK < pend) fetch(pbeg + f * BK, av[f], bv[f]);
+    for (int p0 = pbeg; p0 < pend; p0 += PF * BK) {
+#pragma unroll
+        for (int f = 0; f < PF; ++f) {
+            const int pp = p0 + f * BK;
+            if (pp < pend) {
+                __syncthreads();
+                *reinterpret_cast<float4*>(&As[lk][lv]) = av[f];
+                *reinterpret_cast<float4*>(&Bs[lk][lv]) = make_float4(bv[f][0], bv[f][1], bv[f][2], bv[f][3]);
+                __syncthreads();
+                if (pp + PF * BK < pend) fetch(pp + PF * BK, av[f], bv[f]);
+                mma_slab(As, Bs, tx, ty, acc);
+            }
+        }
     }
     // rows = co, cols = n'; the weight gradient always accumulates (+=) into the gradient arena
     cluster_reduce_store(acc, red, out, d.Cout, d.Kpitch, m0, n0, K, tx, ty, 1);

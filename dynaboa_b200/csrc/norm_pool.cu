@@ -340,7 +340,7 @@ static int launch_x_cluster(K kernel, dim3 grid, cudaStream_t st, Args... args) 
 }
 
 // grid (chunks, 4, B), cluster (chunks, 1, 1)
-__global__ void __launch_bounds__(GN_NT) gn_fwd_fused_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(GN_NT, 2) gn_fwd_fused_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const float* __restrict__ res,
                                                              float* __restrict__ out, float* __restrict__ stats, int HW, int C, int R,
                                                              int relu) {
@@ -354,16 +354,26 @@ __global__ void __launch_bounds__(GN_NT) gn_fwd_fused_kernel(const float* __rest
     const int r0 = chunk * R, rows = min(R, HW - r0);
     const int nvec = rows * cg4;
     const size_t base = ((size_t)b * HW + r0) * C + g * cg;
-    float4 v[GN_VMAX];
+    // every independent global load is issued up front (input slab, residual slab, affine parameters) so that the
+    // kernel pays ONE memory round trip before its reductions
+    const int cvf = threadIdx.x % cg4;                     // 256 % cg4 == 0: the channel vector is fixed per thread
+    const float4 ga = ldg4(gamma + g * cg + cvf * 4), be = ldg4(beta + g * cg + cvf * 4);
+    float4 v[GN_VMAX], rr[GN_VMAX];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < GN_VMAX; ++i) {
         int idx = threadIdx.x + i * GN_NT;
         if (idx < nvec) {
-            int row = idx / cg4, cv = idx - row * cg4;
-            v[i] = ldg4(y + base + (size_t)row * C + cv * 4);
-            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            int row = idx / cg4;
+            const size_t e = base + (size_t)row * C + cvf * 4;
+            v[i] = ldg4(y + e);
+            if (res != nullptr) rr[i] = ldg4(res + e);
         }
+    }
+#pragma unroll
+    for (int i = 0; i < GN_VMAX; ++i) {
+        int idx = threadIdx.x + i * GN_NT;
+        if (idx < nvec) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
     const float cnt = (float)(rows * cg);
     const float cmean = block_sum(s, red) / cnt;
@@ -398,8 +408,6 @@ __global__ void __launch_bounds__(GN_NT) gn_fwd_fused_kernel(const float* __rest
     }
     __syncthreads();
     const float mean = sm[0], rstd = sm[1];
-    const int cvf = threadIdx.x % cg4;                     // 256 % cg4 == 0: the channel vector is fixed per thread
-    const float4 ga = ldg4(gamma + g * cg + cvf * 4), be = ldg4(beta + g * cg + cvf * 4);
 #pragma unroll
     for (int i = 0; i < GN_VMAX; ++i) {
         int idx = threadIdx.x + i * GN_NT;
@@ -409,7 +417,7 @@ __global__ void __launch_bounds__(GN_NT) gn_fwd_fused_kernel(const float* __rest
             float4 o;
             o.x = (v[i].x - mean) * rstd * ga.x + be.x; o.y = (v[i].y - mean) * rstd * ga.y + be.y;
             o.z = (v[i].z - mean) * rstd * ga.z + be.z; o.w = (v[i].w - mean) * rstd * ga.w + be.w;
-            if (res != nullptr) { float4 r = ldg4(res + e); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+            if (res != nullptr) { o.x += rr[i].x; o.y += rr[i].y; o.z += rr[i].z; o.w += rr[i].w; }
             if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             *reinterpret_cast<float4*>(out + e) = o;
         }
