@@ -180,6 +180,8 @@ def run_ours(args, rank, world, local):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     lib = _lib.load()
+    if args.tc >= 0:
+        lib.dboa_set_tensor_core_conv(args.tc)
     work = tempfile.mkdtemp(prefix=f'dboa_bench_r{rank}_')
     synthetic.write_asset_dir(os.path.join(work, 'data'))
     config.set_data_root(os.path.join(work, 'data'))
@@ -312,6 +314,7 @@ def main():
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--cpu-frames', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--tc', type=int, default=-1, help='tensor-core conv mode override (0 fp32 CUDA cores, 1 forward, 2 forward+backward)')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

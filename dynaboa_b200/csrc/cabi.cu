@@ -100,6 +100,21 @@ int dboa_conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin
     conv_tc_set_workspace(ws, ws ? (size_t)ws_floats : 0);
     return conv1x1_tc_fwd(x, w, y, M, Cin, Cout, ST(stream));
 }
+int dboa_conv2d_tc_fwd(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
+                       int Kpitch, dboa_stream_t stream) {
+    if (!x || !w || !y) return DBOA_ERR_ARG;
+    return conv_tc_fwd(x, w, y, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), ST(stream));
+}
+int dboa_conv2d_tc_dgrad(const float* dy, const float* w, float* dx, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
+                         int Kpitch, int accumulate, dboa_stream_t stream) {
+    if (!dy || !w || !dx) return DBOA_ERR_ARG;
+    return conv_tc_dgrad(dy, w, dx, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), accumulate, ST(stream));
+}
+int dboa_conv2d_tc_wgrad(const float* dy, const float* x, float* dw, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
+                         int Kpitch, dboa_stream_t stream) {
+    if (!dy || !x || !dw) return DBOA_ERR_ARG;
+    return conv_tc_wgrad(dy, x, dw, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), ST(stream));
+}
 long long dboa_gn_partial_floats(int B, int HW, int C) { return (long long)gn_partial_floats(B, HW, C); }
 long long dboa_gn_bwd_partial_floats(int B, int HW, int C) { return (long long)gn_bwd_partial_floats(B, HW, C); }
 int dboa_groupnorm_fwd(const float* y, const float* gamma, const float* beta, const float* residual, float* out, float* stats, float* partial,

@@ -1,44 +1,62 @@
-// tcgen05 (5th-generation tensor core) path for GEMM-shaped convolutions: 1x1 / stride-1 convolutions of the
-// backbone, i.e.  Y[M][N] = X[M][K] * W[N][K]^T  with M = B*H*W pixels, K = Cin, N = Cout, all fp32 K-major.
+// tcgen05 (5th-generation tensor core) implicit-GEMM convolution: forward, data gradient and weight gradient of
+// every backbone convolution with Cin % 64 == 0 and Cout % 64 == 0 (all but the 7x7 stem).
 //
-// Precision: `tcgen05.mma.kind::tf32` with a 3-term split.  Every operand value x is split by the loader
-// warps into hi = x with the low 13 mantissa bits cleared (exactly a TF32 number, so the tensor core's own
-// fp32->tf32 conversion is the identity) and lo = x - hi (exact in fp32); the accumulator receives
+//   FWD   : Y [m=(b,ho,wo)][n=co]      = sum_{k=(tap,ci)} Xcol[m][k]  * W[co][k]
+//   DGRAD : dX[m=(b,hi,wi)][n=ci]   (+)= sum_{k=(tap,co)} dYcol[m][k] * W[co][tap][ci]
+//   WGRAD : dW[m=co][n=(tap,ci)]      += sum_{k=pixel}    dY[pix][co] * Xcol[pix][(tap,ci)]
+// activations NHWC, weights [Cout][kh][kw][Cin] (row pitch == kh*kw*Cin).
+//
+// Precision: `tcgen05.mma.kind::tf32` with a 3-term split.  Every operand value x is split by the loader threads
+// into hi = x with the low 13 mantissa bits cleared (exactly a TF32 number, so the tensor core's own fp32->tf32
+// conversion is the identity) and lo = x - hi (exact in fp32); the accumulator receives
 //   Ah*Bh + Ah*Bl + Al*Bh      (the dropped Al*Bl term is ~2^-22 relative)
-// in fp32 inside TMEM, which keeps the result within ~1e-6 of the exact-fp32 CUDA-core path (conv.cu), against
+// in fp32 inside TMEM, which keeps the result within ~2e-6 of the exact-fp32 CUDA-core path (conv.cu), against
 // which this kernel is validated on the device (tests/test_gpu_tc.py).  SURVEY.md §7 "hard part 1".
 //
-// Structure (one CTA = 128 threads, one 128 x BN output tile, BK = 32 per stage, 2 stages):
-//   all threads : coalesced float4 loads of the X / W sub-tiles -> hi/lo split in registers -> st.shared into the
-//                 UMMA canonical K-major no-swizzle layout (8-row x 16-byte core matrices)
-//   thread 0    : 12 x tcgen05.mma (4 k-steps of 8 x 3 products) per stage, tcgen05.commit -> mbarrier of the stage
-//   epilogue    : tcgen05.ld (32 lanes x 32 columns per warp) -> registers -> global (or split-K partial) stores
-// Accumulators live in TMEM (BN columns x 128 lanes), never in registers.
+// Structure (one CTA = 128 threads, one 128 x 64 output tile, 32 reduction elements per k-block):
+//   loaders  : 12 float4 global loads per thread and k-block (8 for the 128-row operand, 4 for the 64-row operand),
+//              im2col / transposed-filter / pixel-major gathers computed on the fly with zero fill, issued TWO k-blocks
+//              ahead in registers; hi/lo are split in registers and stored into the UMMA canonical K-major no-swizzle
+//              layout (8-row x 16-byte core matrices) of one of 2 shared-memory stages.  Operands whose memory order
+//              is reduction-minor (K-major) are stored with float4; the others are transposed by the store.
+//   thread 0 : 12 x tcgen05.mma (4 k-steps of 8 x 3 products) per stage, tcgen05.commit -> mbarrier of the stage.
+//   epilogue : tcgen05.ld (32 lanes x 32 columns per warp) -> registers.  Split-K runs across a thread-block cluster
+//              (1,1,nz): partial tiles are parked in shared memory and each CTA sums a band of 128/nz rows over its
+//              peers through distributed shared memory in the fixed order z = 0..nz-1 (deterministic).
+// Accumulators live in TMEM (64 columns x 128 lanes), never in registers.
+#include <cooperative_groups.h>
 #include <stdint.h>
 
 #include "common.cuh"
 #include "kernels.h"
 
+namespace cg = cooperative_groups;
+
 namespace dboa {
 
-static int g_tc_mode = 0;          // 0 = off, 1 = on, 2 = on with LBO/SBO roles swapped (bring-up aid)
+static int g_tc_mode = 0;          // 0 = off, 1 = forward on tensor cores, 2 = forward + backward on tensor cores
 bool conv_tc_enabled() { return g_tc_mode != 0; }
-void conv_tc_set_enabled(bool on) { g_tc_mode = on ? 1 : 0; }
+bool conv_tc_bwd_enabled() { return g_tc_mode >= 2; }
+void conv_tc_set_enabled(bool on) { g_tc_mode = on ? 2 : 0; }
 void conv_tc_set_mode(int mode) { g_tc_mode = mode; }
+void conv_tc_set_workspace(float*, size_t) {}
 
 namespace tc {
 
-constexpr int BM = 128, BK = 32, NT = 128, STAGES = 2;
-constexpr uint32_t CORE_BYTES = 128;                 // one 8 x 16B core matrix
-constexpr uint32_t KCHUNKS = BK / 4;                 // 16-byte chunks along K per stage (8)
-constexpr uint32_t GROUP_BYTES = KCHUNKS * CORE_BYTES;   // one 8-row group of a stage tile (1024 B)
+enum { FWD = 0, DGRAD = 1, WGRAD = 2 };
+constexpr int BM = 128, BN = 64, BK = 32, NT = 128, STAGES = 2;
+constexpr uint32_t CORE_BYTES = 128;                     // one 8 x 16B core matrix
+constexpr uint32_t GROUP_BYTES = (BK / 4) * CORE_BYTES;  // one 8-row group of a stage tile (1024 B)
+constexpr uint32_t A_TILE = BM * BK * 4, B_TILE = BN * BK * 4;
+constexpr int RED_LD = BN + 4;                           // padded row pitch of the split-K partial tile (bank-conflict free)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     // cute::UMMA::SmemDescriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | layout_type=0 (no swizzle)
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+    // K-major: LBO = byte step between the two 16-byte k-chunks of one MMA, SBO = byte step between 8-row groups
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((CORE_BYTES >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((GROUP_BYTES >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
 
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -72,39 +90,53 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// split a float4 into (hi, lo) and store both at byte offset `off` of the hi / lo stage tiles
-__device__ __forceinline__ void split_store(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, float4 v) {
-    float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// K-major source: 4 consecutive reduction elements of one row -> one float4 slot of the canonical layout
+__device__ __forceinline__ void split_store4(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, float4 v) {
+    float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
     *reinterpret_cast<float4*>(hi_tile + off) = h;
-    *reinterpret_cast<float4*>(lo_tile + off) = l;
+    *reinterpret_cast<float4*>(lo_tile + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+// row-minor source: 4 consecutive ROWS (row0 % 4 == 0) at one reduction index k -> 4 scalar slots (transposing store)
+__device__ __forceinline__ void split_store_t(uint8_t* hi_tile, uint8_t* lo_tile, int row0, int k, float4 v) {
+    const uint32_t off = (uint32_t)(row0 >> 3) * GROUP_BYTES + (uint32_t)(k >> 2) * CORE_BYTES + (uint32_t)(row0 & 7) * 16 + (uint32_t)(k & 3) * 4;
+    const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float h = tf32_hi(x[e]);
+        *reinterpret_cast<float*>(hi_tile + off + e * 16) = h;
+        *reinterpret_cast<float*>(lo_tile + off + e * 16) = x[e] - h;
+    }
 }
 
-template <int BN>
 struct Smem {
-    // stage tiles in UMMA canonical layout: [row_group][k_chunk][8 rows][16 B]
-    alignas(128) uint8_t a_hi[STAGES][BM * BK * 4];
-    alignas(128) uint8_t a_lo[STAGES][BM * BK * 4];
-    alignas(128) uint8_t b_hi[STAGES][BN * BK * 4];
-    alignas(128) uint8_t b_lo[STAGES][BN * BK * 4];
+    // stage tiles in UMMA canonical layout: [row_group][k_chunk][8 rows][16 B]; after the last MMA the A tiles are
+    // re-used as the 128 x RED_LD fp32 partial tile of the cluster split-K reduction
+    alignas(128) uint8_t a_hi[STAGES][A_TILE];
+    alignas(128) uint8_t a_lo[STAGES][A_TILE];
+    alignas(128) uint8_t b_hi[STAGES][B_TILE];
+    alignas(128) uint8_t b_lo[STAGES][B_TILE];
     alignas(8) uint64_t mma_done[STAGES];
     uint32_t tmem_base;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(NT) gemm_tf32x3_kernel(const float* __restrict__ X, const float* __restrict__ W, float* __restrict__ Y,
-                                                         int M, int N, int K, int kb_per_split, int swap_lbo_sbo) {
+// P: the operand that pairs with the weights in FWD/DGRAD (x or dy); Q: weights (FWD/DGRAD) or x (WGRAD, with P = dy)
+template <int MODE>
+__global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict__ P, const float* __restrict__ Q, float* __restrict__ O,
+                                                         ConvDims d, int kb_per_split, int accumulate) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    Smem<BN>& sm = *reinterpret_cast<Smem<BN>*>(smem_raw);
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int Ktaps = d.kh * d.kw, Kfull = Ktaps * d.Cin;
+    // GEMM extents of this mode
+    const int Mrows = MODE == FWD ? d.B * d.Ho * d.Wo : (MODE == DGRAD ? d.B * d.Hi * d.Wi : d.Cout);
+    const int ldo = MODE == FWD ? d.Cout : (MODE == DGRAD ? d.Cin : Kfull);
+    const int Kred = MODE == FWD ? Kfull : (MODE == DGRAD ? Ktaps * d.Cout : d.B * d.Ho * d.Wo);
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    const int nkb_total = K / BK;
+    const int nkb_total = (Kred + BK - 1) / BK;
     const int kb_begin = blockIdx.z * kb_per_split;
-    const int kb_end = min(kb_begin + kb_per_split, nkb_total);
-    const int nkb = kb_end - kb_begin;
+    const int nkb = max(0, min(kb_begin + kb_per_split, nkb_total) - kb_begin);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&sm.mma_done[s], 1);
@@ -118,125 +150,273 @@ __global__ void __launch_bounds__(NT) gemm_tf32x3_kernel(const float* __restrict
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = sm.tmem_base;
-
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N>>3, M>>4
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    const uint32_t lbo = swap_lbo_sbo ? GROUP_BYTES : CORE_BYTES;
-    const uint32_t sbo = swap_lbo_sbo ? CORE_BYTES : GROUP_BYTES;
 
-    for (int it = 0; it < nkb; ++it) {
-        const int s = it & 1;
-        if (it >= STAGES) mbar_wait(&sm.mma_done[s], (uint32_t)(((it >> 1) - 1) & 1));   // stage buffers free again
-        const int k0 = (kb_begin + it) * BK;
-        // ---- A (activations): 128 x 32 floats = 1024 float4, 8 per thread
-#pragma unroll
-        for (int j = 0; j < (BM * BK / 4) / NT; ++j) {
-            const int idx = tid + NT * j;
-            const int i = idx & 7, c = (idx >> 3) & 7, g = idx >> 6;
-            const int row = m0 + g * 8 + i;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < M) v = ldg4(X + (size_t)row * K + k0 + c * 4);
-            split_store(sm.a_hi[s], sm.a_lo[s], g * GROUP_BYTES + c * CORE_BYTES + i * 16, v);
-        }
-        // ---- B (weights): BN x 32 floats
-#pragma unroll
-        for (int j = 0; j < (BN * BK / 4) / NT; ++j) {
-            const int idx = tid + NT * j;
-            const int i = idx & 7, c = (idx >> 3) & 7, g = idx >> 6;
-            float4 v = ldg4(W + (size_t)(n0 + g * 8 + i) * K + k0 + c * 4);
-            split_store(sm.b_hi[s], sm.b_lo[s], g * GROUP_BYTES + c * CORE_BYTES + i * 16, v);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async-proxy (UMMA) reads
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t ah = smem_u32(sm.a_hi[s]), al = smem_u32(sm.a_lo[s]);
-            const uint32_t bh = smem_u32(sm.b_hi[s]), bl = smem_u32(sm.b_lo[s]);
-#pragma unroll
-            for (int kk = 0; kk < BK / 8; ++kk) {
-                const uint32_t koff = kk * 2 * CORE_BYTES;                 // 8 tf32 = two 16-byte chunks along K
-                const uint64_t dah = make_desc(ah + koff, lbo, sbo), dal = make_desc(al + koff, lbo, sbo);
-                const uint64_t dbh = make_desc(bh + koff, lbo, sbo), dbl = make_desc(bl + koff, lbo, sbo);
-                mma_tf32(tmem_d, dah, dbh, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                mma_tf32(tmem_d, dah, dbl, idesc, 1u);
-                mma_tf32(tmem_d, dal, dbh, idesc, 1u);
-            }
-            umma_commit(&sm.mma_done[s]);        // arrives when every MMA issued so far has completed
+    // ---- per-thread loader state
+    // FWD / DGRAD: the 128-row operand is pixel-major: thread t owns tile row t and its whole 32-float k-block
+    const int arow = m0 + tid;
+    bool avalid = false;
+    int ph = 0, pw = 0;                                // FWD: hi0, wi0 (top-left of the window); DGRAD: hi, wi
+    const float* pb = P;
+    if (MODE != WGRAD) {
+        const int HW = MODE == FWD ? d.Ho * d.Wo : d.Hi * d.Wi, Wd = MODE == FWD ? d.Wo : d.Wi;
+        avalid = arow < Mrows;
+        if (avalid) {
+            const int b = arow / HW, rem = arow - b * HW;
+            const int h = rem / Wd, w_ = rem - h * Wd;
+            if (MODE == FWD) { ph = h * d.stride - d.pad; pw = w_ * d.stride - d.pad; pb = P + (size_t)b * d.Hi * d.Wi * d.Cin; }
+            else { ph = h; pw = w_; pb = P + (size_t)b * d.Ho * d.Wo * d.Cout; }
         }
     }
-    // the last commit covers all MMAs of this CTA
-    if (nkb > 0) {
+    const uint32_t a_off = (uint32_t)(tid >> 3) * GROUP_BYTES + (uint32_t)(tid & 7) * 16;      // + c * CORE_BYTES  (row t, K-major)
+    // FWD: weight tile is K-major: half a weight row (4 chunks) per thread
+    const int brow = tid >> 1, bc0 = (tid & 1) * 4;
+    const uint32_t b_off = (uint32_t)(brow >> 3) * GROUP_BYTES + (uint32_t)(brow & 7) * 16;
+    // WGRAD: column tile -> (tap, ci0)
+    const int wtap = MODE == WGRAD ? n0 / d.Cin : 0, wci0 = MODE == WGRAD ? n0 - wtap * d.Cin : 0;
+    const int wr = wtap / d.kw, wsx = wtap - wr * d.kw;
+
+    auto fetch = [&](int kb, float4 (&ra)[8], float4 (&rb)[4]) {
+        const int k0 = kb * BK;
+        if (MODE == FWD) {
+            const int tap = k0 / d.Cin, ci0 = k0 - tap * d.Cin;
+            const int r = tap / d.kw, s = tap - r * d.kw;
+            const int hi = ph + r, wi = pw + s;
+            const bool inb = avalid && (unsigned)hi < (unsigned)d.Hi && (unsigned)wi < (unsigned)d.Wi;
+            const float* src = pb + ((size_t)hi * d.Wi + wi) * d.Cin + ci0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ra[c] = inb ? ldg4(src + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* wrow = Q + (size_t)(n0 + brow) * Kfull + k0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) rb[c] = ldg4(wrow + (bc0 + c) * 4);
+        } else if (MODE == DGRAD) {
+            const int tap = k0 / d.Cout, co0 = k0 - tap * d.Cout;
+            const int r = tap / d.kw, s = tap - r * d.kw;
+            const int th = ph + d.pad - r, tw = pw + d.pad - s;
+            bool inb = avalid && th >= 0 && tw >= 0;
+            int ho = 0, wo = 0;
+            if (inb) {
+                ho = th / d.stride; wo = tw / d.stride;
+                inb = (ho * d.stride == th) && (wo * d.stride == tw) && ho < d.Ho && wo < d.Wo;
+            }
+            const float* src = pb + ((size_t)ho * d.Wo + wo) * d.Cout + co0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ra[c] = inb ? ldg4(src + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // B[n=ci][k=co] = W[co][tap][ci]: rows of 64 consecutive ci, one row per co (transposed by the store)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = tid + NT * j, k = idx >> 4, nv = idx & 15;
+                rb[j] = ldg4(Q + (size_t)(co0 + k) * Kfull + (size_t)tap * d.Cin + n0 + nv * 4);
+            }
+        } else {
+            // A'[m=co][k=pix] = dY[pix][co]: rows of 128 consecutive co, one row per pixel (transposed by the store)
+            const int Mpix = Kred;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int idx = tid + NT * j, k = idx >> 5, cv = idx & 31;
+                const int pix = k0 + k, co = m0 + cv * 4;
+                ra[j] = (pix < Mpix && co < d.Cout) ? ldg4(P + (size_t)pix * d.Cout + co) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            // B'[n=ci][k=pix] = X[pixel shifted by the tap][ci0 + n]
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = tid + NT * j, k = idx >> 4, nv = idx & 15;
+                const int pix = k0 + k;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pix < Mpix) {
+                    const int b = pix / (d.Ho * d.Wo), rem = pix - b * d.Ho * d.Wo;
+                    const int ho = rem / d.Wo, wo = rem - ho * d.Wo;
+                    const int hi = ho * d.stride - d.pad + wr, wi = wo * d.stride - d.pad + wsx;
+                    if ((unsigned)hi < (unsigned)d.Hi && (unsigned)wi < (unsigned)d.Wi)
+                        v = ldg4(Q + (((size_t)b * d.Hi + hi) * d.Wi + wi) * d.Cin + wci0 + nv * 4);
+                }
+                rb[j] = v;
+            }
+        }
+    };
+    auto stash = [&](int s, const float4 (&ra)[8], const float4 (&rb)[4]) {
+        if (MODE != WGRAD) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) split_store4(sm.a_hi[s], sm.a_lo[s], a_off + c * CORE_BYTES, ra[c]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int idx = tid + NT * j;
+                split_store_t(sm.a_hi[s], sm.a_lo[s], (idx & 31) * 4, idx >> 5, ra[j]);
+            }
+        }
+        if (MODE == FWD) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) split_store4(sm.b_hi[s], sm.b_lo[s], b_off + (bc0 + c) * CORE_BYTES, rb[c]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = tid + NT * j;
+                split_store_t(sm.b_hi[s], sm.b_lo[s], (idx & 15) * 4, idx >> 4, rb[j]);
+            }
+        }
+    };
+
+    float4 ra[2][8], rb[2][4];
+    if (nkb > 0) fetch(kb_begin, ra[0], rb[0]);
+    if (nkb > 1) fetch(kb_begin + 1, ra[1], rb[1]);
+    for (int it0 = 0; it0 < nkb; it0 += 2) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            const int it = it0 + f;
+            if (it < nkb) {
+                const int s = f;                                                                  // stage == register set
+                if (it >= STAGES) mbar_wait(&sm.mma_done[s], (uint32_t)(((it >> 1) - 1) & 1));   // stage buffers free again
+                stash(s, ra[f], rb[f]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async-proxy (UMMA) reads
+                __syncthreads();
+                if (it + 2 < nkb) fetch(kb_begin + it + 2, ra[f], rb[f]);          // in flight behind the MMAs below
+                if (tid == 0) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t ah = smem_u32(sm.a_hi[s]), al = smem_u32(sm.a_lo[s]);
+                    const uint32_t bh = smem_u32(sm.b_hi[s]), bl = smem_u32(sm.b_lo[s]);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 8; ++kk) {
+                        const uint32_t koff = kk * 2 * CORE_BYTES;                 // 8 tf32 = two 16-byte chunks along K
+                        const uint64_t dah = make_desc(ah + koff), dal = make_desc(al + koff);
+                        const uint64_t dbh = make_desc(bh + koff), dbl = make_desc(bl + koff);
+                        mma_tf32(tmem_d, dah, dbh, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                        mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                        mma_tf32(tmem_d, dal, dbh, idesc, 1u);
+                    }
+                    umma_commit(&sm.mma_done[s]);        // arrives when every MMA issued so far has completed
+                }
+            }
+        }
+    }
+    if (nkb > 0) {                                        // the last commit covers all MMAs of this CTA
         const int last = nkb - 1;
         mbar_wait(&sm.mma_done[last & 1], (uint32_t)((last >> 1) & 1));
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: thread t owns accumulator lane (= output row) t; 32 columns per tcgen05.ld
-    const int row = m0 + tid;
-    float* out = Y + (size_t)blockIdx.z * M * N;
+    // ---- epilogue: thread t owns accumulator lane (= output row) t
+    const int nz = gridDim.z;
+    const int orow = m0 + tid;
+    float* red = reinterpret_cast<float*>(sm.a_hi[0]);    // 128 rows x RED_LD floats (34 KB) over the A tiles, free after the last MMA
 #pragma unroll
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
-        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < M && nkb > 0) {
-            float4* dst = reinterpret_cast<float4*>(out + (size_t)row * N + n0 + c0);
+        if (nkb > 0) {
+            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) r[q] = 0u;
+        }
+        if (nz == 1) {
+            if (orow < Mrows) {
+                float4* dst = reinterpret_cast<float4*>(O + (size_t)orow * ldo + n0 + c0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 v = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
+                                           __uint_as_float(r[q * 4 + 3]));
+                    if (accumulate) { const float4 c = dst[q]; v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w; }
+                    dst[q] = v;
+                }
+            }
+        } else {
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-                dst[q] = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
-                                     __uint_as_float(r[q * 4 + 3]));
+                *reinterpret_cast<float4*>(red + tid * RED_LD + c0 + q * 4) =
+                    make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
+                                __uint_as_float(r[q * 4 + 3]));
         }
+    }
+    if (nz > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();
+        const int rank = (int)cluster.block_rank();
+        const int rows_per = BM / nz;                                 // nz is a power of two <= 16
+        for (int v = tid; v < rows_per * (BN / 4); v += NT) {
+            const int lr = rank * rows_per + v / (BN / 4), c4 = (v % (BN / 4)) * 4;
+            const int row = m0 + lr;
+            if (row >= Mrows) continue;
+            float4* dst = reinterpret_cast<float4*>(O + (size_t)row * ldo + n0 + c4);
+            float4 sacc = accumulate ? *dst : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int z = 0; z < nz; ++z) {
+                const float* peer = cluster.map_shared_rank(red, z);
+                const float4 q = *reinterpret_cast<const float4*>(peer + lr * RED_LD + c4);
+                sacc.x += q.x; sacc.y += q.y; sacc.z += q.z; sacc.w += q.w;
+            }
+            *dst = sacc;
+        }
+        cluster.sync();                                               // peers may still be reading this CTA's tile
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
 }
 
-}  // namespace tc
-
-static float* g_tc_ws = nullptr;           // split-K workspace handed over by the plan
-static size_t g_tc_ws_floats = 0;
-void conv_tc_set_workspace(float* ws, size_t floats) { g_tc_ws = ws; g_tc_ws_floats = floats; }
-
-int conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin, int Cout, cudaStream_t st) {
-    using namespace tc;
-    constexpr int BN = 64;
-    if (g_tc_mode == 0 || Cin % BK != 0 || Cout % BN != 0 || M < 1) return DBOA_ERR_UNSUPPORTED;
-    const int nkb = Cin / BK;
-    const int tiles = ceil_div(M, BM) * (Cout / BN);
+template <int MODE>
+static int launch(const float* p, const float* q, float* o, const ConvDims& d, int rows, int cols, int kred, int accumulate, cudaStream_t st) {
+    const int nkb = (kred + BK - 1) / BK;
+    const int tiles = ceil_div(rows, BM) * (cols / BN);
     int ns = 1;
-    if (tiles < 148 && nkb >= 8 && g_tc_ws != nullptr) {
-        ns = (296 + tiles - 1) / tiles;
-        if (ns > nkb / 4) ns = nkb / 4;
-        while (ns > 1 && (size_t)ns * M * Cout > g_tc_ws_floats) --ns;
-        if (ns < 1) ns = 1;
-    }
-    int per = (nkb + ns - 1) / ns;
-    ns = (nkb + per - 1) / per;
-    static bool attr_set = false;
-    const size_t smem = sizeof(Smem<BN>) + 128;
+    while (ns < 16 && tiles * ns * 2 <= 296 + tiles && nkb / (ns * 2) >= 2) ns *= 2;
+    const int per = (nkb + ns - 1) / ns;
+    static bool attr_set = false;                     // one flag per MODE instantiation
+    const size_t smem = sizeof(Smem) + 128;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_tf32x3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tf32x3_kernel<MODE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) { g_last_cuda_error = (int)e; return DBOA_ERR_CUDA; }
         attr_set = true;
     }
-    dim3 grid(ceil_div(M, BM), Cout / BN, ns);
-    gemm_tf32x3_kernel<BN><<<grid, NT, smem, st>>>(x, w, ns > 1 ? g_tc_ws : y, M, Cout, Cin, per, g_tc_mode == 2 ? 1 : 0);
-    DBOA_TRY(check_launch());
-    if (ns > 1) {
-        DBOA_TRY(splitk_reduce(g_tc_ws, y, (size_t)M * Cout, ns, 0, st));
-    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ceil_div(rows, BM), cols / BN, ns);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = ns;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tf32x3_kernel<MODE>, p, q, o, d, per, accumulate);
+    ++g_launch_count;
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return DBOA_ERR_CUDA; }
     return DBOA_OK;
+}
+
+static bool shape_ok(const ConvDims& d) {
+    return d.Cin % 64 == 0 && d.Cout % 64 == 0 && d.Kpitch == d.kh * d.kw * d.Cin;
+}
+
+}  // namespace tc
+
+int conv_tc_fwd(const float* x, const float* w, float* y, const ConvDims& d, cudaStream_t st) {
+    if (g_tc_mode == 0 || !tc::shape_ok(d)) return DBOA_ERR_UNSUPPORTED;
+    return tc::launch<tc::FWD>(x, w, y, d, d.B * d.Ho * d.Wo, d.Cout, d.kh * d.kw * d.Cin, 0, st);
+}
+int conv_tc_dgrad(const float* dy, const float* w, float* dx, const ConvDims& d, int accumulate, cudaStream_t st) {
+    if (g_tc_mode < 2 || !tc::shape_ok(d)) return DBOA_ERR_UNSUPPORTED;
+    return tc::launch<tc::DGRAD>(dy, w, dx, d, d.B * d.Hi * d.Wi, d.Cin, d.kh * d.kw * d.Cout, accumulate, st);
+}
+int conv_tc_wgrad(const float* dy, const float* x, float* dw, const ConvDims& d, cudaStream_t st) {
+    if (g_tc_mode < 2 || !tc::shape_ok(d)) return DBOA_ERR_UNSUPPORTED;
+    return tc::launch<tc::WGRAD>(dy, x, dw, d, d.Cout, d.kh * d.kw * d.Cin, d.B * d.Ho * d.Wo, 1, st);
+}
+
+int conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin, int Cout, cudaStream_t st) {
+    ConvDims d;
+    d.B = 1; d.Hi = M; d.Wi = 1; d.Cin = Cin; d.Ho = M; d.Wo = 1; d.Cout = Cout; d.kh = 1; d.kw = 1; d.stride = 1; d.pad = 0; d.Kpitch = Cin;
+    return conv_tc_fwd(x, w, y, d, st);
 }
 
 }  // namespace dboa

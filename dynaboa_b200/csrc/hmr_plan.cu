@@ -186,6 +186,11 @@ struct Scratch {
     }
 };
 
+static ConvDims dims_of(const ConvLayer& c, int B);
+// backward convolutions: tcgen05 implicit GEMM when enabled and the shape is taken, else the fp32 CUDA-core kernels
+static int conv_backward_data(const ConvLayer& c, int B, const float* dy, const float* w, float* dx, int accumulate, float* ws, cudaStream_t st);
+static int conv_backward_weight(const ConvLayer& c, int B, const float* dy, const float* x, float* dw, float* ws, cudaStream_t st);
+
 static ConvDims dims_of(const ConvLayer& c, int B) {
     ConvDims d;
     d.B = B; d.Hi = c.hin; d.Wi = c.hin; d.Cin = c.cin; d.Ho = c.hout; d.Wo = c.hout; d.Cout = c.cout;
@@ -193,13 +198,28 @@ static ConvDims dims_of(const ConvLayer& c, int B) {
     return d;
 }
 
-// conv forward with the tensor-core path for plain GEMM shapes (1x1, stride 1) when enabled
+// conv forward: tcgen05 implicit GEMM when enabled and the shape is taken (Cin % 32 == 0), else the fp32 CUDA-core kernel
 static int conv_forward(const ConvLayer& c, int B, const float* x, const float* w, float* y, float* ws, cudaStream_t st) {
-    if (c.k == 1 && c.stride == 1 && conv_tc_enabled()) {
-        int s = conv1x1_tc_fwd(x, w, y, B * c.hout * c.hout, c.cin, c.cout, st);
+    if (conv_tc_enabled()) {
+        int s = conv_tc_fwd(x, w, y, dims_of(c, B), st);
         if (s != DBOA_ERR_UNSUPPORTED) return s;
     }
     return conv_fwd(x, w, y, dims_of(c, B), ws, (size_t)kConvWs, st);
+}
+
+static int conv_backward_data(const ConvLayer& c, int B, const float* dy, const float* w, float* dx, int accumulate, float* ws, cudaStream_t st) {
+    if (conv_tc_bwd_enabled()) {
+        int s = conv_tc_dgrad(dy, w, dx, dims_of(c, B), accumulate, st);
+        if (s != DBOA_ERR_UNSUPPORTED) return s;
+    }
+    return conv_dgrad(dy, w, dx, dims_of(c, B), accumulate, ws, (size_t)kConvWs, st);
+}
+static int conv_backward_weight(const ConvLayer& c, int B, const float* dy, const float* x, float* dw, float* ws, cudaStream_t st) {
+    if (conv_tc_bwd_enabled()) {
+        int s = conv_tc_wgrad(dy, x, dw, dims_of(c, B), st);
+        if (s != DBOA_ERR_UNSUPPORTED) return s;
+    }
+    return conv_wgrad(dy, x, dw, dims_of(c, B), ws, (size_t)kConvWs, st);
 }
 
 __global__ void head_init_kernel(const float* __restrict__ ip, const float* __restrict__ is, const float* __restrict__ ic,
@@ -384,19 +404,19 @@ int hmr_backward(const float* P, const float* T, int B, int masked_in, const flo
         if (b.cd >= 0) {
             const ConvLayer& cd = n.convs[b.cd];
             DBOA_TRY(gnb(b.cd, dOut, a3, sc.t2));
-            DBOA_TRY(conv_wgrad(sc.t2, xin, G + cd.w_off, dims_of(cd, B), sc.ws, (size_t)kConvWs, st));
-            DBOA_TRY(conv_dgrad(sc.t2, P + cd.w_off, dIn, dims_of(cd, B), 0, sc.ws, (size_t)kConvWs, st));
+            DBOA_TRY(conv_backward_weight(cd, B, sc.t2, xin, G + cd.w_off, sc.ws, st));
+            DBOA_TRY(conv_backward_data(cd, B, sc.t2, P + cd.w_off, dIn, 0, sc.ws, st));
         } else {
             DBOA_TRY(relu_mask(dOut, a3, dIn, (size_t)B * c3.hout * c3.hout * c3.cout, st));
         }
-        DBOA_TRY(conv_wgrad(sc.t1, T + t.conv[b.c2].a, G + c3.w_off, dims_of(c3, B), sc.ws, (size_t)kConvWs, st));
-        DBOA_TRY(conv_dgrad(sc.t1, P + c3.w_off, sc.t3, dims_of(c3, B), 0, sc.ws, (size_t)kConvWs, st));
+        DBOA_TRY(conv_backward_weight(c3, B, sc.t1, T + t.conv[b.c2].a, G + c3.w_off, sc.ws, st));
+        DBOA_TRY(conv_backward_data(c3, B, sc.t1, P + c3.w_off, sc.t3, 0, sc.ws, st));
         DBOA_TRY(gnb(b.c2, sc.t3, T + t.conv[b.c2].a, sc.t1));
-        DBOA_TRY(conv_wgrad(sc.t1, T + t.conv[b.c1].a, G + c2.w_off, dims_of(c2, B), sc.ws, (size_t)kConvWs, st));
-        DBOA_TRY(conv_dgrad(sc.t1, P + c2.w_off, sc.t2, dims_of(c2, B), 0, sc.ws, (size_t)kConvWs, st));
+        DBOA_TRY(conv_backward_weight(c2, B, sc.t1, T + t.conv[b.c1].a, G + c2.w_off, sc.ws, st));
+        DBOA_TRY(conv_backward_data(c2, B, sc.t1, P + c2.w_off, sc.t2, 0, sc.ws, st));
         DBOA_TRY(gnb(b.c1, sc.t2, T + t.conv[b.c1].a, sc.t3));
-        DBOA_TRY(conv_wgrad(sc.t3, xin, G + c1.w_off, dims_of(c1, B), sc.ws, (size_t)kConvWs, st));
-        DBOA_TRY(conv_dgrad(sc.t3, P + c1.w_off, dIn, dims_of(c1, B), 1, sc.ws, (size_t)kConvWs, st));
+        DBOA_TRY(conv_backward_weight(c1, B, sc.t3, xin, G + c1.w_off, sc.ws, st));
+        DBOA_TRY(conv_backward_data(c1, B, sc.t3, P + c1.w_off, dIn, 1, sc.ws, st));
         float* tmp = dOut; dOut = dIn; dIn = tmp;
     }
     // ---- stem: maxpool, GroupNorm+ReLU, conv (weight gradient only; the image needs none)

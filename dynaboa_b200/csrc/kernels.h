@@ -16,6 +16,10 @@ int conv_dgrad(const float* dy, const float* w, float* dx, const ConvDims& d, in
 int conv_wgrad(const float* dy, const float* x, float* dw, const ConvDims& d, float* ws, size_t ws_floats, cudaStream_t st);
 
 // ---- conv_tc.cu (tcgen05 TF32x3 GEMM for 1x1 / stride-1 convolutions); returns DBOA_ERR_UNSUPPORTED when the shape is not taken
+int conv_tc_fwd(const float* x, const float* w, float* y, const ConvDims& d, cudaStream_t st);
+int conv_tc_dgrad(const float* dy, const float* w, float* dx, const ConvDims& d, int accumulate, cudaStream_t st);
+int conv_tc_wgrad(const float* dy, const float* x, float* dw, const ConvDims& d, cudaStream_t st);
+bool conv_tc_bwd_enabled();
 int conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin, int Cout, cudaStream_t st);
 bool conv_tc_enabled();
 void conv_tc_set_enabled(bool on);

@@ -30,7 +30,7 @@ typedef void* dboa_stream_t;
 const char* dboa_version(void);
 int dboa_last_cuda_error(void);            /* cudaError_t of the last failed launch */
 long long dboa_launch_count(void);         /* kernels launched by this library so far */
-int dboa_set_tensor_core_conv(int enable); /* 1: tcgen05 TF32x3 path for eligible convs (default), 0: fp32 CUDA-core path */
+int dboa_set_tensor_core_conv(int mode);   /* 0: fp32 CUDA-core convs; 1: tcgen05 TF32x3 forward; 2: tcgen05 forward + dgrad + wgrad */
 
 /* ---- HMR regressor: parameter arena and tape layout ----------------------------------------
  * replaces: model/hmr.py:67-124 (HMR.__init__/_make_layer state_dict contract).
@@ -68,6 +68,14 @@ int dboa_conv2d_wgrad(const float* dy, const float* x, float* dw, int B, int Hi,
  * needs dboa_set_tensor_core_conv(1); returns DBOA_ERR_UNSUPPORTED for shapes it does not take (Cin % 32, Cout % 64) */
 int dboa_conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin, int Cout, float* ws, long long ws_floats,
                         dboa_stream_t stream);
+/* general convolution forward as a tcgen05 TF32x3 implicit GEMM (same arguments as dboa_conv2d_fwd; Cin % 32 == 0) */
+int dboa_conv2d_tc_fwd(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
+                       int Kpitch, dboa_stream_t stream);
+/* data / weight gradient on the same tensor-core kernel (dboa_set_tensor_core_conv(2)); dw is accumulated (+=) */
+int dboa_conv2d_tc_dgrad(const float* dy, const float* w, float* dx, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
+                         int Kpitch, int accumulate, dboa_stream_t stream);
+int dboa_conv2d_tc_wgrad(const float* dy, const float* x, float* dw, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
+                         int Kpitch, dboa_stream_t stream);
 /* replaces: nn.GroupNorm(4, C) + ReLU (+ residual) forward / backward (model/hmr.py:14-18,40-60) */
 long long dboa_gn_partial_floats(int B, int HW, int C);
 long long dboa_gn_bwd_partial_floats(int B, int HW, int C);
