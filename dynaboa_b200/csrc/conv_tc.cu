@@ -34,7 +34,7 @@ namespace cg = cooperative_groups;
 
 namespace dboa {
 
-static int g_tc_mode = 0;          // 0 = off, 1 = forward on tensor cores, 2 = forward + backward on tensor cores
+static int g_tc_mode = 1;          // 0 = fp32 CUDA cores, 1 = forward on tensor cores (default), 2 = forward + backward on tensor cores
 bool conv_tc_enabled() { return g_tc_mode != 0; }
 bool conv_tc_bwd_enabled() { return g_tc_mode >= 2; }
 void conv_tc_set_enabled(bool on) { g_tc_mode = on ? 2 : 0; }

@@ -159,7 +159,7 @@ static const Tape& tape_for(int B) {
 static const long long kConvWs = 8LL << 20;    // split-K workspace (floats)
 
 struct Scratch {
-    float *ws, *g0, *g1, *t1, *t2, *t3, *gnp, *dP, *dy_dec, *d_h2, *d_h1, *dxc, *dxf, *tmp1024, *lin_ws;
+    float *ws, *g0, *g1, *t1, *t2, *t3, *t4, *t5, *t6, *gnp, *dP, *dy_dec, *d_h2, *d_h1, *dxc, *dxf, *tmp1024, *lin_ws;
     long long total;
     long long lin_ws_floats;
     Scratch(float* base, int B) {
@@ -167,7 +167,7 @@ struct Scratch {
         long long off = 0;
         auto take = [&](long long cnt) { float* p = base ? base + off : nullptr; off = align32(off + cnt); return p; };
         ws = take(kConvWs);
-        g0 = take(S); g1 = take(S); t1 = take(S); t2 = take(S); t3 = take(S);
+        g0 = take(S); g1 = take(S); t1 = take(S); t2 = take(S); t3 = take(S); t4 = take(S); t5 = take(S); t6 = take(S);
         long long gmax = 0;
         for (const ConvLayer& c : net().convs) {
             long long v = (long long)gn_bwd_partial_floats(B, c.hout * c.hout, c.cout);
@@ -185,6 +185,36 @@ struct Scratch {
         total = off;
     }
 };
+
+// Weight gradients run on a library-owned side stream: every wgrad only needs (dy of its layer, the saved input
+// activation) and writes its own slice of the gradient arena, so the chain  gn_bwd -> dgrad -> gn_bwd -> ...  on the
+// caller's stream never waits for them.  At batch 1 each kernel fills a fraction of the 148 SMs, and the two chains
+// overlap.  Buffers read by a pending wgrad are protected by per-buffer events; the side stream is joined before return.
+struct BwdAsync {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_ready[8];      // main -> side: "dy is ready" (ring)
+    cudaEvent_t ev_read[8];       // side -> main: "buffer k has been read"
+    cudaEvent_t ev_join;
+    bool pending[8];
+    int ring = 0;
+    bool ok = false;
+    bool init() {
+        if (ok) return true;
+        if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) return false;
+        for (int i = 0; i < 8; ++i) {
+            if (cudaEventCreateWithFlags(&ev_ready[i], cudaEventDisableTiming) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&ev_read[i], cudaEventDisableTiming) != cudaSuccess) return false;
+            pending[i] = false;
+        }
+        if (cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) return false;
+        ok = true;
+        return true;
+    }
+};
+static BwdAsync g_async;
+// DBOA_ASYNC_WGRAD=0 in the environment keeps everything on the caller's stream (A/B measurements, debugging)
+static bool g_async_enabled = [] { const char* e = getenv("DBOA_ASYNC_WGRAD"); return !(e && e[0] == '0'); }();
+void hmr_set_async_wgrad(bool on) { g_async_enabled = on; }
 
 static ConvDims dims_of(const ConvLayer& c, int B);
 // backward convolutions: tcgen05 implicit GEMM when enabled and the shape is taken, else the fp32 CUDA-core kernels
@@ -390,39 +420,71 @@ int hmr_backward(const float* P, const float* T, int B, int masked_in, const flo
     float* dOut = sc.g0;
     float* dIn = sc.g1;
     DBOA_TRY(avgpool_bwd(sc.dxf, 2048, dOut, B, 49, 2048, st));
+    float* const tmp[6] = {sc.t1, sc.t2, sc.t3, sc.t4, sc.t5, sc.t6};
+    const bool async = g_async_enabled && g_async.init();
+    BwdAsync& A = g_async;
+    if (async) {                                   // the side stream starts after everything enqueued so far
+        for (int i = 0; i < 8; ++i) A.pending[i] = false;
+        cudaEventRecord(A.ev_ready[A.ring], st);
+        cudaStreamWaitEvent(A.side, A.ev_ready[A.ring], 0);
+        A.ring = (A.ring + 1) & 7;
+    }
+    // before the main chain overwrites temp k: wait for the weight-gradient kernel that still reads it
+    auto claim = [&](int k) {
+        if (async && A.pending[k]) { cudaStreamWaitEvent(st, A.ev_read[k], 0); A.pending[k] = false; }
+        return tmp[k];
+    };
     auto gnb = [&](int ci, const float* dout, const float* mask_src, float* dy) {
         const ConvLayer& c = n.convs[ci];
         return gn_bwd_fused(dout, mask_src, T + t.conv[ci].y, T + t.conv[ci].stats, P + c.g_off, dy, G + c.g_off, G + c.b_off, sc.gnp, B,
-                      c.hout * c.hout, c.cout, st);
+                            c.hout * c.hout, c.cout, st);
+    };
+    // weight gradient of conv `c` from dy held in temp k
+    auto wgrad = [&](const ConvLayer& c, int k, const float* xin_) {
+        if (!async) return conv_backward_weight(c, B, tmp[k], xin_, G + c.w_off, sc.ws, st);
+        cudaEventRecord(A.ev_ready[A.ring], st);
+        cudaStreamWaitEvent(A.side, A.ev_ready[A.ring], 0);
+        A.ring = (A.ring + 1) & 7;
+        int s_ = conv_backward_weight(c, B, tmp[k], xin_, G + c.w_off, sc.ws, A.side);
+        cudaEventRecord(A.ev_read[k], A.side);
+        A.pending[k] = true;
+        return s_;
     };
     for (int bi = (int)n.blocks.size() - 1; bi >= 0; --bi) {
         const Block& b = n.blocks[bi];
         const ConvLayer &c1 = n.convs[b.c1], &c2 = n.convs[b.c2], &c3 = n.convs[b.c3];
         const float* xin = bi == 0 ? T + t.p0 : T + t.conv[n.blocks[bi - 1].c3].a;
         const float* a3 = T + t.conv[b.c3].a;
-        DBOA_TRY(gnb(b.c3, dOut, a3, sc.t1));
+        // temps: 0 = dy3, 1 = dy_downsample, 2 = da2, 3 = dy2, 4 = da1, 5 = dy1
+        DBOA_TRY(gnb(b.c3, dOut, a3, claim(0)));
+        DBOA_TRY(wgrad(c3, 0, T + t.conv[b.c2].a));
         if (b.cd >= 0) {
             const ConvLayer& cd = n.convs[b.cd];
-            DBOA_TRY(gnb(b.cd, dOut, a3, sc.t2));
-            DBOA_TRY(conv_backward_weight(cd, B, sc.t2, xin, G + cd.w_off, sc.ws, st));
-            DBOA_TRY(conv_backward_data(cd, B, sc.t2, P + cd.w_off, dIn, 0, sc.ws, st));
+            DBOA_TRY(gnb(b.cd, dOut, a3, claim(1)));
+            DBOA_TRY(wgrad(cd, 1, xin));
+            DBOA_TRY(conv_backward_data(cd, B, tmp[1], P + cd.w_off, dIn, 0, sc.ws, st));
         } else {
             DBOA_TRY(relu_mask(dOut, a3, dIn, (size_t)B * c3.hout * c3.hout * c3.cout, st));
         }
-        DBOA_TRY(conv_backward_weight(c3, B, sc.t1, T + t.conv[b.c2].a, G + c3.w_off, sc.ws, st));
-        DBOA_TRY(conv_backward_data(c3, B, sc.t1, P + c3.w_off, sc.t3, 0, sc.ws, st));
-        DBOA_TRY(gnb(b.c2, sc.t3, T + t.conv[b.c2].a, sc.t1));
-        DBOA_TRY(conv_backward_weight(c2, B, sc.t1, T + t.conv[b.c1].a, G + c2.w_off, sc.ws, st));
-        DBOA_TRY(conv_backward_data(c2, B, sc.t1, P + c2.w_off, sc.t2, 0, sc.ws, st));
-        DBOA_TRY(gnb(b.c1, sc.t2, T + t.conv[b.c1].a, sc.t3));
-        DBOA_TRY(conv_backward_weight(c1, B, sc.t3, xin, G + c1.w_off, sc.ws, st));
-        DBOA_TRY(conv_backward_data(c1, B, sc.t3, P + c1.w_off, dIn, 1, sc.ws, st));
-        float* tmp = dOut; dOut = dIn; dIn = tmp;
+        DBOA_TRY(conv_backward_data(c3, B, tmp[0], P + c3.w_off, claim(2), 0, sc.ws, st));
+        DBOA_TRY(gnb(b.c2, tmp[2], T + t.conv[b.c2].a, claim(3)));
+        DBOA_TRY(wgrad(c2, 3, T + t.conv[b.c1].a));
+        DBOA_TRY(conv_backward_data(c2, B, tmp[3], P + c2.w_off, claim(4), 0, sc.ws, st));
+        DBOA_TRY(gnb(b.c1, tmp[4], T + t.conv[b.c1].a, claim(5)));
+        DBOA_TRY(wgrad(c1, 5, xin));
+        DBOA_TRY(conv_backward_data(c1, B, tmp[5], P + c1.w_off, dIn, 1, sc.ws, st));
+        float* sw = dOut; dOut = dIn; dIn = sw;
     }
     // ---- stem: maxpool, GroupNorm+ReLU, conv (weight gradient only; the image needs none)
     DBOA_TRY(maxpool3x3s2_bwd(dOut, reinterpret_cast<const unsigned char*>(T + t.p0_idx), dIn, B, 112, 112, 64, st));
-    DBOA_TRY(gnb(0, dIn, T + t.conv[0].a, sc.t1));
-    return conv_wgrad(sc.t1, T + t.x0, G + n.convs[0].w_off, dims_of(n.convs[0], B), sc.ws, (size_t)kConvWs, st);
+    DBOA_TRY(gnb(0, dIn, T + t.conv[0].a, claim(0)));
+    int rc = conv_wgrad(tmp[0], T + t.x0, G + n.convs[0].w_off, dims_of(n.convs[0], B), sc.ws, (size_t)kConvWs, st);
+    if (async) {                                   // join: nothing of this call is left running when the caller's stream continues
+        cudaEventRecord(A.ev_join, A.side);
+        cudaStreamWaitEvent(st, A.ev_join, 0);
+        for (int i = 0; i < 8; ++i) A.pending[i] = false;
+    }
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------

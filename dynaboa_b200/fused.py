@@ -13,11 +13,22 @@ What changes relative to the autograd path (``Adaptor.adaptation``), none of it 
   launch; the only host syncs are retrieval's cluster index and the ``dynamic_boa`` decision.
 """
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib, hmr as hmr_mod, losses
 from ._lib import ptr, stream
+
+
+_SIDE = {}
+_TEACHER_OVERLAP = os.environ.get('DBOA_TEACHER_STREAM', '1') != '0'     # 0: teacher forward on the caller's stream
+
+
+def _side_stream(device):
+    if device.index not in _SIDE:
+        _SIDE[device.index] = torch.cuda.Stream(device=device)
+    return _SIDE[device.index]
 
 
 class _Pred:
@@ -102,6 +113,19 @@ def level_backward(ad, arena, buffers, image, kp, lower, grad_arena, main=None):
     use_temporal = o.use_temporal_losses_lower if lower else o.use_temporal_losses_upper
     motion = bool(use_temporal and o.use_motion and (ad.global_step - o.interval) > 0)
     hist = None
+    # the teacher forward is independent of the fast-weight forward: issue it on a side stream so that the two chains
+    # of small, latency-bound kernels overlap on the GPU (each one alone leaves most SMs idle at batch 1)
+    tpred, side = None, None
+    if use_temporal and o.use_meanteacher:
+        teacher = ad.teacher
+        if _TEACHER_OVERLAP:
+            cur = torch.cuda.current_stream()
+            side = _side_stream(image.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                tpred = forward_graph(ad, teacher.arena, teacher._buffers, image, teacher._masks(nb, image.device))
+        else:
+            tpred = forward_graph(ad, teacher.arena, teacher._buffers, image, teacher._masks(nb, image.device))
     if motion:
         hist_image, hist_kp = ad.get_hist()
         if main is None:
@@ -114,9 +138,13 @@ def level_backward(ad, arena, buffers, image, kp, lower, grad_arena, main=None):
     targets = {}
     if use_frame:
         w[0], w[1], w[2] = o.s2dloss_weight, o.shape_prior_weight, o.pose_prior_weight
-    if use_temporal and o.use_meanteacher:
-        teacher = ad.teacher
-        t = forward_graph(ad, teacher.arena, teacher._buffers, image, teacher._masks(nb, image.device))
+    if tpred is not None:
+        t = tpred
+        if side is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(side)
+            for ten in (t.p2d, t.joints, t.shape, t.rot, t.tape, t.verts, t.smpl_tape, t.cam):
+                ten.record_stream(cur)
         tw = o.teacherloss_weight
         w[3], w[4], w[5], w[6] = 5 * tw, 5 * tw, 0.001 * tw, 1 * tw
         targets = dict(t_p2d=t.p2d, t_j3d=t.joints, t_beta=t.shape, t_R=t.rot)

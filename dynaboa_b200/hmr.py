@@ -80,8 +80,9 @@ def tape_floats(B):
 
 
 def scratch_for(B, device):
-    """Per-(device, B) scratch shared by forward split-K and backward; stream-ordered reuse is safe."""
-    key = (device.index, B)
+    """Per-(device, B, stream) scratch shared by forward and backward; stream-ordered reuse is safe, and forwards
+    issued concurrently on different streams (teacher next to the fast-weight forward) get separate buffers."""
+    key = (device.index, B, torch.cuda.current_stream(device).cuda_stream)
     if key not in _SCRATCH:
         _SCRATCH[key] = torch.empty(_lib.load().dboa_hmr_scratch_floats(B), dtype=torch.float32, device=device)
     return _SCRATCH[key]
