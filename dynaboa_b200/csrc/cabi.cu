@@ -119,7 +119,7 @@ long long dboa_gn_partial_floats(int B, int HW, int C) { return (long long)gn_pa
 long long dboa_gn_bwd_partial_floats(int B, int HW, int C) { return (long long)gn_bwd_partial_floats(B, HW, C); }
 int dboa_groupnorm_fwd(const float* y, const float* gamma, const float* beta, const float* residual, float* out, float* stats, float* partial,
                        int B, int HW, int C, int relu, dboa_stream_t stream) {
-    if (!y || !gamma || !beta || !out || !stats || !partial) return DBOA_ERR_ARG;
+    if (!y || !gamma || !beta || !out || !stats) return DBOA_ERR_ARG;       // `partial` may be NULL: dboa_gn_partial_floats() is 0
     return gn_fwd_fused(y, gamma, beta, residual, out, stats, partial, B, HW, C, relu, ST(stream));
 }
 int dboa_groupnorm_bwd(const float* dout, const float* mask_src, const float* y, const float* stats, const float* gamma, float* dy,

@@ -6,8 +6,8 @@
 //
 // This is the exact-fp32 path: it is the numerical reference the tcgen05 TF32x3 path
 // (conv_tc.cu) is checked against on the GPU, and it serves the shapes that path does not
-// take (Cin = 3 stem, odd tiles).  Split-K is deterministic: partial tiles go to a workspace
-// and are summed in a fixed order by `splitk_reduce_kernel`.
+// take (Cin = 3 stem, odd tiles).  Split-K is deterministic: the K slices of a tile form a cluster
+// whose partial tiles are summed in a fixed order through distributed shared memory (cluster_reduce_store).
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -155,6 +155,8 @@ __global__ void __launch_bounds__(NT) conv_fwd_kernel(const float* __restrict__ 
     float acc[4][4] = {};
     float av[PF][4];
     float4 bv[PF];
+    pdl_wait();                             // index set-up above overlaps the previous kernel's tail
+    pdl_trigger();
 #pragma unroll
     for (int f = 0; f < PF; ++f)
         if (kbeg + f * BK < kend) fetch(kbeg + f * BK, av[f], bv[f]);
@@ -228,6 +230,8 @@ __global__ void __launch_bounds__(NT) conv_dgrad_kernel(const float* __restrict_
     };
     float acc[4][4] = {};
     float4 av[PF], bv[PF];
+    pdl_wait();                             // index set-up above overlaps the previous kernel's tail
+    pdl_trigger();
 #pragma unroll
     for (int f = 0; f < PF; ++f)
         if (kbeg + f * BK < kend) fetch(kbeg + f * BK, av[f], bv[f]);
@@ -306,6 +310,8 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const float* __restrict_
     float acc[4][4] = {};
     float4 av[PF];
     float bv[PF][4];
+    pdl_wait();                             // index set-up above overlaps the previous kernel's tail
+    pdl_trigger();
 #pragma unroll
     for (int f = 0; f < PF; ++f)
         if (pbeg + f * BK < pend) fetch(pbeg + f * BK, av[f], bv[f]);
@@ -327,24 +333,6 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const float* __restrict_
     cluster_reduce_store(acc, red, out, d.Cout, d.Kpitch, m0, n0, K, tx, ty, 1);
 }
 
-// out[i] = (accumulate ? out[i] : 0) + sum_z part[z][i]   (fixed order => deterministic)
-__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, size_t n4, int nsplit, int accumulate) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    float4 s = accumulate ? reinterpret_cast<float4*>(out)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int z = 0; z < nsplit; ++z) {
-        float4 v = reinterpret_cast<const float4*>(part)[(size_t)z * n4 + i];
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
-    reinterpret_cast<float4*>(out)[i] = s;
-}
-
-int splitk_reduce(const float* part, float* out, size_t n, int nsplit, int accumulate, cudaStream_t st) {
-    size_t n4 = n / 4;
-    splitk_reduce_kernel<<<ceil_div(n4, 256), 256, 0, st>>>(part, out, n4, nsplit, accumulate);
-    return check_launch();
-}
-
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
@@ -359,28 +347,7 @@ static int pick_split(int tiles, int kiters) {
 
 template <typename K, typename... Args>
 static int launch_z_cluster(K kernel, dim3 grid, cudaStream_t st, Args... args) {
-    if (grid.z > 8) {
-        // non-portable cluster sizes (9..16) must be enabled per kernel FUNCTION (several kernels share this template's type)
-        static const void* enabled[16];
-        static int n_enabled = 0;
-        bool seen = false;
-        for (int i = 0; i < n_enabled; ++i) seen = seen || (enabled[i] == (const void*)kernel);
-        if (!seen) {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-            if (e != cudaSuccess) { g_last_cuda_error = (int)e; return DBOA_ERR_CUDA; }
-            if (n_enabled < 16) enabled[n_enabled++] = (const void*)kernel;
-        }
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = grid.z;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
-    ++g_launch_count;
-    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return DBOA_ERR_CUDA; }
-    return DBOA_OK;
+    return launch_ex(kernel, grid, dim3(NT), 0, st, dim3(1, 1, grid.z), true, args...);
 }
 
 int conv_fwd(const float* x, const float* w, float* y, const ConvDims& d, float* ws, size_t ws_floats, cudaStream_t st) {

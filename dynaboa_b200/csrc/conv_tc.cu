@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
     const int wtap = MODE == WGRAD ? n0 / d.Cin : 0, wci0 = MODE == WGRAD ? n0 - wtap * d.Cin : 0;
     const int wr = wtap / d.kw, wsx = wtap - wr * d.kw;
 
-    auto fetch = [&](int kb, float4 (&ra)[8], float4 (&rb)[4]) {
+    auto fetch = [&](int kb, float4 (&ra)[8], float4 (&rb)[4], bool do_a, bool do_b) {
         const int k0 = kb * BK;
         if (MODE == FWD) {
             const int tap = k0 / d.Cin, ci0 = k0 - tap * d.Cin;
@@ -185,11 +185,15 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
             const int hi = ph + r, wi = pw + s;
             const bool inb = avalid && (unsigned)hi < (unsigned)d.Hi && (unsigned)wi < (unsigned)d.Wi;
             const float* src = pb + ((size_t)hi * d.Wi + wi) * d.Cin + ci0;
+            if (do_a) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) ra[c] = inb ? ldg4(src + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = 0; c < 8; ++c) ra[c] = inb ? ldg4(src + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             const float* wrow = Q + (size_t)(n0 + brow) * Kfull + k0;
+            if (do_b) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) rb[c] = ldg4(wrow + (bc0 + c) * 4);
+                for (int c = 0; c < 4; ++c) rb[c] = ldg4(wrow + (bc0 + c) * 4);
+            }
         } else if (MODE == DGRAD) {
             const int tap = k0 / d.Cout, co0 = k0 - tap * d.Cout;
             const int r = tap / d.kw, s = tap - r * d.kw;
@@ -201,13 +205,17 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
                 inb = (ho * d.stride == th) && (wo * d.stride == tw) && ho < d.Ho && wo < d.Wo;
             }
             const float* src = pb + ((size_t)ho * d.Wo + wo) * d.Cout + co0;
+            if (do_a) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) ra[c] = inb ? ldg4(src + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = 0; c < 8; ++c) ra[c] = inb ? ldg4(src + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             // B[n=ci][k=co] = W[co][tap][ci]: rows of 64 consecutive ci, one row per co (transposed by the store)
+            if (do_b) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int idx = tid + NT * j, k = idx >> 4, nv = idx & 15;
-                rb[j] = ldg4(Q + (size_t)(co0 + k) * Kfull + (size_t)tap * d.Cin + n0 + nv * 4);
+                for (int j = 0; j < 4; ++j) {
+                    const int idx = tid + NT * j, k = idx >> 4, nv = idx & 15;
+                    rb[j] = ldg4(Q + (size_t)(co0 + k) * Kfull + (size_t)tap * d.Cin + n0 + nv * 4);
+                }
             }
         } else {
             // A'[m=co][k=pix] = dY[pix][co]: rows of 128 consecutive co, one row per pixel (transposed by the store)
@@ -258,9 +266,19 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
         }
     };
 
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, index set-up) and -- for the
+    // forward and data-gradient products -- the first WEIGHT tiles do not depend on the previous kernel in the stream
+    // and overlap its tail; activations are touched only after the wait.  (Weights are never written by the kernel
+    // that immediately precedes a convolution: optimizer updates are followed by a normally serialized launch.)
     float4 ra[2][8], rb[2][4];
-    if (nkb > 0) fetch(kb_begin, ra[0], rb[0]);
-    if (nkb > 1) fetch(kb_begin + 1, ra[1], rb[1]);
+    if (MODE != WGRAD) {
+        if (nkb > 0) fetch(kb_begin, ra[0], rb[0], false, true);
+        if (nkb > 1) fetch(kb_begin + 1, ra[1], rb[1], false, true);
+    }
+    pdl_wait();
+    pdl_trigger();
+    if (nkb > 0) fetch(kb_begin, ra[0], rb[0], true, MODE == WGRAD);
+    if (nkb > 1) fetch(kb_begin + 1, ra[1], rb[1], true, MODE == WGRAD);
     for (int it0 = 0; it0 < nkb; it0 += 2) {
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
@@ -271,7 +289,7 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
                 stash(s, ra[f], rb[f]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async-proxy (UMMA) reads
                 __syncthreads();
-                if (it + 2 < nkb) fetch(kb_begin + it + 2, ra[f], rb[f]);          // in flight behind the MMAs below
+                if (it + 2 < nkb) fetch(kb_begin + it + 2, ra[f], rb[f], true, true);          // in flight behind the MMAs below
                 if (tid == 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t ah = smem_u32(sm.a_hi[s]), al = smem_u32(sm.a_lo[s]);
@@ -371,27 +389,9 @@ static int launch(const float* p, const float* q, float* o, const ConvDims& d, i
     int ns = 1;
     while (ns < 16 && tiles * ns * 2 <= 296 + tiles && nkb / (ns * 2) >= 2) ns *= 2;
     const int per = (nkb + ns - 1) / ns;
-    static bool attr_set = false;                     // one flag per MODE instantiation
     const size_t smem = sizeof(Smem) + 128;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tf32x3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tf32x3_kernel<MODE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) { g_last_cuda_error = (int)e; return DBOA_ERR_CUDA; }
-        attr_set = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ceil_div(rows, BM), cols / BN, ns);
-    cfg.blockDim = dim3(NT);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = ns;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tf32x3_kernel<MODE>, p, q, o, d, per, accumulate);
-    ++g_launch_count;
-    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return DBOA_ERR_CUDA; }
-    return DBOA_OK;
+    return launch_ex(conv_tf32x3_kernel<MODE>, dim3(ceil_div(rows, BM), cols / BN, ns), dim3(NT), smem, st, dim3(1, 1, ns), true, p, q, o, d, per,
+                     accumulate);
 }
 
 static bool shape_ok(const ConvDims& d) {

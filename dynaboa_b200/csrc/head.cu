@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ mask, float* __restrict__ pre,
                                                          float* __restrict__ post, int ld_out, float* __restrict__ post2, int ld_out2,
                                                          int b0, int nb, int N, int K) {
+    pdl_wait();
+    pdl_trigger();
     const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (n >= N) return;
     const float* wr = W + (size_t)n * ldw;
@@ -69,9 +71,7 @@ int linear_fwd(const float* x, int ldx, const float* W, int ldw, const float* bi
     const int warps_per_block = 8;
     for (int b0 = 0; b0 < B; b0 += 8) {
         int nb = B - b0 < 8 ? B - b0 : 8;
-        linear_fwd_kernel<8><<<ceil_div(N, warps_per_block), 256, 0, st>>>(x, ldx, W, ldw, bias, addend, ld_add, mask, pre, post, ld_out,
-                                                                          post2, ld_out2, b0, nb, N, K);
-        DBOA_TRY(check_launch());
+        DBOA_TRY(launch_ex(linear_fwd_kernel<8>, dim3(ceil_div(N, warps_per_block)), dim3(256), 0, st, dim3(1, 1, 1), true, x, ldx, W, ldw, bias, addend, ld_add, mask, pre, post, ld_out, post2, ld_out2, b0, nb, N, K));
     }
     return DBOA_OK;
 }
@@ -81,6 +81,8 @@ int linear_fwd(const float* x, int ldx, const float* W, int ldw, const float* bi
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) linear_dgrad_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ W, int ldw,
                                                            float* __restrict__ part, int b0, int nb, int B, int N, int K, int nlen) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sdy[8][128];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int nbeg = blockIdx.y * nlen, nend = min(nbeg + nlen, N);
@@ -106,6 +108,8 @@ __global__ void __launch_bounds__(256) linear_dgrad_kernel(const float* __restri
 }
 
 __global__ void linear_dgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dx, int ldx, int B, int K, int nsplit) {
+    pdl_wait();
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * K) return;
     int b = i / K, k = i - b * K;
@@ -125,11 +129,9 @@ int linear_dgrad(const float* dy, int ldy, const float* W, int ldw, float* dx, i
     for (int b0 = 0; b0 < B; b0 += 8) {
         int nb = B - b0 < 8 ? B - b0 : 8;
         dim3 grid(ceil_div(K, 256), nsplit);
-        linear_dgrad_kernel<<<grid, 256, 0, st>>>(dy, ldy, W, ldw, ws, b0, nb, B, N, K, nlen);
-        DBOA_TRY(check_launch());
+        DBOA_TRY(launch_ex(linear_dgrad_kernel, dim3(grid), dim3(256), 0, st, dim3(1, 1, 1), true, dy, ldy, W, ldw, ws, b0, nb, B, N, K, nlen));
     }
-    linear_dgrad_reduce_kernel<<<ceil_div(B * K, 256), 256, 0, st>>>(ws, dx, ldx, B, K, nsplit);
-    return check_launch();
+    return launch_ex(linear_dgrad_reduce_kernel, dim3(ceil_div(B * K, 256)), dim3(256), 0, st, dim3(1, 1, 1), true, ws, dx, ldx, B, K, nsplit);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -137,6 +139,8 @@ int linear_dgrad(const float* dy, int ldy, const float* W, int ldw, float* dx, i
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ x, int ldx,
                                                            float* __restrict__ dW, int ldw, float* __restrict__ db, int R, int N, int K) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sdy[64];
     const int n = blockIdx.y;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -157,12 +161,13 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restri
 
 int linear_wgrad(const float* dy, int ldy, const float* x, int ldx, float* dW, int ldw, float* db, int R, int N, int K, cudaStream_t st) {
     dim3 grid(ceil_div(K, 256), N);
-    linear_wgrad_kernel<<<grid, 256, 0, st>>>(dy, ldy, x, ldx, dW, ldw, db, R, N, K);
-    return check_launch();
+    return launch_ex(linear_wgrad_kernel, dim3(grid), dim3(256), 0, st, dim3(1, 1, 1), true, dy, ldy, x, ldx, dW, ldw, db, R, N, K);
 }
 
 // ---------------------------------------------------------------------------------------------
 __global__ void rot6d_fwd_kernel(const float* __restrict__ x, float* __restrict__ R, int n) {
+    pdl_wait();
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float xi[6], Ri[9];
@@ -171,6 +176,8 @@ __global__ void rot6d_fwd_kernel(const float* __restrict__ x, float* __restrict_
     for (int k = 0; k < 9; ++k) R[(size_t)i * 9 + k] = Ri[k];
 }
 __global__ void rot6d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dR, float* __restrict__ dx, int n) {
+    pdl_wait();
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float xi[6], gi[9], di[6];
@@ -180,32 +187,32 @@ __global__ void rot6d_bwd_kernel(const float* __restrict__ x, const float* __res
     for (int k = 0; k < 6; ++k) dx[(size_t)i * 6 + k] = di[k];
 }
 int rot6d_fwd_launch(const float* pose6d, float* rotmat, int n, cudaStream_t st) {
-    rot6d_fwd_kernel<<<ceil_div(n, 128), 128, 0, st>>>(pose6d, rotmat, n);
-    return check_launch();
+    return launch_ex(rot6d_fwd_kernel, dim3(ceil_div(n, 128)), dim3(128), 0, st, dim3(1, 1, 1), true, pose6d, rotmat, n);
 }
 int rot6d_bwd_launch(const float* pose6d, const float* drot, float* dpose, int n, cudaStream_t st) {
-    rot6d_bwd_kernel<<<ceil_div(n, 128), 128, 0, st>>>(pose6d, drot, dpose, n);
-    return check_launch();
+    return launch_ex(rot6d_bwd_kernel, dim3(ceil_div(n, 128)), dim3(128), 0, st, dim3(1, 1, 1), true, pose6d, drot, dpose, n);
 }
 
 __global__ void ew_mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, size_t n) {
+    pdl_wait();
+    pdl_trigger();
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) o[i] = a[i] * b[i];
 }
 int ew_mul(const float* a, const float* b, float* out, size_t n, cudaStream_t st) {
-    ew_mul_kernel<<<ceil_div(n, 256), 256, 0, st>>>(a, b, out, n);
-    return check_launch();
+    return launch_ex(ew_mul_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, st, dim3(1, 1, 1), true, a, b, out, n);
 }
 // dst[b][j] = a[b][j] + b[b][j] for j < n
 __global__ void ew_add_rows_kernel(float* dst, int ld_dst, const float* a, int lda, const float* b, int ldb, int B, int n) {
+    pdl_wait();
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * n) return;
     int r = i / n, j = i - r * n;
     dst[(size_t)r * ld_dst + j] = a[(size_t)r * lda + j] + b[(size_t)r * ldb + j];
 }
 int ew_add_rows(float* dst, int ld_dst, const float* a, int lda, const float* b, int ldb, int B, int n, cudaStream_t st) {
-    ew_add_rows_kernel<<<ceil_div(B * n, 256), 256, 0, st>>>(dst, ld_dst, a, lda, b, ldb, B, n);
-    return check_launch();
+    return launch_ex(ew_add_rows_kernel, dim3(ceil_div(B * n, 256)), dim3(256), 0, st, dim3(1, 1, 1), true, dst, ld_dst, a, lda, b, ldb, B, n);
 }
 
 }  // namespace dboa

@@ -6,6 +6,7 @@
 // learn2learn's MAML.adapt / loss.backward() run over it (reference dynaboa_benchmark.py:140,150).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -17,6 +18,10 @@ namespace dboa {
 
 int g_last_cuda_error = 0;
 int g_launch_count = 0;
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("DBOA_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 // ---------------------------------------------------------------------------------------------
 // static network description
@@ -254,6 +259,8 @@ static int conv_backward_weight(const ConvLayer& c, int B, const float* dy, cons
 
 __global__ void head_init_kernel(const float* __restrict__ ip, const float* __restrict__ is, const float* __restrict__ ic,
                                  float* __restrict__ params0, float* __restrict__ xc0, int B) {
+    pdl_wait();
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * NDEC) return;
     int b = i / NDEC, j = i - b * NDEC;
@@ -263,6 +270,8 @@ __global__ void head_init_kernel(const float* __restrict__ ip, const float* __re
 }
 __global__ void head_out_kernel(const float* __restrict__ params3, float* __restrict__ shape, float* __restrict__ cam,
                                 float* __restrict__ pose6d, int B) {
+    pdl_wait();
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * NDEC) return;
     int b = i / NDEC, j = i - b * NDEC;
@@ -273,6 +282,8 @@ __global__ void head_out_kernel(const float* __restrict__ params3, float* __rest
 }
 // dP[b][:] = [rot6d-adjoint (filled separately) | d_shape | d_cam]
 __global__ void head_grad_in_kernel(const float* __restrict__ dshape, const float* __restrict__ dcam, float* __restrict__ dP, int B) {
+    pdl_wait();
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * 16) return;
     int b = i / 16, j = i - b * 16;
@@ -289,6 +300,12 @@ __global__ void rot6d_rows_bwd_kernel(const float* __restrict__ params3, const f
 namespace dboa {
 
 __global__ void rot6d_rows_fwd_kernel(const float* __restrict__ params3, float* __restrict__ rotmat, int B) {
+    pdl_wait();
+    pdl_trigger();
+    pdl_wait();
+    pdl_trigger();
+    pdl_wait();
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * 24) return;
     int b = i / 24, j = i - b * 24;
@@ -298,6 +315,8 @@ __global__ void rot6d_rows_fwd_kernel(const float* __restrict__ params3, float* 
     for (int k = 0; k < 9; ++k) rotmat[(size_t)i * 9 + k] = R[k];
 }
 __global__ void rot6d_rows_bwd_kernel(const float* __restrict__ params3, const float* __restrict__ drot, float* __restrict__ dP, int B) {
+    pdl_wait();
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * 24) return;
     int b = i / 24, j = i - b * 24;
@@ -351,8 +370,7 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
     }
     // pooled feature goes straight into the three regressor input rows
     DBOA_TRY(avgpool_fwd(x, T + t.xc, B, 49, 2048, HEAD_LD, 3, (size_t)B * HEAD_LD, st));
-    head_init_kernel<<<ceil_div(B * NDEC, 128), 128, 0, st>>>(init_pose, init_shape, init_cam, T + t.params, T + t.xc, B);
-    DBOA_TRY(check_launch());
+    DBOA_TRY(launch_ex(head_init_kernel, dim3(ceil_div(B * NDEC, 128)), dim3(128), 0, st, dim3(1, 1, 1), true, init_pose, init_shape, init_cam, T + t.params, T + t.xc, B));
     if (drop_masks) cudaMemcpyAsync(T + t.masks, drop_masks, 6ULL * B * HID * sizeof(float), cudaMemcpyDeviceToDevice, st);
     for (int it = 0; it < 3; ++it) {
         const float* m1 = drop_masks ? T + t.masks + (size_t)(it * 2 + 0) * B * HID : nullptr;
@@ -369,10 +387,8 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
                             HID, st));
     }
     const float* p3 = T + t.params + 3ULL * B * DEC_LD;
-    rot6d_rows_fwd_kernel<<<ceil_div(B * 24, 128), 128, 0, st>>>(p3, rotmat, B);
-    DBOA_TRY(check_launch());
-    head_out_kernel<<<ceil_div(B * NDEC, 128), 128, 0, st>>>(p3, shape, cam, pose6d, B);
-    return check_launch();
+    DBOA_TRY(launch_ex(rot6d_rows_fwd_kernel, dim3(ceil_div(B * 24, 128)), dim3(128), 0, st, dim3(1, 1, 1), true, p3, rotmat, B));
+    return launch_ex(head_out_kernel, dim3(ceil_div(B * NDEC, 128)), dim3(128), 0, st, dim3(1, 1, 1), true, p3, shape, cam, pose6d, B);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -389,10 +405,8 @@ int hmr_backward(const float* P, const float* T, int B, int masked_in, const flo
     // ---- head
     const float* p3 = T + t.params + 3ULL * B * DEC_LD;
     cudaMemsetAsync(sc.dP, 0, (size_t)B * DEC_LD * sizeof(float), st);
-    rot6d_rows_bwd_kernel<<<ceil_div(B * 24, 128), 128, 0, st>>>(p3, d_rotmat, sc.dP, B);
-    DBOA_TRY(check_launch());
-    head_grad_in_kernel<<<ceil_div(B * 16, 128), 128, 0, st>>>(d_shape, d_cam, sc.dP, B);
-    DBOA_TRY(check_launch());
+    DBOA_TRY(launch_ex(rot6d_rows_bwd_kernel, dim3(ceil_div(B * 24, 128)), dim3(128), 0, st, dim3(1, 1, 1), true, p3, d_rotmat, sc.dP, B));
+    DBOA_TRY(launch_ex(head_grad_in_kernel, dim3(ceil_div(B * 16, 128)), dim3(128), 0, st, dim3(1, 1, 1), true, d_shape, d_cam, sc.dP, B));
     cudaMemsetAsync(sc.dxf, 0, (size_t)B * 2048 * sizeof(float), st);
     for (int it = 2; it >= 0; --it) {
         float* dy_dec = sc.dy_dec + (size_t)it * B * DEC_LD;

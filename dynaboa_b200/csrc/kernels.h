@@ -25,25 +25,17 @@ bool conv_tc_enabled();
 void conv_tc_set_enabled(bool on);
 void conv_tc_set_mode(int mode);                      // 0 off, 1 on, 2 on with LBO/SBO swapped (bring-up aid)
 void conv_tc_set_workspace(float* ws, size_t floats);
-int splitk_reduce(const float* part, float* out, size_t n, int nsplit, int accumulate, cudaStream_t st);
 
-// ---- norm_pool.cu
-int gn_chunks(int HW, int C);                       // number of row chunks the statistics kernels use
-size_t gn_partial_floats(int B, int HW, int C);     // floats for [B][4][chunks][3]
-int gn_stats(const float* y, int B, int HW, int C, float* partial, cudaStream_t st);
-// out = relu?( gn(y) [+ res] [+ gn(y2)] ); writes final (mean, rstd) to stats[B][4][2] (and stats2)
-int gn_apply(const float* y, const float* partial, const float* gamma, const float* beta, float* stats,
-             const float* res, const float* y2, const float* partial2, const float* gamma2, const float* beta2, float* stats2,
-             float* out, int B, int HW, int C, int relu, cudaStream_t st);
-size_t gn_bwd_partial_floats(int B, int HW, int C);
-// dz = dout * (mask_src > 0 if mask_src else 1); dy = GN backward; dgamma/dbeta accumulate (+=)
-int gn_bwd(const float* dout, const float* mask_src, const float* y, const float* stats, const float* gamma,
-           float* dy, float* dgamma, float* dbeta, float* partial, int B, int HW, int C, cudaStream_t st);
-// single-launch variants (statistics + apply, and the whole backward) -- the ones the network plan uses
+// ---- groupnorm.cu (single-launch cluster kernels)
+size_t gn_partial_floats(int B, int HW, int C);     // forward scratch (none; kept for the C ABI)
+size_t gn_bwd_partial_floats(int B, int HW, int C); // backward scratch: per-sample dgamma / dbeta rows
+// out = relu?( gn(y) [+ res] ); writes (mean, rstd) to stats[B][4][2]
+// backward: dz = dout * (mask_src > 0 if mask_src else 1); dy = GN backward; dgamma/dbeta accumulate (+=)
 int gn_fwd_fused(const float* y, const float* gamma, const float* beta, const float* res, float* out, float* stats, float* partial,
                  int B, int HW, int C, int relu, cudaStream_t st);
 int gn_bwd_fused(const float* dout, const float* mask_src, const float* y, const float* stats, const float* gamma, float* dy,
                  float* dgamma, float* dbeta, float* partial, int B, int HW, int C, cudaStream_t st);
+// ---- norm_pool.cu
 int relu_mask(const float* dout, const float* mask_src, float* dz, size_t n, cudaStream_t st);
 int nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, cudaStream_t st);
 int maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, cudaStream_t st);

@@ -76,7 +76,9 @@ int dboa_conv2d_tc_dgrad(const float* dy, const float* w, float* dx, int B, int 
                          int Kpitch, int accumulate, dboa_stream_t stream);
 int dboa_conv2d_tc_wgrad(const float* dy, const float* x, float* dw, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
                          int Kpitch, dboa_stream_t stream);
-/* replaces: nn.GroupNorm(4, C) + ReLU (+ residual) forward / backward (model/hmr.py:14-18,40-60) */
+/* replaces: nn.GroupNorm(4, C) + ReLU (+ residual) forward / backward (model/hmr.py:14-18,40-60).
+ * C / 16 must be a power of two; one launch each (thread-block clusters).  `partial` is caller-provided scratch of
+ * dboa_gn_*partial_floats() floats; the forward size is 0 in this version and the pointer may then be NULL. */
 long long dboa_gn_partial_floats(int B, int HW, int C);
 long long dboa_gn_bwd_partial_floats(int B, int HW, int C);
 int dboa_groupnorm_fwd(const float* y, const float* gamma, const float* beta, const float* residual, float* out, float* stats,

@@ -82,7 +82,7 @@ def test_conv_fwd_dgrad_wgrad(L, case):
             assert rel_err(got.permute(0, 3, 1, 2), xr.grad) < 5e-5
 
 
-@pytest.mark.parametrize('shape', [(2, 112, 64), (1, 56, 256), (3, 14, 1024), (2, 7, 2048), (1, 28, 128)])
+@pytest.mark.parametrize('shape', [(2, 112, 64), (1, 56, 256), (3, 14, 1024), (2, 7, 2048), (1, 28, 128), (1, 56, 64), (1, 14, 256), (1, 7, 512)])
 @pytest.mark.parametrize('with_res', [False, True])
 def test_groupnorm_fwd_bwd(L, shape, with_res):
     B, H, Cc = shape
