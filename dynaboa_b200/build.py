@@ -15,6 +15,8 @@ CUDA_SOURCES = ['conv.cu', 'conv_tc.cu', 'groupnorm.cu', 'norm_pool.cu', 'head.c
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
               '--expt-relaxed-constexpr', '-Xptxas', '-v']
+if os.environ.get('DBOA_TIMELINE') == '1':          # diagnostic build: in-kernel phase timestamps (scripts/kernel_timeline.py)
+    NVCC_FLAGS.append('-DDBOA_TIMELINE')
 
 
 def _stale(target, deps):

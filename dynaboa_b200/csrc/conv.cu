@@ -71,12 +71,14 @@ __device__ __forceinline__ void cluster_reduce_store(const float acc[4][4], floa
         const int lr = rank * rows_per + v / (BN / 4), c4 = (v % (BN / 4)) * 4;
         const int row = r0 + lr;
         if (row >= nrows) continue;
+        float4 q[16];                                     // all remote loads in flight before the first add (DSMEM latency ~200 cycles each)
+#pragma unroll
+        for (int z = 0; z < 16; ++z)
+            if (z < nz) q[z] = *reinterpret_cast<const float4*>(cluster.map_shared_rank(red, z) + lr * BN + c4);
         float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int z = 0; z < nz; ++z) {
-            const float* peer = cluster.map_shared_rank(red, z);
-            const float4 q = *reinterpret_cast<const float4*>(peer + lr * BN + c4);
-            sacc.x += q.x; sacc.y += q.y; sacc.z += q.z; sacc.w += q.w;
-        }
+#pragma unroll
+        for (int z = 0; z < 16; ++z)
+            if (z < nz) { sacc.x += q[z].x; sacc.y += q[z].y; sacc.z += q[z].z; sacc.w += q[z].w; }
         float* p = out + (size_t)row * ld + c0 + c4;
         if (c0 + c4 + 3 < ncols) {
             if (accumulate) { float4 c = *reinterpret_cast<float4*>(p); sacc.x += c.x; sacc.y += c.y; sacc.z += c.z; sacc.w += c.w; }

@@ -34,14 +34,33 @@ namespace cg = cooperative_groups;
 
 namespace dboa {
 
-static int g_tc_mode = 1;          // 0 = fp32 CUDA cores, 1 = forward on tensor cores (default), 2 = forward + backward on tensor cores
+// 0 = fp32 CUDA cores; 1 = forward on tensor cores; 2 = forward, data and weight gradient on tensor cores;
+// 3 = forward and data gradient on tensor cores, weight gradient on CUDA cores (default: fastest per scripts/conv_microbench.py)
+static int g_tc_mode = 3;
 bool conv_tc_enabled() { return g_tc_mode != 0; }
 bool conv_tc_bwd_enabled() { return g_tc_mode >= 2; }
+bool conv_tc_wgrad_enabled() { return g_tc_mode == 2; }
 void conv_tc_set_enabled(bool on) { g_tc_mode = on ? 2 : 0; }
 void conv_tc_set_mode(int mode) { g_tc_mode = mode; }
 void conv_tc_set_workspace(float*, size_t) {}
 
 namespace tc {
+
+// Diagnostic build (-DDBOA_TIMELINE, scripts/kernel_timeline.py): thread 0 of every CTA stamps %globaltimer at the phase
+// boundaries of the kernel into a device buffer [cta][16]; compiled out of the product library.
+#ifdef DBOA_TIMELINE
+__device__ unsigned long long* g_timeline = nullptr;
+#define DBOA_TL(i)                                                                                        \
+    do {                                                                                                  \
+        if (threadIdx.x == 0 && g_timeline != nullptr) {                                                  \
+            unsigned long long t_;                                                                        \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                        \
+            g_timeline[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (i)] = t_; \
+        }                                                                                                 \
+    } while (0)
+#else
+#define DBOA_TL(i)
+#endif
 
 enum { FWD = 0, DGRAD = 1, WGRAD = 2 };
 constexpr int BM = 128, BN = 64, BK = 32, NT = 128, STAGES = 2;
@@ -128,6 +147,7 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5;
+    DBOA_TL(0);
     const int Ktaps = d.kh * d.kw, Kfull = Ktaps * d.Cin;
     // GEMM extents of this mode
     const int Mrows = MODE == FWD ? d.B * d.Ho * d.Wo : (MODE == DGRAD ? d.B * d.Hi * d.Wi : d.Cout);
@@ -150,29 +170,37 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = sm.tmem_base;
+    DBOA_TL(1);
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N>>3, M>>4
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
     // ---- per-thread loader state
-    // FWD / DGRAD: the 128-row operand is pixel-major: thread t owns tile row t and its whole 32-float k-block
-    const int arow = m0 + tid;
-    bool avalid = false;
-    int ph = 0, pw = 0;                                // FWD: hi0, wi0 (top-left of the window); DGRAD: hi, wi
-    const float* pb = P;
+    // FWD / DGRAD: the 128-row operand is pixel-major.  One LDG.128 of a warp covers 8 rows x 4 consecutive 16-byte
+    // k-chunks (64 contiguous bytes per row: whole sectors, 8 cache lines per request instead of 32), and the 8 lanes of
+    // one shared-memory store phase hit the 8 rows of one core matrix (conflict free).  Thread (warp, lane) owns rows
+    // warp*32 + q*8 + (lane & 7), q = 0..3, and k-chunks h*4 + (lane >> 3), h = 0..1  ->  register slot q*2 + h.
+    const int lane = tid & 31, lr8 = lane & 7, cpair = lane >> 3;
+    bool avalid[4] = {false, false, false, false};
+    int ph[4] = {0, 0, 0, 0}, pw[4] = {0, 0, 0, 0};     // FWD: hi0, wi0 (top-left of the window); DGRAD: hi, wi
+    const float* pb[4] = {P, P, P, P};
     if (MODE != WGRAD) {
         const int HW = MODE == FWD ? d.Ho * d.Wo : d.Hi * d.Wi, Wd = MODE == FWD ? d.Wo : d.Wi;
-        avalid = arow < Mrows;
-        if (avalid) {
-            const int b = arow / HW, rem = arow - b * HW;
-            const int h = rem / Wd, w_ = rem - h * Wd;
-            if (MODE == FWD) { ph = h * d.stride - d.pad; pw = w_ * d.stride - d.pad; pb = P + (size_t)b * d.Hi * d.Wi * d.Cin; }
-            else { ph = h; pw = w_; pb = P + (size_t)b * d.Ho * d.Wo * d.Cout; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int arow = m0 + warp * 32 + q * 8 + lr8;
+            avalid[q] = arow < Mrows;
+            if (avalid[q]) {
+                const int b = arow / HW, rem = arow - b * HW;
+                const int h = rem / Wd, w_ = rem - h * Wd;
+                if (MODE == FWD) { ph[q] = h * d.stride - d.pad; pw[q] = w_ * d.stride - d.pad; pb[q] = P + (size_t)b * d.Hi * d.Wi * d.Cin; }
+                else { ph[q] = h; pw[q] = w_; pb[q] = P + (size_t)b * d.Ho * d.Wo * d.Cout; }
+            }
         }
     }
-    const uint32_t a_off = (uint32_t)(tid >> 3) * GROUP_BYTES + (uint32_t)(tid & 7) * 16;      // + c * CORE_BYTES  (row t, K-major)
-    // FWD: weight tile is K-major: half a weight row (4 chunks) per thread
-    const int brow = tid >> 1, bc0 = (tid & 1) * 4;
-    const uint32_t b_off = (uint32_t)(brow >> 3) * GROUP_BYTES + (uint32_t)(brow & 7) * 16;
+    // byte offset of (row group warp*4 + q, k-chunk h*4 + cpair, row lr8) in a stage tile: + q * GROUP_BYTES + h * 4 * CORE_BYTES
+    const uint32_t a_off = (uint32_t)(warp * 4) * GROUP_BYTES + (uint32_t)cpair * CORE_BYTES + (uint32_t)lr8 * 16;
+    // FWD: weight tile is K-major: rows warp*16 + q*8 + lr8 (q = 0..1), same chunk assignment  ->  register slot q*2 + h
+    const uint32_t b_off = (uint32_t)(warp * 2) * GROUP_BYTES + (uint32_t)cpair * CORE_BYTES + (uint32_t)lr8 * 16;
     // WGRAD: column tile -> (tap, ci0)
     const int wtap = MODE == WGRAD ? n0 / d.Cin : 0, wci0 = MODE == WGRAD ? n0 - wtap * d.Cin : 0;
     const int wr = wtap / d.kw, wsx = wtap - wr * d.kw;
@@ -182,32 +210,41 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
         if (MODE == FWD) {
             const int tap = k0 / d.Cin, ci0 = k0 - tap * d.Cin;
             const int r = tap / d.kw, s = tap - r * d.kw;
-            const int hi = ph + r, wi = pw + s;
-            const bool inb = avalid && (unsigned)hi < (unsigned)d.Hi && (unsigned)wi < (unsigned)d.Wi;
-            const float* src = pb + ((size_t)hi * d.Wi + wi) * d.Cin + ci0;
             if (do_a) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) ra[c] = inb ? ldg4(src + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < 4; ++q) {
+                    const int hi = ph[q] + r, wi = pw[q] + s;
+                    const bool inb = avalid[q] && (unsigned)hi < (unsigned)d.Hi && (unsigned)wi < (unsigned)d.Wi;
+                    const float* src = pb[q] + ((size_t)hi * d.Wi + wi) * d.Cin + ci0 + cpair * 4;
+                    ra[q * 2] = inb ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    ra[q * 2 + 1] = inb ? ldg4(src + 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
-            const float* wrow = Q + (size_t)(n0 + brow) * Kfull + k0;
             if (do_b) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) rb[c] = ldg4(wrow + (bc0 + c) * 4);
+                for (int q = 0; q < 2; ++q) {
+                    const float* wrow = Q + (size_t)(n0 + warp * 16 + q * 8 + lr8) * Kfull + k0 + cpair * 4;
+                    rb[q * 2] = ldg4(wrow);
+                    rb[q * 2 + 1] = ldg4(wrow + 16);
+                }
             }
         } else if (MODE == DGRAD) {
             const int tap = k0 / d.Cout, co0 = k0 - tap * d.Cout;
             const int r = tap / d.kw, s = tap - r * d.kw;
-            const int th = ph + d.pad - r, tw = pw + d.pad - s;
-            bool inb = avalid && th >= 0 && tw >= 0;
-            int ho = 0, wo = 0;
-            if (inb) {
-                ho = th / d.stride; wo = tw / d.stride;
-                inb = (ho * d.stride == th) && (wo * d.stride == tw) && ho < d.Ho && wo < d.Wo;
-            }
-            const float* src = pb + ((size_t)ho * d.Wo + wo) * d.Cout + co0;
             if (do_a) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) ra[c] = inb ? ldg4(src + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < 4; ++q) {
+                    const int th = ph[q] + d.pad - r, tw = pw[q] + d.pad - s;
+                    bool inb = avalid[q] && th >= 0 && tw >= 0;
+                    int ho = 0, wo = 0;
+                    if (inb) {
+                        ho = th / d.stride; wo = tw / d.stride;
+                        inb = (ho * d.stride == th) && (wo * d.stride == tw) && ho < d.Ho && wo < d.Wo;
+                    }
+                    const float* src = pb[q] + ((size_t)ho * d.Wo + wo) * d.Cout + co0 + cpair * 4;
+                    ra[q * 2] = inb ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    ra[q * 2 + 1] = inb ? ldg4(src + 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
             // B[n=ci][k=co] = W[co][tap][ci]: rows of 64 consecutive ci, one row per co (transposed by the store)
             if (do_b) {
@@ -246,7 +283,8 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
     auto stash = [&](int s, const float4 (&ra)[8], const float4 (&rb)[4]) {
         if (MODE != WGRAD) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) split_store4(sm.a_hi[s], sm.a_lo[s], a_off + c * CORE_BYTES, ra[c]);
+            for (int j = 0; j < 8; ++j)
+                split_store4(sm.a_hi[s], sm.a_lo[s], a_off + (j >> 1) * GROUP_BYTES + (j & 1) * 4 * CORE_BYTES, ra[j]);
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -256,7 +294,8 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
         }
         if (MODE == FWD) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) split_store4(sm.b_hi[s], sm.b_lo[s], b_off + (bc0 + c) * CORE_BYTES, rb[c]);
+            for (int j = 0; j < 4; ++j)
+                split_store4(sm.b_hi[s], sm.b_lo[s], b_off + (j >> 1) * GROUP_BYTES + (j & 1) * 4 * CORE_BYTES, rb[j]);
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -275,8 +314,10 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
         if (nkb > 0) fetch(kb_begin, ra[0], rb[0], false, true);
         if (nkb > 1) fetch(kb_begin + 1, ra[1], rb[1], false, true);
     }
+    DBOA_TL(2);
     pdl_wait();
     pdl_trigger();
+    DBOA_TL(3);
     if (nkb > 0) fetch(kb_begin, ra[0], rb[0], true, MODE == WGRAD);
     if (nkb > 1) fetch(kb_begin + 1, ra[1], rb[1], true, MODE == WGRAD);
     for (int it0 = 0; it0 < nkb; it0 += 2) {
@@ -289,6 +330,7 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
                 stash(s, ra[f], rb[f]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async-proxy (UMMA) reads
                 __syncthreads();
+                if (it == 0) DBOA_TL(4);
                 if (it + 2 < nkb) fetch(kb_begin + it + 2, ra[f], rb[f], true, true);          // in flight behind the MMAs below
                 if (tid == 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -308,15 +350,16 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
             }
         }
     }
+    DBOA_TL(5);
     if (nkb > 0) {                                        // the last commit covers all MMAs of this CTA
         const int last = nkb - 1;
         mbar_wait(&sm.mma_done[last & 1], (uint32_t)((last >> 1) & 1));
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    DBOA_TL(6);
 
     // ---- epilogue: thread t owns accumulator lane (= output row) t
     const int nz = gridDim.z;
-    const int orow = m0 + tid;
     float* red = reinterpret_cast<float*>(sm.a_hi[0]);    // 128 rows x RED_LD floats (34 KB) over the A tiles, free after the last MMA
 #pragma unroll
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -338,45 +381,55 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
 #pragma unroll
             for (int q = 0; q < 32; ++q) r[q] = 0u;
         }
-        if (nz == 1) {
-            if (orow < Mrows) {
-                float4* dst = reinterpret_cast<float4*>(O + (size_t)orow * ldo + n0 + c0);
+        // the fp32 tile goes through shared memory (thread = row, conflict free) so that global stores are row-contiguous
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float4 v = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
-                                           __uint_as_float(r[q * 4 + 3]));
-                    if (accumulate) { const float4 c = dst[q]; v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w; }
-                    dst[q] = v;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<float4*>(red + tid * RED_LD + c0 + q * 4) =
-                    make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
-                                __uint_as_float(r[q * 4 + 3]));
-        }
+        for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(red + tid * RED_LD + c0 + q * 4) =
+                make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
+                            __uint_as_float(r[q * 4 + 3]));
     }
-    if (nz > 1) {
+    DBOA_TL(7);
+    if (nz == 1) {
+        __syncthreads();
+#pragma unroll 4
+        for (int v = tid; v < BM * (BN / 4); v += NT) {               // 16 lanes write one 256-byte output row
+            const int lr = v >> 4, c4 = (v & 15) * 4;
+            const int row = m0 + lr;
+            if (row < Mrows) {
+                float4 q = *reinterpret_cast<const float4*>(red + lr * RED_LD + c4);
+                float4* dst = reinterpret_cast<float4*>(O + (size_t)row * ldo + n0 + c4);
+                if (accumulate) { const float4 c = *dst; q.x += c.x; q.y += c.y; q.z += c.z; q.w += c.w; }
+                *dst = q;
+            }
+        }
+    } else {
         cg::cluster_group cluster = cg::this_cluster();
         cluster.sync();
+        DBOA_TL(8);
         const int rank = (int)cluster.block_rank();
         const int rows_per = BM / nz;                                 // nz is a power of two <= 16
+        const float* peers[16];
+#pragma unroll
+        for (int z = 0; z < 16; ++z) peers[z] = cluster.map_shared_rank(red, z < nz ? z : 0);
         for (int v = tid; v < rows_per * (BN / 4); v += NT) {
-            const int lr = rank * rows_per + v / (BN / 4), c4 = (v % (BN / 4)) * 4;
+            const int lr = rank * rows_per + (v >> 4), c4 = (v & 15) * 4;
             const int row = m0 + lr;
             if (row >= Mrows) continue;
             float4* dst = reinterpret_cast<float4*>(O + (size_t)row * ldo + n0 + c4);
+            float4 q[16];                                             // all remote loads in flight before the first add
+#pragma unroll
+            for (int z = 0; z < 16; ++z)
+                if (z < nz) q[z] = *reinterpret_cast<const float4*>(peers[z] + lr * RED_LD + c4);
             float4 sacc = accumulate ? *dst : make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int z = 0; z < nz; ++z) {
-                const float* peer = cluster.map_shared_rank(red, z);
-                const float4 q = *reinterpret_cast<const float4*>(peer + lr * RED_LD + c4);
-                sacc.x += q.x; sacc.y += q.y; sacc.z += q.z; sacc.w += q.w;
-            }
+#pragma unroll
+            for (int z = 0; z < 16; ++z)
+                if (z < nz) { sacc.x += q[z].x; sacc.y += q[z].y; sacc.z += q[z].z; sacc.w += q[z].w; }
             *dst = sacc;
         }
+        DBOA_TL(9);
         cluster.sync();                                               // peers may still be reading this CTA's tile
     }
+    DBOA_TL(10);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN) : "memory");
@@ -399,6 +452,12 @@ static bool shape_ok(const ConvDims& d) {
 }
 
 }  // namespace tc
+
+#ifdef DBOA_TIMELINE
+extern "C" int dboa_debug_set_timeline(unsigned long long* buf) {
+    return cudaMemcpyToSymbol(tc::g_timeline, &buf, sizeof(buf)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 int conv_tc_fwd(const float* x, const float* w, float* y, const ConvDims& d, cudaStream_t st) {
     if (g_tc_mode == 0 || !tc::shape_ok(d)) return DBOA_ERR_UNSUPPORTED;

@@ -191,27 +191,31 @@ struct Scratch {
     }
 };
 
-// Weight gradients run on a library-owned side stream: every wgrad only needs (dy of its layer, the saved input
+// Weight gradients run on two library-owned side streams (alternating): every wgrad only needs (dy of its layer, the saved input
 // activation) and writes its own slice of the gradient arena, so the chain  gn_bwd -> dgrad -> gn_bwd -> ...  on the
 // caller's stream never waits for them.  At batch 1 each kernel fills a fraction of the 148 SMs, and the two chains
 // overlap.  Buffers read by a pending wgrad are protected by per-buffer events; the side stream is joined before return.
 struct BwdAsync {
-    cudaStream_t side = nullptr;
+    static const int NSIDE = 2;
+    cudaStream_t side[NSIDE] = {nullptr, nullptr};
+    int next_side = 0;
     cudaEvent_t ev_ready[8];      // main -> side: "dy is ready" (ring)
     cudaEvent_t ev_read[8];       // side -> main: "buffer k has been read"
-    cudaEvent_t ev_join;
+    cudaEvent_t ev_join[NSIDE];
     bool pending[8];
     int ring = 0;
     bool ok = false;
     bool init() {
         if (ok) return true;
-        if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) return false;
+        for (int i = 0; i < NSIDE; ++i)
+            if (cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking) != cudaSuccess) return false;
         for (int i = 0; i < 8; ++i) {
             if (cudaEventCreateWithFlags(&ev_ready[i], cudaEventDisableTiming) != cudaSuccess) return false;
             if (cudaEventCreateWithFlags(&ev_read[i], cudaEventDisableTiming) != cudaSuccess) return false;
             pending[i] = false;
         }
-        if (cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) return false;
+        for (int i = 0; i < NSIDE; ++i)
+            if (cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming) != cudaSuccess) return false;
         ok = true;
         return true;
     }
@@ -220,6 +224,8 @@ static BwdAsync g_async;
 // DBOA_ASYNC_WGRAD=0 in the environment keeps everything on the caller's stream (A/B measurements, debugging)
 static bool g_async_enabled = [] { const char* e = getenv("DBOA_ASYNC_WGRAD"); return !(e && e[0] == '0'); }();
 void hmr_set_async_wgrad(bool on) { g_async_enabled = on; }
+// DBOA_WGRAD_STREAMS=1|2: how many side streams the weight gradients alternate over
+static const int g_wgrad_streams = [] { const char* e = getenv("DBOA_WGRAD_STREAMS"); return (e && e[0] == '1') ? 1 : BwdAsync::NSIDE; }();
 
 static ConvDims dims_of(const ConvLayer& c, int B);
 // backward convolutions: tcgen05 implicit GEMM when enabled and the shape is taken, else the fp32 CUDA-core kernels
@@ -250,7 +256,7 @@ static int conv_backward_data(const ConvLayer& c, int B, const float* dy, const 
     return conv_dgrad(dy, w, dx, dims_of(c, B), accumulate, ws, (size_t)kConvWs, st);
 }
 static int conv_backward_weight(const ConvLayer& c, int B, const float* dy, const float* x, float* dw, float* ws, cudaStream_t st) {
-    if (conv_tc_bwd_enabled()) {
+    if (conv_tc_wgrad_enabled()) {
         int s = conv_tc_wgrad(dy, x, dw, dims_of(c, B), st);
         if (s != DBOA_ERR_UNSUPPORTED) return s;
     }
@@ -440,7 +446,7 @@ int hmr_backward(const float* P, const float* T, int B, int masked_in, const flo
     if (async) {                                   // the side stream starts after everything enqueued so far
         for (int i = 0; i < 8; ++i) A.pending[i] = false;
         cudaEventRecord(A.ev_ready[A.ring], st);
-        cudaStreamWaitEvent(A.side, A.ev_ready[A.ring], 0);
+        for (int i = 0; i < BwdAsync::NSIDE; ++i) cudaStreamWaitEvent(A.side[i], A.ev_ready[A.ring], 0);
         A.ring = (A.ring + 1) & 7;
     }
     // before the main chain overwrites temp k: wait for the weight-gradient kernel that still reads it
@@ -456,11 +462,13 @@ int hmr_backward(const float* P, const float* T, int B, int masked_in, const flo
     // weight gradient of conv `c` from dy held in temp k
     auto wgrad = [&](const ConvLayer& c, int k, const float* xin_) {
         if (!async) return conv_backward_weight(c, B, tmp[k], xin_, G + c.w_off, sc.ws, st);
+        cudaStream_t ss = A.side[A.next_side];
+        A.next_side = (A.next_side + 1) % g_wgrad_streams;
         cudaEventRecord(A.ev_ready[A.ring], st);
-        cudaStreamWaitEvent(A.side, A.ev_ready[A.ring], 0);
+        cudaStreamWaitEvent(ss, A.ev_ready[A.ring], 0);
         A.ring = (A.ring + 1) & 7;
-        int s_ = conv_backward_weight(c, B, tmp[k], xin_, G + c.w_off, sc.ws, A.side);
-        cudaEventRecord(A.ev_read[k], A.side);
+        int s_ = conv_backward_weight(c, B, tmp[k], xin_, G + c.w_off, sc.ws, ss);
+        cudaEventRecord(A.ev_read[k], ss);
         A.pending[k] = true;
         return s_;
     };
@@ -494,8 +502,10 @@ int hmr_backward(const float* P, const float* T, int B, int masked_in, const flo
     DBOA_TRY(gnb(0, dIn, T + t.conv[0].a, claim(0)));
     int rc = conv_wgrad(tmp[0], T + t.x0, G + n.convs[0].w_off, dims_of(n.convs[0], B), sc.ws, (size_t)kConvWs, st);
     if (async) {                                   // join: nothing of this call is left running when the caller's stream continues
-        cudaEventRecord(A.ev_join, A.side);
-        cudaStreamWaitEvent(st, A.ev_join, 0);
+        for (int i = 0; i < BwdAsync::NSIDE; ++i) {
+            cudaEventRecord(A.ev_join[i], A.side[i]);
+            cudaStreamWaitEvent(st, A.ev_join[i], 0);
+        }
         for (int i = 0; i < 8; ++i) A.pending[i] = false;
     }
     return rc;

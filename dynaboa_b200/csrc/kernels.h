@@ -20,10 +20,11 @@ int conv_tc_fwd(const float* x, const float* w, float* y, const ConvDims& d, cud
 int conv_tc_dgrad(const float* dy, const float* w, float* dx, const ConvDims& d, int accumulate, cudaStream_t st);
 int conv_tc_wgrad(const float* dy, const float* x, float* dw, const ConvDims& d, cudaStream_t st);
 bool conv_tc_bwd_enabled();
+bool conv_tc_wgrad_enabled();
 int conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin, int Cout, cudaStream_t st);
 bool conv_tc_enabled();
 void conv_tc_set_enabled(bool on);
-void conv_tc_set_mode(int mode);                      // 0 off, 1 on, 2 on with LBO/SBO swapped (bring-up aid)
+void conv_tc_set_mode(int mode);                      // 0 off, 1 forward, 2 forward + dgrad + wgrad, 3 forward + dgrad
 void conv_tc_set_workspace(float* ws, size_t floats);
 
 // ---- groupnorm.cu (single-launch cluster kernels)

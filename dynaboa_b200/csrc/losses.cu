@@ -16,6 +16,8 @@ namespace dboa {
 // projection: thread per (body, joint)
 // ---------------------------------------------------------------------------------------------
 __global__ void project_fwd_kernel(const float* __restrict__ cam, const float* __restrict__ j3d, float* __restrict__ p2d, int B, int NJ) {
+    pdl_wait();
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * NJ) return;
     int b = i / NJ;
@@ -26,6 +28,8 @@ __global__ void project_fwd_kernel(const float* __restrict__ cam, const float* _
 // one warp per body; dj3d (+)= , dcam (+)=
 __global__ void project_bwd_kernel(const float* __restrict__ cam, const float* __restrict__ j3d, const float* __restrict__ dp2d,
                                    float* __restrict__ dj3d, float* __restrict__ dcam, int NJ, int acc_j, int acc_c) {
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.x, lane = threadIdx.x;
     float c[3] = {cam[b * 3], cam[b * 3 + 1], cam[b * 3 + 2]};
     float dc[3] = {0.f, 0.f, 0.f};
@@ -41,13 +45,11 @@ __global__ void project_bwd_kernel(const float* __restrict__ cam, const float* _
         for (int k = 0; k < 3; ++k) dcam[b * 3 + k] = acc_c ? dcam[b * 3 + k] + dc[k] : dc[k];
 }
 int project_fwd_launch(const float* cam, const float* j3d, float* p2d, int B, int NJ, cudaStream_t st) {
-    project_fwd_kernel<<<ceil_div(B * NJ, 128), 128, 0, st>>>(cam, j3d, p2d, B, NJ);
-    return check_launch();
+    return launch_ex(project_fwd_kernel, dim3(ceil_div(B * NJ, 128)), dim3(128), 0, st, dim3(1, 1, 1), true, cam, j3d, p2d, B, NJ);
 }
 int project_bwd_launch(const float* cam, const float* j3d, const float* dp2d, float* dj3d, float* dcam, int B, int NJ, int acc_j, int acc_c,
                        cudaStream_t st) {
-    project_bwd_kernel<<<B, 32, 0, st>>>(cam, j3d, dp2d, dj3d, dcam, NJ, acc_j, acc_c);
-    return check_launch();
+    return launch_ex(project_bwd_kernel, dim3(B), dim3(32), 0, st, dim3(1, 1, 1), true, cam, j3d, dp2d, dj3d, dcam, NJ, acc_j, acc_c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -59,6 +61,8 @@ template <bool FROM_ROT>
 __global__ void __launch_bounds__(256) pose_prior_kernel(const float* __restrict__ in, const float* __restrict__ means,
                                                          const float* __restrict__ prec, const float* __restrict__ neg_log_w,
                                                          float* __restrict__ prior_b, float* __restrict__ d_in, float scale) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sx[69], sd[8][69], sPd[8][69], sg[8][69], sll[8];
     __shared__ int sbest;
     const int b = blockIdx.x, t = threadIdx.x, m = t >> 5, lane = t & 31;
@@ -126,13 +130,11 @@ __global__ void __launch_bounds__(256) pose_prior_kernel(const float* __restrict
 }
 int pose_prior_launch(const float* rot, const float* means, const float* prec, const float* neg_log_w, float* prior_b, float* drot,
                       float scale, int B, cudaStream_t st) {
-    pose_prior_kernel<true><<<B, 256, 0, st>>>(rot, means, prec, neg_log_w, prior_b, drot, scale);
-    return check_launch();
+    return launch_ex(pose_prior_kernel<true>, dim3(B), dim3(256), 0, st, dim3(1, 1, 1), true, rot, means, prec, neg_log_w, prior_b, drot, scale);
 }
 int gmm_prior_launch(const float* pose69, const float* means, const float* prec, const float* neg_log_w, float* prior_b, float* dpose,
                      float scale, int B, cudaStream_t st) {
-    pose_prior_kernel<false><<<B, 256, 0, st>>>(pose69, means, prec, neg_log_w, prior_b, dpose, scale);
-    return check_launch();
+    return launch_ex(pose_prior_kernel<false>, dim3(B), dim3(256), 0, st, dim3(1, 1, 1), true, pose69, means, prec, neg_log_w, prior_b, dpose, scale);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -141,6 +143,8 @@ int gmm_prior_launch(const float* pose69, const float* means, const float* prec,
 //        3 target p2d MSE  4 target j3d MSE  5 target beta MSE  6 target R MSE  7 hip-centred 3D
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) loss_multi_kernel(LossArgs a) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float red[32];
     __shared__ float sterm[8];
     const int t = threadIdx.x, B = a.B;
@@ -242,8 +246,7 @@ __global__ void __launch_bounds__(256) loss_multi_kernel(LossArgs a) {
 }
 int loss_multi_launch(const LossArgs& a, cudaStream_t st) {
     if (a.B < 1 || a.B > 256) return DBOA_ERR_SHAPE;
-    loss_multi_kernel<<<1, 256, 0, st>>>(a);
-    return check_launch();
+    return launch_ex(loss_multi_kernel, dim3(1), dim3(256), 0, st, dim3(1, 1, 1), true, a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -254,6 +257,8 @@ __global__ void __launch_bounds__(256) loss_motion_kernel(const float* __restric
                                                           const float* __restrict__ ka, const float* __restrict__ kh, float w,
                                                           float* __restrict__ term, float* __restrict__ dpa, float* __restrict__ dph,
                                                           int B, int acc_a) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float red[32];
     float acc = 0.f;
     for (int i = threadIdx.x; i < B * 98; i += 256) {
@@ -274,8 +279,7 @@ __global__ void __launch_bounds__(256) loss_motion_kernel(const float* __restric
 }
 int loss_motion_launch(const float* pa, const float* ph, const float* ka, const float* kh, float w, float* term, float* dpa, float* dph,
                        int B, int acc_a, cudaStream_t st) {
-    loss_motion_kernel<<<1, 256, 0, st>>>(pa, ph, ka, kh, w, term, dpa, dph, B, acc_a);
-    return check_launch();
+    return launch_ex(loss_motion_kernel, dim3(1), dim3(256), 0, st, dim3(1, 1, 1), true, pa, ph, ka, kh, w, term, dpa, dph, B, acc_a);
 }
 
 }  // namespace dboa

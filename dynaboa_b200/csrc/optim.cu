@@ -98,6 +98,8 @@ int ema_update(float* teacher, const float* p, size_t n, float alpha, cudaStream
 constexpr int COS_CHUNK = 256 * 16;
 
 __global__ void __launch_bounds__(256) cosine_partial_kernel(CosinePairs cp, float* __restrict__ partial) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float red[32];
     int pair = 0;
     while (pair + 1 < cp.npairs && (int)blockIdx.x >= cp.blk_off[pair + 1]) ++pair;
@@ -114,6 +116,8 @@ __global__ void __launch_bounds__(256) cosine_partial_kernel(CosinePairs cp, flo
     if (threadIdx.x == 0) { partial[blockIdx.x * 3] = ab; partial[blockIdx.x * 3 + 1] = aa; partial[blockIdx.x * 3 + 2] = bb; }
 }
 __global__ void cosine_finish_kernel(CosinePairs cp, const float* __restrict__ partial, float* __restrict__ out, float eps) {
+    pdl_wait();
+    pdl_trigger();
     int pair = threadIdx.x;
     if (pair >= cp.npairs) return;
     double ab = 0, aa = 0, bb = 0;
@@ -129,15 +133,15 @@ int cosine_pairs(const CosinePairs& cp_in, float* partial, size_t partial_floats
     for (int i = 0; i < cp.npairs; ++i) cp.blk_off[i + 1] = cp.blk_off[i] + ceil_div(cp.n[i], COS_CHUNK);
     const int nblk = cp.blk_off[cp.npairs];
     if ((size_t)nblk * 3 > partial_floats) return DBOA_ERR_ARG;
-    cosine_partial_kernel<<<nblk, 256, 0, st>>>(cp, partial);
-    DBOA_TRY(check_launch());
-    cosine_finish_kernel<<<1, 32, 0, st>>>(cp, partial, out, eps);
-    return check_launch();
+    DBOA_TRY(launch_ex(cosine_partial_kernel, dim3(nblk), dim3(256), 0, st, dim3(1, 1, 1), true, cp, partial));
+    return launch_ex(cosine_finish_kernel, dim3(1), dim3(32), 0, st, dim3(1, 1, 1), true, cp, partial, out, eps);
 }
 
 // nearest cluster centre by cosine distance: one block, warp per centre (round robin)
 __global__ void __launch_bounds__(256) retrieval_kernel(const float* __restrict__ feat, const float* __restrict__ centers, int K, int D,
                                                         int* __restrict__ best, float* __restrict__ dists) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sd[64];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float ff = 0.f;
@@ -158,8 +162,7 @@ __global__ void __launch_bounds__(256) retrieval_kernel(const float* __restrict_
 }
 int retrieval_nearest(const float* feat, const float* centers, int K, int D, int* best, float* dists, cudaStream_t st) {
     if (K < 1 || K > 64) return DBOA_ERR_SHAPE;
-    retrieval_kernel<<<1, 256, 0, st>>>(feat, centers, K, D, best, dists);
-    return check_launch();
+    return launch_ex(retrieval_kernel, dim3(1), dim3(256), 0, st, dim3(1, 1, 1), true, feat, centers, K, D, best, dists);
 }
 
 }  // namespace dboa

@@ -33,6 +33,8 @@ __device__ __forceinline__ float blend_coeff(const float* betas, const float* ro
 __global__ void __launch_bounds__(256) smpl_blend_fwd_kernel(const float* __restrict__ D, const float* __restrict__ vt,
                                                              const float* __restrict__ betas, const float* __restrict__ rot,
                                                              float* __restrict__ partial, int b0, int nb, int B) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sc[8][ROWS_PER_SPLIT];
     const int s = blockIdx.y, rbeg = s * ROWS_PER_SPLIT, rend = min(rbeg + ROWS_PER_SPLIT, NROW);
     for (int i = threadIdx.x; i < 8 * ROWS_PER_SPLIT; i += 256) {
@@ -63,6 +65,8 @@ __global__ void __launch_bounds__(32) smpl_chain_fwd_kernel(const float* __restr
                                                             const float* __restrict__ rot, float* __restrict__ A_out,
                                                             float* __restrict__ Gr_out, float* __restrict__ J_out,
                                                             float* __restrict__ Jtr_out) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sR[216], sJ[72], sGr[216], sGt[72], sA[288];
     __shared__ int sp[24];
     const int b = blockIdx.x, t = threadIdx.x;
@@ -87,6 +91,8 @@ __global__ void __launch_bounds__(32) smpl_chain_fwd_kernel(const float* __restr
 __global__ void __launch_bounds__(128) smpl_skin_fwd_kernel(const float* __restrict__ partial, const float* __restrict__ A,
                                                             const float* __restrict__ W, float* __restrict__ vposed,
                                                             float* __restrict__ verts, int B) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sA[288];
     const int b = blockIdx.y;
     for (int i = threadIdx.x; i < 288; i += 128) sA[i] = A[(size_t)b * 288 + i];
@@ -126,6 +132,8 @@ __global__ void __launch_bounds__(128) smpl_skin_fwd_kernel(const float* __restr
 __global__ void __launch_bounds__(128) smpl_joints_fwd_kernel(const float* __restrict__ verts, const float* __restrict__ Jtr,
                                                               const float* __restrict__ Jx, const int* __restrict__ joint_map,
                                                               const int* __restrict__ vertex_ids, float* __restrict__ joints) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float red[32];
     const int i = blockIdx.x, b = blockIdx.y, src = joint_map[i];
     float* o = joints + ((size_t)b * 49 + i) * 3;
@@ -153,15 +161,11 @@ int smpl_forward(const dboa_smpl_model& m, const float* betas, const float* rot,
     for (int b0 = 0; b0 < B; b0 += 8) {
         int nb = B - b0 < 8 ? B - b0 : 8;
         dim3 g(ceil_div(NV3, 256), NSPLIT);
-        smpl_blend_fwd_kernel<<<g, 256, 0, st>>>(m.blend_dirs, m.v_template, betas, rot, t.partial, b0, nb, B);
-        DBOA_TRY(check_launch());
+        DBOA_TRY(launch_ex(smpl_blend_fwd_kernel, dim3(g), dim3(256), 0, st, dim3(1, 1, 1), true, m.blend_dirs, m.v_template, betas, rot, t.partial, b0, nb, B));
     }
-    smpl_chain_fwd_kernel<<<B, 32, 0, st>>>(m.J_template, m.J_shapedirs, m.parents, betas, rot, t.A, t.Gr, t.J, t.Jtr);
-    DBOA_TRY(check_launch());
-    smpl_skin_fwd_kernel<<<dim3(ceil_div(NV, 128), B), 128, 0, st>>>(t.partial, t.A, m.lbs_weights, t.vposed, verts, B);
-    DBOA_TRY(check_launch());
-    smpl_joints_fwd_kernel<<<dim3(49, B), 128, 0, st>>>(verts, t.Jtr, m.J_extra, m.joint_map, m.vertex_ids, joints);
-    return check_launch();
+    DBOA_TRY(launch_ex(smpl_chain_fwd_kernel, dim3(B), dim3(32), 0, st, dim3(1, 1, 1), true, m.J_template, m.J_shapedirs, m.parents, betas, rot, t.A, t.Gr, t.J, t.Jtr));
+    DBOA_TRY(launch_ex(smpl_skin_fwd_kernel, dim3(ceil_div(NV, 128), B), dim3(128), 0, st, dim3(1, 1, 1), true, t.partial, t.A, m.lbs_weights, t.vposed, verts, B));
+    return launch_ex(smpl_joints_fwd_kernel, dim3(49, B), dim3(128), 0, st, dim3(1, 1, 1), true, verts, t.Jtr, m.J_extra, m.joint_map, m.vertex_ids, joints);
 }
 
 // =============================================================================================
@@ -171,6 +175,8 @@ int smpl_forward(const dboa_smpl_model& m, const float* betas, const float* rot,
 __global__ void __launch_bounds__(256) smpl_joints_bwd_kernel(const float* __restrict__ dj, const float* __restrict__ Jx,
                                                               const int* __restrict__ joint_map, const int* __restrict__ vertex_ids,
                                                               float* __restrict__ dverts, float* __restrict__ dJtr) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sde[9][3], sdp[21][3], sdk[24][3];
     __shared__ int svid[21];
     const int b = blockIdx.y;
@@ -206,6 +212,8 @@ __global__ void __launch_bounds__(256) smpl_joints_bwd_kernel(const float* __res
 __global__ void __launch_bounds__(128) smpl_skin_bwd_kernel(const float* __restrict__ dverts, const float* __restrict__ vposed,
                                                             const float* __restrict__ A, const float* __restrict__ W,
                                                             float* __restrict__ dvposed, float* __restrict__ dA_part) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sA[288];
     __shared__ float sw[128][25];
     __shared__ float sdT[128][13];
@@ -262,6 +270,8 @@ __global__ void __launch_bounds__(128) smpl_skin_bwd_kernel(const float* __restr
 // blend backward: dc[b][row] = sum_idx D[row][idx] dvposed[b][idx]; grid (217), 256 threads
 __global__ void __launch_bounds__(256) smpl_blend_bwd_kernel(const float* __restrict__ D, const float* __restrict__ dvposed,
                                                              float* __restrict__ dc, int b0, int nb) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float red[32];
     const int row = blockIdx.x;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -283,6 +293,8 @@ __global__ void __launch_bounds__(32) smpl_chain_bwd_kernel(const float* __restr
                                                             const float* __restrict__ Gr, const float* __restrict__ dA_part, int nparts,
                                                             const float* __restrict__ dJtr, const float* __restrict__ dc,
                                                             float* __restrict__ drot, float* __restrict__ dbetas, int accumulate) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sR[216], sJ[72], sGr[216], sdA[288], sdJt[72], sdGr[216], sdGt[72], sdR[216], sdJ[72];
     __shared__ int sp[24];
     const int b = blockIdx.x, t = threadIdx.x;
@@ -316,22 +328,19 @@ int smpl_backward(const dboa_smpl_model& m, const float* rot, int B, const float
     SmplTape t(const_cast<float*>(tape), B);
     SmplScratch s(scratch, B);
     const int nparts = ceil_div(NV, 128);
-    smpl_joints_bwd_kernel<<<dim3(ceil_div(NV, 256), B), 256, 0, st>>>(djoints, m.J_extra, m.joint_map, m.vertex_ids, s.dverts, s.dJtr);
-    DBOA_TRY(check_launch());
-    smpl_skin_bwd_kernel<<<dim3(nparts, B), 128, 0, st>>>(s.dverts, t.vposed, t.A, m.lbs_weights, s.dvposed, s.dA_part);
-    DBOA_TRY(check_launch());
+    DBOA_TRY(launch_ex(smpl_joints_bwd_kernel, dim3(ceil_div(NV, 256), B), dim3(256), 0, st, dim3(1, 1, 1), true, djoints, m.J_extra, m.joint_map, m.vertex_ids, s.dverts, s.dJtr));
+    DBOA_TRY(launch_ex(smpl_skin_bwd_kernel, dim3(nparts, B), dim3(128), 0, st, dim3(1, 1, 1), true, s.dverts, t.vposed, t.A, m.lbs_weights, s.dvposed, s.dA_part));
     for (int b0 = 0; b0 < B; b0 += 8) {
         int nb = B - b0 < 8 ? B - b0 : 8;
-        smpl_blend_bwd_kernel<<<NROW, 256, 0, st>>>(m.blend_dirs, s.dvposed, s.dc, b0, nb);
-        DBOA_TRY(check_launch());
+        DBOA_TRY(launch_ex(smpl_blend_bwd_kernel, dim3(NROW), dim3(256), 0, st, dim3(1, 1, 1), true, m.blend_dirs, s.dvposed, s.dc, b0, nb));
     }
-    smpl_chain_bwd_kernel<<<B, 32, 0, st>>>(m.J_shapedirs, m.parents, rot, t.J, t.Gr, s.dA_part, nparts, s.dJtr, s.dc, drot, dbetas,
-                                           accumulate);
-    return check_launch();
+    return launch_ex(smpl_chain_bwd_kernel, dim3(B), dim3(32), 0, st, dim3(1, 1, 1), true, m.J_shapedirs, m.parents, rot, t.J, t.Gr, s.dA_part, nparts, s.dJtr, s.dc, drot, dbetas, accumulate);
 }
 
 // axis-angle -> rotation matrix, kind 0 = reference quaternion route, 1 = smplx Rodrigues formula
 __global__ void rodrigues_kernel(const float* __restrict__ aa, float* __restrict__ R, int n, int kind) {
+    pdl_wait();
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float th[3] = {aa[(size_t)i * 3], aa[(size_t)i * 3 + 1], aa[(size_t)i * 3 + 2]}, Ri[9];
@@ -339,8 +348,7 @@ __global__ void rodrigues_kernel(const float* __restrict__ aa, float* __restrict
     for (int k = 0; k < 9; ++k) R[(size_t)i * 9 + k] = Ri[k];
 }
 int rodrigues_launch(const float* aa, float* R, int n, int kind, cudaStream_t st) {
-    rodrigues_kernel<<<ceil_div(n, 128), 128, 0, st>>>(aa, R, n, kind);
-    return check_launch();
+    return launch_ex(rodrigues_kernel, dim3(ceil_div(n, 128)), dim3(128), 0, st, dim3(1, 1, 1), true, aa, R, n, kind);
 }
 
 }  // namespace dboa

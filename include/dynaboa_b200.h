@@ -30,7 +30,9 @@ typedef void* dboa_stream_t;
 const char* dboa_version(void);
 int dboa_last_cuda_error(void);            /* cudaError_t of the last failed launch */
 long long dboa_launch_count(void);         /* kernels launched by this library so far */
-int dboa_set_tensor_core_conv(int mode);   /* 0: fp32 CUDA-core convs; 1: tcgen05 TF32x3 forward; 2: tcgen05 forward + dgrad + wgrad */
+/* which convolution products of the HMR plan run on the tcgen05 TF32x3 kernel -- 0: none (fp32 CUDA cores); 1: forward;
+ * 2: forward + dgrad + wgrad; 3 (default): forward + dgrad, weight gradients on CUDA cores */
+int dboa_set_tensor_core_conv(int mode);
 
 /* ---- HMR regressor: parameter arena and tape layout ----------------------------------------
  * replaces: model/hmr.py:67-124 (HMR.__init__/_make_layer state_dict contract).
@@ -71,7 +73,7 @@ int dboa_conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin
 /* general convolution forward as a tcgen05 TF32x3 implicit GEMM (same arguments as dboa_conv2d_fwd; Cin % 32 == 0) */
 int dboa_conv2d_tc_fwd(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
                        int Kpitch, dboa_stream_t stream);
-/* data / weight gradient on the same tensor-core kernel (dboa_set_tensor_core_conv(2)); dw is accumulated (+=) */
+/* data / weight gradient on the same tensor-core kernel (needs dboa_set_tensor_core_conv(2 or 3)); dw is accumulated (+=) */
 int dboa_conv2d_tc_dgrad(const float* dy, const float* w, float* dx, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
                          int Kpitch, int accumulate, dboa_stream_t stream);
 int dboa_conv2d_tc_wgrad(const float* dy, const float* x, float* dw, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
