@@ -13,16 +13,20 @@
 // in fp32 inside TMEM, which keeps the result within ~2e-6 of the exact-fp32 CUDA-core path (conv.cu), against
 // which this kernel is validated on the device (tests/test_gpu_tc.py).  SURVEY.md §7 "hard part 1".
 //
-// Structure (one CTA = 128 threads, one 128 x 64 output tile, 32 reduction elements per k-block):
-//   loaders  : 12 float4 global loads per thread and k-block (8 for the 128-row operand, 4 for the 64-row operand),
-//              im2col / transposed-filter / pixel-major gathers computed on the fly with zero fill, issued TWO k-blocks
-//              ahead in registers; hi/lo are split in registers and stored into the UMMA canonical K-major no-swizzle
-//              layout (8-row x 16-byte core matrices) of one of 2 shared-memory stages.  Operands whose memory order
-//              is reduction-minor (K-major) are stored with float4; the others are transposed by the store.
+// Structure (one CTA = 512 threads, one 128 x 64 output tile, 32 reduction elements per k-block).  At batch 1 a CTA
+// has 2..9 k-blocks and the kernel is a chain of dependent phases; the first version (128 threads, every thread 12
+// loads + their index arithmetic per k-block) spent ~1.5 us per k-block with ONE warp per scheduler and nothing to hide
+// instruction latency behind (scripts/kernel_timeline.py).  Hence 16 warps and <= 3 loads per thread and k-block:
+//   loaders  : per k-block 2 float4 of the 128-row operand and 1 of the 64-row operand per thread; im2col /
+//              transposed-filter / pixel-major gathers computed on the fly with zero fill, issued THREE k-blocks
+//              ahead in registers; a warp request covers 8 rows x 64 contiguous bytes.  hi/lo are split in registers
+//              and stored into the UMMA canonical K-major no-swizzle layout (8-row x 16-byte core matrices) of one of
+//              3 shared-memory stages.  Operands whose memory order is reduction-minor (K-major) are stored with
+//              float4 (conflict free); the others are transposed by the store.
 //   thread 0 : 12 x tcgen05.mma (4 k-steps of 8 x 3 products) per stage, tcgen05.commit -> mbarrier of the stage.
-//   epilogue : tcgen05.ld (32 lanes x 32 columns per warp) -> registers.  Split-K runs across a thread-block cluster
-//              (1,1,nz): partial tiles are parked in shared memory and each CTA sums a band of 128/nz rows over its
-//              peers through distributed shared memory in the fixed order z = 0..nz-1 (deterministic).
+//   epilogue : tcgen05.ld (32 lanes x 16 columns per warp) -> shared memory -> row-contiguous global stores.  Split-K
+//              runs across a thread-block cluster (1,1,nz): each CTA sums a band of 128/nz rows over its peers through
+//              distributed shared memory (all remote loads in flight, then added in the fixed order z = 0..nz-1).
 // Accumulators live in TMEM (64 columns x 128 lanes), never in registers.
 #include <cooperative_groups.h>
 #include <stdint.h>
@@ -58,12 +62,27 @@ __device__ unsigned long long* g_timeline = nullptr;
             g_timeline[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (i)] = t_; \
         }                                                                                                 \
     } while (0)
+// per-iteration cycle stamps of CTA (0,0,0), thread 0: slot 40000 + it * 8 + j
+#define DBOA_TLC(it, j)                                                                                   \
+    do {                                                                                                  \
+        if (threadIdx.x == 0 && g_timeline != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (it) < 12)   \
+            g_timeline[40000 + (it) * 8 + (j)] = (unsigned long long)clock64();                           \
+    } while (0)
+// same for the MMA-issuer thread (slots 5..7 of the iteration)
+#define DBOA_TLM(it, j)                                                                                   \
+    do {                                                                                                  \
+        if (g_timeline != nullptr && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (it) < 12)            \
+            g_timeline[40000 + (it) * 8 + (j)] = (unsigned long long)clock64();                           \
+    } while (0)
 #else
 #define DBOA_TL(i)
+#define DBOA_TLC(it, j)
+#define DBOA_TLM(it, j)
 #endif
 
 enum { FWD = 0, DGRAD = 1, WGRAD = 2 };
-constexpr int BM = 128, BN = 64, BK = 32, NT = 128, STAGES = 2;
+constexpr int BM = 128, BN = 64, BK = 32, STAGES = 2;
+constexpr int NPW = 8, NPROD = NPW * 32, NT = NPROD + 32;     // 8 producer warps + 1 MMA-issuer warp
 constexpr uint32_t CORE_BYTES = 128;                     // one 8 x 16B core matrix
 constexpr uint32_t GROUP_BYTES = (BK / 4) * CORE_BYTES;  // one 8-row group of a stage tile (1024 B)
 constexpr uint32_t A_TILE = BM * BK * 4, B_TILE = BN * BK * 4;
@@ -90,6 +109,9 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0, addr = smem_u32(bar);
@@ -136,17 +158,19 @@ struct Smem {
     alignas(128) uint8_t a_lo[STAGES][A_TILE];
     alignas(128) uint8_t b_hi[STAGES][B_TILE];
     alignas(128) uint8_t b_lo[STAGES][B_TILE];
-    alignas(8) uint64_t mma_done[STAGES];
+    alignas(8) uint64_t full[STAGES];      // producers -> MMA issuer: stage filled (one arrival per producer warp)
+    alignas(8) uint64_t empty[STAGES];     // tcgen05.commit -> producers: the MMAs that read the stage have completed
+    alignas(8) uint64_t done;              // tcgen05.commit after the last MMA -> epilogue
     uint32_t tmem_base;
 };
 
 // P: the operand that pairs with the weights in FWD/DGRAD (x or dy); Q: weights (FWD/DGRAD) or x (WGRAD, with P = dy)
 template <int MODE>
-__global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict__ P, const float* __restrict__ Q, float* __restrict__ O,
-                                                         ConvDims d, int kb_per_split, int accumulate) {
+__global__ void __launch_bounds__(NT, 2) conv_tf32x3_kernel(const float* __restrict__ P, const float* __restrict__ Q, float* __restrict__ O,
+                                                            ConvDims d, int kb_per_split, int accumulate) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     DBOA_TL(0);
     const int Ktaps = d.kh * d.kw, Kfull = Ktaps * d.Cin;
     // GEMM extents of this mode
@@ -159,7 +183,8 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
     const int nkb = max(0, min(kb_begin + kb_per_split, nkb_total) - kb_begin);
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&sm.mma_done[s], 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], NPW); mbar_init(&sm.empty[s], 1); }
+        mbar_init(&sm.done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -171,201 +196,237 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = sm.tmem_base;
     DBOA_TL(1);
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N>>3, M>>4
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-    // ---- per-thread loader state
-    // FWD / DGRAD: the 128-row operand is pixel-major.  One LDG.128 of a warp covers 8 rows x 4 consecutive 16-byte
-    // k-chunks (64 contiguous bytes per row: whole sectors, 8 cache lines per request instead of 32), and the 8 lanes of
-    // one shared-memory store phase hit the 8 rows of one core matrix (conflict free).  Thread (warp, lane) owns rows
-    // warp*32 + q*8 + (lane & 7), q = 0..3, and k-chunks h*4 + (lane >> 3), h = 0..1  ->  register slot q*2 + h.
-    const int lane = tid & 31, lr8 = lane & 7, cpair = lane >> 3;
-    bool avalid[4] = {false, false, false, false};
-    int ph[4] = {0, 0, 0, 0}, pw[4] = {0, 0, 0, 0};     // FWD: hi0, wi0 (top-left of the window); DGRAD: hi, wi
-    const float* pb[4] = {P, P, P, P};
-    if (MODE != WGRAD) {
-        const int HW = MODE == FWD ? d.Ho * d.Wo : d.Hi * d.Wi, Wd = MODE == FWD ? d.Wo : d.Wi;
+    if (warp == NPW) {
+        // =====================================================================================
+        // MMA issuer: one thread.  Per filled stage 12 x tcgen05.mma (4 k-steps of 8 x {Ah*Bh, Ah*Bl, Al*Bh}); the commit
+        // releases the stage to the producers.  Descriptors are precomputed per stage -- a k-step only advances the
+        // 14-bit start-address field -- because this thread's issue rate bounds the k-loop (scripts/kernel_timeline.py).
+        // =====================================================================================
+        if (lane == 0 && nkb > 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N>>3, M>>4
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            uint64_t dah[STAGES], dal[STAGES], dbh[STAGES], dbl[STAGES];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int arow = m0 + warp * 32 + q * 8 + lr8;
-            avalid[q] = arow < Mrows;
-            if (avalid[q]) {
-                const int b = arow / HW, rem = arow - b * HW;
-                const int h = rem / Wd, w_ = rem - h * Wd;
-                if (MODE == FWD) { ph[q] = h * d.stride - d.pad; pw[q] = w_ * d.stride - d.pad; pb[q] = P + (size_t)b * d.Hi * d.Wi * d.Cin; }
-                else { ph[q] = h; pw[q] = w_; pb[q] = P + (size_t)b * d.Ho * d.Wo * d.Cout; }
+            for (int s = 0; s < STAGES; ++s) {
+                dah[s] = make_desc(smem_u32(sm.a_hi[s])); dal[s] = make_desc(smem_u32(sm.a_lo[s]));
+                dbh[s] = make_desc(smem_u32(sm.b_hi[s])); dbl[s] = make_desc(smem_u32(sm.b_lo[s]));
             }
-        }
-    }
-    // byte offset of (row group warp*4 + q, k-chunk h*4 + cpair, row lr8) in a stage tile: + q * GROUP_BYTES + h * 4 * CORE_BYTES
-    const uint32_t a_off = (uint32_t)(warp * 4) * GROUP_BYTES + (uint32_t)cpair * CORE_BYTES + (uint32_t)lr8 * 16;
-    // FWD: weight tile is K-major: rows warp*16 + q*8 + lr8 (q = 0..1), same chunk assignment  ->  register slot q*2 + h
-    const uint32_t b_off = (uint32_t)(warp * 2) * GROUP_BYTES + (uint32_t)cpair * CORE_BYTES + (uint32_t)lr8 * 16;
-    // WGRAD: column tile -> (tap, ci0)
-    const int wtap = MODE == WGRAD ? n0 / d.Cin : 0, wci0 = MODE == WGRAD ? n0 - wtap * d.Cin : 0;
-    const int wr = wtap / d.kw, wsx = wtap - wr * d.kw;
-
-    auto fetch = [&](int kb, float4 (&ra)[8], float4 (&rb)[4], bool do_a, bool do_b) {
-        const int k0 = kb * BK;
-        if (MODE == FWD) {
-            const int tap = k0 / d.Cin, ci0 = k0 - tap * d.Cin;
-            const int r = tap / d.kw, s = tap - r * d.kw;
-            if (do_a) {
+            constexpr uint64_t KSTEP = (2 * CORE_BYTES) >> 4;      // 8 tf32 = two 16-byte chunks along K, in descriptor units
+            for (int it0 = 0, round = 0; it0 < nkb; it0 += STAGES, ++round) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int hi = ph[q] + r, wi = pw[q] + s;
-                    const bool inb = avalid[q] && (unsigned)hi < (unsigned)d.Hi && (unsigned)wi < (unsigned)d.Wi;
-                    const float* src = pb[q] + ((size_t)hi * d.Wi + wi) * d.Cin + ci0 + cpair * 4;
-                    ra[q * 2] = inb ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    ra[q * 2 + 1] = inb ? ldg4(src + 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int s = 0; s < STAGES; ++s) {
+                    const int it = it0 + s;
+                    if (it < nkb) {
+                        DBOA_TLM(it, 5);
+                        mbar_wait(&sm.full[s], (uint32_t)(round & 1));
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        DBOA_TLM(it, 6);
+#pragma unroll
+                        for (int kk = 0; kk < BK / 8; ++kk) {
+                            mma_tf32(tmem_d, dah[s] + kk * KSTEP, dbh[s] + kk * KSTEP, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                            mma_tf32(tmem_d, dah[s] + kk * KSTEP, dbl[s] + kk * KSTEP, idesc, 1u);
+                            mma_tf32(tmem_d, dal[s] + kk * KSTEP, dbh[s] + kk * KSTEP, idesc, 1u);
+                        }
+                        umma_commit(&sm.empty[s]);       // arrives when every MMA issued so far has completed
+                        DBOA_TLM(it, 7);
+                    }
                 }
             }
-            if (do_b) {
+            umma_commit(&sm.done);
+        }
+        pdl_wait();          // every thread of a programmatically launched grid passes the dependency wait before it exits
+        pdl_trigger();
+    } else {
+        // =====================================================================================
+        // producers (8 warps): global -> registers (two k-blocks ahead) -> hi/lo split -> shared memory stage
+        // FWD / DGRAD: the 128-row operand is pixel-major.  Warp w owns the 8-row groups 2w, 2w+1; lane = (row lr8, chunk
+        // pair cpair): one LDG.128 of a warp covers 8 rows x 64 contiguous bytes (whole sectors), and the 8 lanes of one
+        // shared-memory store phase fill the 8 rows of one core matrix (conflict free).  Register slot q*2 + h holds
+        // row group 2w + q, 16-byte k-chunk h*4 + cpair.
+        // =====================================================================================
+        const int lr8 = lane & 7, cpair = lane >> 3;
+        bool avalid[2] = {false, false};
+        int ph[2] = {0, 0}, pw[2] = {0, 0};                // FWD: hi0, wi0 (top-left of the window); DGRAD: hi, wi
+        const float* pb[2] = {P, P};
+        if (MODE != WGRAD) {
+            const int HW = MODE == FWD ? d.Ho * d.Wo : d.Hi * d.Wi, Wd = MODE == FWD ? d.Wo : d.Wi;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int arow = m0 + (warp * 2 + q) * 8 + lr8;
+                avalid[q] = arow < Mrows;
+                if (avalid[q]) {
+                    const int b = arow / HW, rem = arow - b * HW;
+                    const int h = rem / Wd, w_ = rem - h * Wd;
+                    if (MODE == FWD) { ph[q] = h * d.stride - d.pad; pw[q] = w_ * d.stride - d.pad; pb[q] = P + (size_t)b * d.Hi * d.Wi * d.Cin; }
+                    else { ph[q] = h; pw[q] = w_; pb[q] = P + (size_t)b * d.Ho * d.Wo * d.Cout; }
+                }
+            }
+        }
+        // byte offset of (row group 2w + q, k-chunk h*4 + cpair, row lr8) in a stage tile: + q * GROUP_BYTES + h * 4 * CORE_BYTES
+        const uint32_t a_off = (uint32_t)(warp * 2) * GROUP_BYTES + (uint32_t)cpair * CORE_BYTES + (uint32_t)lr8 * 16;
+        // FWD: the weight tile is K-major too: row group w, chunks h*4 + cpair  ->  register slot h
+        const uint32_t b_off = (uint32_t)warp * GROUP_BYTES + (uint32_t)cpair * CORE_BYTES + (uint32_t)lr8 * 16;
+        // WGRAD: column tile -> (tap, ci0)
+        const int wtap = MODE == WGRAD ? n0 / d.Cin : 0, wci0 = MODE == WGRAD ? n0 - wtap * d.Cin : 0;
+        const int wr = wtap / d.kw, wsx = wtap - wr * d.kw;
+        // reduction cursor of the two operand streams (tap row, tap column, channel offset): k-blocks are fetched in order,
+        // so the im2col decode is an increment, not a division, per k-block
+        const int Cred = MODE == DGRAD ? d.Cout : d.Cin;
+        struct Cursor { int r, s, c; };
+        auto make_cursor = [&](int kb) { Cursor c; const int k0 = kb * BK, tap = k0 / Cred; c.c = k0 - tap * Cred; c.r = tap / d.kw; c.s = tap - c.r * d.kw; return c; };
+        auto advance = [&](Cursor& c) { c.c += BK; if (c.c >= Cred) { c.c = 0; if (++c.s == d.kw) { c.s = 0; ++c.r; } } };
+        Cursor ca = make_cursor(kb_begin), cb = ca;
+        int kb_a = kb_begin, kb_b = kb_begin;              // next k-block of each stream
+
+        auto fetch_a = [&](float4 (&ra)[4]) {
+            if (MODE == FWD) {
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const float* wrow = Q + (size_t)(n0 + warp * 16 + q * 8 + lr8) * Kfull + k0 + cpair * 4;
-                    rb[q * 2] = ldg4(wrow);
-                    rb[q * 2 + 1] = ldg4(wrow + 16);
-                }
-            }
-        } else if (MODE == DGRAD) {
-            const int tap = k0 / d.Cout, co0 = k0 - tap * d.Cout;
-            const int r = tap / d.kw, s = tap - r * d.kw;
-            if (do_a) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int th = ph[q] + d.pad - r, tw = pw[q] + d.pad - s;
-                    bool inb = avalid[q] && th >= 0 && tw >= 0;
-                    int ho = 0, wo = 0;
-                    if (inb) {
-                        ho = th / d.stride; wo = tw / d.stride;
-                        inb = (ho * d.stride == th) && (wo * d.stride == tw) && ho < d.Ho && wo < d.Wo;
-                    }
-                    const float* src = pb[q] + ((size_t)ho * d.Wo + wo) * d.Cout + co0 + cpair * 4;
+                    const int hi = ph[q] + ca.r, wi = pw[q] + ca.s;
+                    const bool inb = avalid[q] && (unsigned)hi < (unsigned)d.Hi && (unsigned)wi < (unsigned)d.Wi;
+                    const float* src = pb[q] + ((size_t)hi * d.Wi + wi) * d.Cin + ca.c + cpair * 4;
                     ra[q * 2] = inb ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
                     ra[q * 2 + 1] = inb ? ldg4(src + 16) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-            }
-            // B[n=ci][k=co] = W[co][tap][ci]: rows of 64 consecutive ci, one row per co (transposed by the store)
-            if (do_b) {
+            } else if (MODE == DGRAD) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int th = ph[q] + d.pad - ca.r, tw = pw[q] + d.pad - ca.s;
+                    bool inb = avalid[q] && th >= 0 && tw >= 0;
+                    int ho = th, wo = tw;
+                    if (d.stride != 1) {
+                        ho = th / d.stride; wo = tw / d.stride;
+                        inb = inb && (ho * d.stride == th) && (wo * d.stride == tw);
+                    }
+                    inb = inb && ho < d.Ho && wo < d.Wo;
+                    const float* src = pb[q] + ((size_t)ho * d.Wo + wo) * d.Cout + ca.c + cpair * 4;
+                    ra[q * 2] = inb ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    ra[q * 2 + 1] = inb ? ldg4(src + 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                // A'[m=co][k=pix] = dY[pix][co]: rows of 128 consecutive co, one row per pixel (transposed by the store)
+                const int k0 = kb_a * BK;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int idx = tid + NT * j, k = idx >> 4, nv = idx & 15;
-                    rb[j] = ldg4(Q + (size_t)(co0 + k) * Kfull + (size_t)tap * d.Cin + n0 + nv * 4);
+                    const int idx = tid + NPROD * j, k = idx >> 5, cv = idx & 31;
+                    const int pix = k0 + k, co = m0 + cv * 4;
+                    ra[j] = (pix < Kred && co < d.Cout) ? ldg4(P + (size_t)pix * d.Cout + co) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
-        } else {
-            // A'[m=co][k=pix] = dY[pix][co]: rows of 128 consecutive co, one row per pixel (transposed by the store)
-            const int Mpix = Kred;
+            ++kb_a;
+            if (MODE != WGRAD) advance(ca);
+        };
+        auto fetch_b = [&](float4 (&rb)[2]) {
+            const int k0 = kb_b * BK;
+            if (MODE == FWD) {
+                const float* wrow = Q + (size_t)(n0 + warp * 8 + lr8) * Kfull + k0 + cpair * 4;
+                rb[0] = ldg4(wrow);
+                rb[1] = ldg4(wrow + 16);
+            } else if (MODE == DGRAD) {
+                // B[n=ci][k=co] = W[co][tap][ci]: rows of 64 consecutive ci, one row per co (transposed by the store)
+                const int tap = cb.r * d.kw + cb.s;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int idx = tid + NT * j, k = idx >> 5, cv = idx & 31;
-                const int pix = k0 + k, co = m0 + cv * 4;
-                ra[j] = (pix < Mpix && co < d.Cout) ? ldg4(P + (size_t)pix * d.Cout + co) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            // B'[n=ci][k=pix] = X[pixel shifted by the tap][ci0 + n]
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int idx = tid + NT * j, k = idx >> 4, nv = idx & 15;
-                const int pix = k0 + k;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pix < Mpix) {
-                    const int b = pix / (d.Ho * d.Wo), rem = pix - b * d.Ho * d.Wo;
-                    const int ho = rem / d.Wo, wo = rem - ho * d.Wo;
-                    const int hi = ho * d.stride - d.pad + wr, wi = wo * d.stride - d.pad + wsx;
-                    if ((unsigned)hi < (unsigned)d.Hi && (unsigned)wi < (unsigned)d.Wi)
-                        v = ldg4(Q + (((size_t)b * d.Hi + hi) * d.Wi + wi) * d.Cin + wci0 + nv * 4);
+                for (int j = 0; j < 2; ++j) {
+                    const int idx = tid + NPROD * j, k = idx >> 4, nv = idx & 15;
+                    rb[j] = ldg4(Q + (size_t)(cb.c + k) * Kfull + (size_t)tap * d.Cin + n0 + nv * 4);
                 }
-                rb[j] = v;
+            } else {
+                // B'[n=ci][k=pix] = X[pixel shifted by the tap][ci0 + n]
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int idx = tid + NPROD * j, k = idx >> 4, nv = idx & 15;
+                    const int pix = k0 + k;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (pix < Kred) {
+                        const int b = pix / (d.Ho * d.Wo), rem = pix - b * d.Ho * d.Wo;
+                        const int ho = rem / d.Wo, wo = rem - ho * d.Wo;
+                        const int hi = ho * d.stride - d.pad + wr, wi = wo * d.stride - d.pad + wsx;
+                        if ((unsigned)hi < (unsigned)d.Hi && (unsigned)wi < (unsigned)d.Wi)
+                            v = ldg4(Q + (((size_t)b * d.Hi + hi) * d.Wi + wi) * d.Cin + wci0 + nv * 4);
+                    }
+                    rb[j] = v;
+                }
             }
-        }
-    };
-    auto stash = [&](int s, const float4 (&ra)[8], const float4 (&rb)[4]) {
+            ++kb_b;
+            if (MODE == DGRAD) advance(cb);
+        };
+        auto stash = [&](int s, const float4 (&ra)[4], const float4 (&rb)[2]) {
+            if (MODE != WGRAD) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    split_store4(sm.a_hi[s], sm.a_lo[s], a_off + (j >> 1) * GROUP_BYTES + (j & 1) * 4 * CORE_BYTES, ra[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int idx = tid + NPROD * j;
+                    split_store_t(sm.a_hi[s], sm.a_lo[s], (idx & 31) * 4, idx >> 5, ra[j]);
+                }
+            }
+            if (MODE == FWD) {
+                split_store4(sm.b_hi[s], sm.b_lo[s], b_off, rb[0]);
+                split_store4(sm.b_hi[s], sm.b_lo[s], b_off + 4 * CORE_BYTES, rb[1]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int idx = tid + NPROD * j;
+                    split_store_t(sm.b_hi[s], sm.b_lo[s], (idx & 15) * 4, idx >> 4, rb[j]);
+                }
+            }
+        };
+
+        // Programmatic dependent launch: everything above (barrier init, TMEM allocation, index set-up) and -- for the
+        // forward and data-gradient products -- the first WEIGHT tiles do not depend on the previous kernel in the stream
+        // and overlap its tail; activations are touched only after the wait.  (Weights are never written by the kernel
+        // that immediately precedes a convolution: optimizer updates are followed by a normally serialized launch.)
+        float4 ra[STAGES][4], rb[STAGES][2];
         if (MODE != WGRAD) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                split_store4(sm.a_hi[s], sm.a_lo[s], a_off + (j >> 1) * GROUP_BYTES + (j & 1) * 4 * CORE_BYTES, ra[j]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int idx = tid + NT * j;
-                split_store_t(sm.a_hi[s], sm.a_lo[s], (idx & 31) * 4, idx >> 5, ra[j]);
-            }
+            for (int f = 0; f < STAGES; ++f)
+                if (f < nkb) fetch_b(rb[f]);
         }
-        if (MODE == FWD) {
+        DBOA_TL(2);
+        pdl_wait();
+        pdl_trigger();
+        DBOA_TL(3);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                split_store4(sm.b_hi[s], sm.b_lo[s], b_off + (j >> 1) * GROUP_BYTES + (j & 1) * 4 * CORE_BYTES, rb[j]);
-        } else {
+        for (int f = 0; f < STAGES; ++f)
+            if (f < nkb) { fetch_a(ra[f]); if (MODE == WGRAD) fetch_b(rb[f]); }
+        for (int it0 = 0, round = 0; it0 < nkb; it0 += STAGES, ++round) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int idx = tid + NT * j;
-                split_store_t(sm.b_hi[s], sm.b_lo[s], (idx & 15) * 4, idx >> 4, rb[j]);
-            }
-        }
-    };
-
-    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, index set-up) and -- for the
-    // forward and data-gradient products -- the first WEIGHT tiles do not depend on the previous kernel in the stream
-    // and overlap its tail; activations are touched only after the wait.  (Weights are never written by the kernel
-    // that immediately precedes a convolution: optimizer updates are followed by a normally serialized launch.)
-    float4 ra[2][8], rb[2][4];
-    if (MODE != WGRAD) {
-        if (nkb > 0) fetch(kb_begin, ra[0], rb[0], false, true);
-        if (nkb > 1) fetch(kb_begin + 1, ra[1], rb[1], false, true);
-    }
-    DBOA_TL(2);
-    pdl_wait();
-    pdl_trigger();
-    DBOA_TL(3);
-    if (nkb > 0) fetch(kb_begin, ra[0], rb[0], true, MODE == WGRAD);
-    if (nkb > 1) fetch(kb_begin + 1, ra[1], rb[1], true, MODE == WGRAD);
-    for (int it0 = 0; it0 < nkb; it0 += 2) {
-#pragma unroll
-        for (int f = 0; f < 2; ++f) {
-            const int it = it0 + f;
-            if (it < nkb) {
-                const int s = f;                                                                  // stage == register set
-                if (it >= STAGES) mbar_wait(&sm.mma_done[s], (uint32_t)(((it >> 1) - 1) & 1));   // stage buffers free again
-                stash(s, ra[f], rb[f]);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async-proxy (UMMA) reads
-                __syncthreads();
-                if (it == 0) DBOA_TL(4);
-                if (it + 2 < nkb) fetch(kb_begin + it + 2, ra[f], rb[f], true, true);          // in flight behind the MMAs below
-                if (tid == 0) {
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t ah = smem_u32(sm.a_hi[s]), al = smem_u32(sm.a_lo[s]);
-                    const uint32_t bh = smem_u32(sm.b_hi[s]), bl = smem_u32(sm.b_lo[s]);
-#pragma unroll
-                    for (int kk = 0; kk < BK / 8; ++kk) {
-                        const uint32_t koff = kk * 2 * CORE_BYTES;                 // 8 tf32 = two 16-byte chunks along K
-                        const uint64_t dah = make_desc(ah + koff), dal = make_desc(al + koff);
-                        const uint64_t dbh = make_desc(bh + koff), dbl = make_desc(bl + koff);
-                        mma_tf32(tmem_d, dah, dbh, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                        mma_tf32(tmem_d, dah, dbl, idesc, 1u);
-                        mma_tf32(tmem_d, dal, dbh, idesc, 1u);
-                    }
-                    umma_commit(&sm.mma_done[s]);        // arrives when every MMA issued so far has completed
+            for (int f = 0; f < STAGES; ++f) {
+                const int it = it0 + f;
+                if (it < nkb) {
+                    const int s = f;                                                              // stage == register set
+                    DBOA_TLC(it, 0);
+                    if (round > 0) mbar_wait(&sm.empty[s], (uint32_t)((round - 1) & 1));         // the MMAs that read this stage are done
+                    DBOA_TLC(it, 1);
+                    stash(s, ra[f], rb[f]);
+                    DBOA_TLC(it, 2);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async-proxy (UMMA) reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.full[s]);
+                    DBOA_TLC(it, 3);
+                    if (it == 0) DBOA_TL(4);
+                    if (it + STAGES < nkb) { fetch_a(ra[f]); fetch_b(rb[f]); }                    // in flight behind the next stage
+                    DBOA_TLC(it, 4);
                 }
             }
         }
     }
     DBOA_TL(5);
-    if (nkb > 0) {                                        // the last commit covers all MMAs of this CTA
-        const int last = nkb - 1;
-        mbar_wait(&sm.mma_done[last & 1], (uint32_t)((last >> 1) & 1));
-    }
+    if (nkb > 0) mbar_wait(&sm.done, 0u);                 // all MMAs of this CTA have completed
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     DBOA_TL(6);
 
-    // ---- epilogue: thread t owns accumulator lane (= output row) t
+    // ---- epilogue: producer warp w reads TMEM lanes (w & 3) * 32 .. + 31 (= output rows), columns (w >> 2) * 32 .. + 31
     const int nz = gridDim.z;
     float* red = reinterpret_cast<float*>(sm.a_hi[0]);    // 128 rows x RED_LD floats (34 KB) over the A tiles, free after the last MMA
-#pragma unroll
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    if (warp < NPW) {
+        const int q4 = warp & 3, cgp = warp >> 2;
         uint32_t r[32];
         if (nkb > 0) {
-            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            const uint32_t taddr = tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(cgp * 32);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -382,16 +443,15 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
             for (int q = 0; q < 32; ++q) r[q] = 0u;
         }
         // the fp32 tile goes through shared memory (thread = row, conflict free) so that global stores are row-contiguous
+        float* dstrow = red + (q4 * 32 + lane) * RED_LD + cgp * 32;
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(red + tid * RED_LD + c0 + q * 4) =
-                make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
-                            __uint_as_float(r[q * 4 + 3]));
+            *reinterpret_cast<float4*>(dstrow + q * 4) = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
+                                                                     __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
     }
     DBOA_TL(7);
     if (nz == 1) {
         __syncthreads();
-#pragma unroll 4
         for (int v = tid; v < BM * (BN / 4); v += NT) {               // 16 lanes write one 256-byte output row
             const int lr = v >> 4, c4 = (v & 15) * 4;
             const int row = m0 + lr;
@@ -408,22 +468,24 @@ __global__ void __launch_bounds__(NT) conv_tf32x3_kernel(const float* __restrict
         DBOA_TL(8);
         const int rank = (int)cluster.block_rank();
         const int rows_per = BM / nz;                                 // nz is a power of two <= 16
-        const float* peers[16];
-#pragma unroll
-        for (int z = 0; z < 16; ++z) peers[z] = cluster.map_shared_rank(red, z < nz ? z : 0);
         for (int v = tid; v < rows_per * (BN / 4); v += NT) {
             const int lr = rank * rows_per + (v >> 4), c4 = (v & 15) * 4;
             const int row = m0 + lr;
             if (row >= Mrows) continue;
             float4* dst = reinterpret_cast<float4*>(O + (size_t)row * ldo + n0 + c4);
-            float4 q[16];                                             // all remote loads in flight before the first add
-#pragma unroll
-            for (int z = 0; z < 16; ++z)
-                if (z < nz) q[z] = *reinterpret_cast<const float4*>(peers[z] + lr * RED_LD + c4);
             float4 sacc = accumulate ? *dst : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int z = 0; z < 16; ++z)
-                if (z < nz) { sacc.x += q[z].x; sacc.y += q[z].y; sacc.z += q[z].z; sacc.w += q[z].w; }
+            for (int zb = 0; zb < 16; zb += 8) {                      // 8 remote loads in flight, then added in the order z = 0..nz-1
+                if (zb < nz) {
+                    float4 q[8];
+#pragma unroll
+                    for (int z = 0; z < 8; ++z)
+                        if (zb + z < nz) q[z] = *reinterpret_cast<const float4*>(cluster.map_shared_rank(red, zb + z) + lr * RED_LD + c4);
+#pragma unroll
+                    for (int z = 0; z < 8; ++z)
+                        if (zb + z < nz) { sacc.x += q[z].x; sacc.y += q[z].y; sacc.z += q[z].z; sacc.w += q[z].w; }
+                }
+            }
             *dst = sacc;
         }
         DBOA_TL(9);

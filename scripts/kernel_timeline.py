@@ -28,7 +28,7 @@ NAMES = ['prologue', 'w-prefetch', 'dep-wait', 'stage k0', 'mma issue', 'mma don
 SHAPES = [(56, 64, 64, 1, 1, 0), (56, 64, 64, 3, 1, 1), (28, 128, 512, 1, 1, 0), (14, 1024, 256, 1, 1, 0), (14, 256, 256, 3, 1, 1),
           (7, 512, 2048, 1, 1, 0), (7, 512, 512, 3, 1, 1)]
 B = 1
-buf = torch.zeros(4096 * 16, dtype=torch.int64, device='cuda')
+buf = torch.zeros(4096 * 16, dtype=torch.int64, device='cuda')      # [cta][16] phase stamps; slots 40000.. = per-iteration cycle stamps of CTA 0
 for mode in ('fwd', 'dgrad'):
     for (H, Cin, Cout, k, s, p) in SHAPES:
         Ho = (H + 2 * p - k) // s + 1
@@ -54,7 +54,8 @@ for mode in ('fwd', 'dgrad'):
         for _ in range(4):
             run()
         torch.cuda.synchronize()
-        t = buf.view(-1, 16).cpu()
+        clk = buf[40000:40000 + 96].view(12, 8).cpu()
+        t = buf[:40000].view(-1, 16).cpu()
         t = t[t[:, 0] > 0][:, :11].double()
         ncta = t.shape[0]
         t0 = t[:, 0].min()
@@ -67,3 +68,8 @@ for mode in ('fwd', 'dgrad'):
             t[:, 9] = t[:, 7]
             d = t[:, 1:] - t[:, :-1]
         print('    ' + '  '.join(f'{n}={d[:, i].median() / 1e3:.2f}/{d[:, i].max() / 1e3:.2f}' for i, n in enumerate(NAMES)) + '   (median/max us)')
+        rows = [r for r in clk.tolist() if r[0] > 0]
+        if rows:        # CTA 0: producer thread 0 [wait stage free, stash, fence+arrive, fetch issue] and MMA thread [wait full, issue 12 MMA + commit]
+            print('    CTA0 cycles/iter producer[free,stash,arrive,fetch] total | mma[wait,issue]: ' + '  '.join(
+                '[' + ','.join(str(r[j + 1] - r[j]) for j in range(4)) + f']{(rows[i + 1][0] - r[0]) if i + 1 < len(rows) else r[4] - r[0]}'
+                + f'|[{r[6] - r[5]},{r[7] - r[6]}]' for i, r in enumerate(rows)))
