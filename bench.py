@@ -147,6 +147,17 @@ def time_oracle(workload, steps, warmup):
     return 1.0 / float(np.median(times)), float(np.sum(times))
 
 
+def forward_traffic_mb():
+    """DRAM bytes of one dboa_hmr_forward (b=1) from the committed ncu capture; None when the capture is absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01b_forward_traffic.json')
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return (d['dram_bytes_read'] + d['dram_bytes_write']) / 1e6
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def cpu_model():
     try:
         for line in open('/proc/cpuinfo'):
@@ -283,7 +294,8 @@ def run_ours(args, rank, world, local):
         achieved = FWD_MB(1) / 1e3 / (fwd_ms / 1e3)
         roof = {'bound': 'hbm', 'kernel': f'dboa_hmr_forward b=1 ({fwd_launches} launches: 53 conv + 53 GroupNorm + head)',
                 'achieved': achieved, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'algorithmic_MB_per_launch': FWD_MB(1), 'ms_per_launch': fwd_ms,
+                'traffic': forward_traffic_mb(), 'traffic_unit': 'MB per forward (dram__bytes_read.sum + dram__bytes_write.sum, ncu capture '
+                'profiles/r01b_forward_traffic.json)', 'algorithmic_MB_per_launch': FWD_MB(1), 'ms_per_launch': fwd_ms,
                 'step_model': {'algorithmic_GB_per_frame': 3.63, 'achieved_GBps': 3.63 / (ms_dev / 1000.0 / args.steps),
                                'frac': 3.63 / (ms_dev / 1000.0 / args.steps) / peak}}
         if world == 1 and not args.no_cpu_baseline:
