@@ -47,39 +47,58 @@ def default_options(**over):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML, every 2 ms from a
+    thread (the timed region is ~0.2 s: `nvidia-smi -lms` starts too slowly to see it)."""
+    REASONS = (('hw_slowdown', 0x8), ('sw_thermal_slowdown', 0x20), ('hw_thermal_slowdown', 0x40), ('sw_power_cap', 0x4))
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, device_index):
+        self.sm, self.bits, self.smax, self.h, self.run, self.err = [], 0, None, None, False, None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            uuid = uuid if uuid.startswith('GPU-') else 'GPU-' + uuid
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:      # noqa: BLE001
+            self.err = f'NVML unavailable: {e}'
+
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+
+    def _loop(self):
+        while self.run:
+            try:
+                self._sample()
+            except Exception as e:      # noqa: BLE001
+                self.err = str(e)
+                return
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
-                                          '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+        if self.h is None:
+            return
+        self.run = True
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace('.', '').isdigit()]
-        smax = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace('.', '').isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) > 8:
-                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
-                    if v.lower().startswith('active'):
-                        reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        if self.h is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [self.err or 'NVML unavailable'], 'samples': 0}
+        self.run = False
+        self.thread.join(timeout=1.0)
+        reasons = sorted(name for name, bit in self.REASONS if self.bits & bit)
+        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.smax, 'reasons': reasons,
+                'samples': len(self.sm)}
 
 
 def load_peaks():
@@ -208,10 +227,13 @@ def run_ours(args, rank, world, local):
     keys = ('image', 'smpl_j2d')
     host = [{k: stream[t][k].pin_memory() for k in keys} for t in range(n_frames)]
     resident = [{k: host[t][k].to(dev) for k in keys} for t in range(n_frames)]
-    out_host = {k: torch.empty(s, pin_memory=True) for k, s in (('rotmat', (1, 24, 3, 3)), ('betas', (1, 10)), ('cam', (1, 3)),
-                                                                  ('joints', (1, 49, 3)), ('vertices', (1, 6890, 3)))}
+    # two pinned output slots: the outputs of frame t are copied back while frame t+1 is adapted, and read (event wait) before
+    # the slot is reused two steps later -- every step copies its result to the host inside the timed region
+    out_host = [{k: torch.empty(s, pin_memory=True) for k, s in (('rotmat', (1, 24, 3, 3)), ('betas', (1, 10)), ('cam', (1, 3)),
+                                                                   ('joints', (1, 49, 3)), ('vertices', (1, 6890, 3)))} for _ in range(2)]
+    landed = [None, None]
     h2d = sum(v.numel() * 4 for v in host[0].values())
-    d2h = sum(v.numel() * 4 for v in out_host.values())
+    d2h = sum(v.numel() * 4 for v in out_host[0].values())
 
     def step(t, from_host):
         ad.global_step, ad.fit_losses = t, {}
@@ -220,10 +242,23 @@ def run_ours(args, rank, world, local):
         else:
             batch = resident[t]
         ad.adapt(batch)
-        pred = ad.predict(batch['image'])
+        if args.serial_output:
+            pred = ad.predict(batch['image'])
+            if from_host:
+                for k, v in out_host[0].items():
+                    v.copy_(pred[k], non_blocking=True)
+            return pred
+        # output forward + SMPL of this frame on the adaptor's side stream: it overlaps the next frame's adaptation
+        pred, ev = ad.predict_async(batch['image'])
         if from_host:
-            for k, v in out_host.items():
-                v.copy_(pred[k], non_blocking=True)
+            slot = t & 1
+            if landed[slot] is not None:
+                landed[slot].synchronize()                  # the host has the result that used this slot
+            with torch.cuda.stream(ad.output_stream):
+                for k, v in out_host[slot].items():
+                    v.copy_(pred[k], non_blocking=True)
+                landed[slot] = torch.cuda.Event()
+                landed[slot].record()
         return pred
 
     def barrier():
@@ -307,6 +342,8 @@ def run_ours(args, rank, world, local):
                 'data': 'synthetic',
                 'config': {'workload': f'{args.workload}: 3DPW-shape synthetic stream, batch 1 per GPU, S-adapt scope '
                                        '(adaptation + one output forward/SMPL)', 'flags': WORKLOADS[args.workload],
+                           'output': 'serial' if args.serial_output else 'output forward + SMPL of frame t on a side stream, overlapped with '
+                           'the adaptation of frame t+1 (same weights; the optimiser step waits for the read); --serial-output disables',
                            'parallelism': f'dp{world}: frames sharded over ranks, 1 all-reduce of the 107.9 MB outer gradient per step'
                            if world > 1 else 'single GPU',
                            'l2': 'per-step working set (theta, fast weights, Adam m/v, teacher, gradient arena: 6 x 108 MB + '
@@ -326,6 +363,8 @@ def main():
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--cpu-frames', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--serial-output', action='store_true',
+                    help='run the output forward on the adaptation stream (no overlap with the next frame)')
     ap.add_argument('--tc', type=int, default=-1, help='tensor-core conv mode override (0 fp32 CUDA cores, 1 forward, 2 forward+dgrad+wgrad, 3 forward+dgrad)')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':

@@ -118,6 +118,24 @@ class Adaptor(BaseAdaptor):
             out = self.decode_smpl_params(rot, shape)
         return dict(rotmat=rot, betas=shape, cam=cam, joints=out['s3d'], vertices=out['vts'])
 
+    def predict_async(self, image):
+        """``predict`` issued on a side stream.  The output forward of frame t and the adaptation of frame t+1 read the
+        same weights, so the caller can go on enqueueing the next frame on its own stream: the two chains of small kernels
+        overlap on the device, and the next optimiser step waits for this read before it overwrites the weights.
+        Returns (outputs, event); consumers on another stream (or the host) wait for the event first."""
+        cur = torch.cuda.current_stream()
+        if getattr(self, 'output_stream', None) is None:
+            self.output_stream = torch.cuda.Stream(device=image.device)
+        side = self.output_stream
+        side.wait_stream(cur)                              # the weights (and the frame) are ready
+        with torch.cuda.stream(side):
+            out = self.predict(image)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        image.record_stream(side)
+        self.optimizer.wait_before_write.append(ev)
+        return out, ev
+
     def inference(self, batch, model, need_feature=False):
         image, gt_pose, gt_betas, gender = batch['image'], batch['pose'], batch['betas'], batch['gender']
         model.eval()

@@ -30,6 +30,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.v = torch.zeros_like(self.model.arena)
         self.step_count = 0
         self.pre_step_hook = None                              # e.g. the data-parallel gradient all-reduce
+        self.wait_before_write = []                            # events of side-stream readers of the weights (Adaptor.predict_async)
 
     def _gather_grads(self):
         """Make sure every ``p.grad`` lives in the flat gradient arena (autograd may have re-created them)."""
@@ -62,6 +63,11 @@ class FusedAdam(torch.optim.Optimizer):
         g = self._gather_grads()
         if self.pre_step_hook is not None:
             self.pre_step_hook(g)
+        if self.wait_before_write:                             # a side stream may still be reading the weights this step overwrites
+            cur = torch.cuda.current_stream()
+            for ev in self.wait_before_write:
+                cur.wait_event(ev)
+            self.wait_before_write = []
         grp = self.param_groups[0]
         self.step_count += 1
         t = None if teacher is None else teacher.arena

@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+nvidia-smi -L
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.log 2> gpurun_out/bench_n2.err
+tail -1 gpurun_out/bench_n2.log; tail -5 gpurun_out/bench_n2.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 > gpurun_out/bench_n2_ref.log 2> gpurun_out/bench_n2_ref.err
+tail -1 gpurun_out/bench_n2_ref.log; tail -3 gpurun_out/bench_n2_ref.err

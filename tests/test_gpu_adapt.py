@@ -102,3 +102,34 @@ def test_excute_loop_runs(asset_dir, tmp_path, golden):
     ad.teacher.eval()
     out = ad.excute(max_frames=3)
     assert np.isfinite(out['mpjpe']) and np.isfinite(out['pampjpe']) and os.path.exists(os.path.join(ad.exppath, 'res.txt'))
+
+
+def test_output_forward_on_side_stream_is_equivalent(asset_dir, tmp_path, golden):
+    """``predict_async`` (output forward of frame t overlapped with the adaptation of frame t+1) must give the same
+    outputs and leave the adaptation trajectory bit-identical to the serial ``predict``: the optimiser step waits for the
+    side-stream read of the weights before it overwrites them."""
+    from dynaboa_b200 import synthetic
+    gd = golden('adapt_c2')
+    runs = []
+    for overlap in (False, True):
+        ad, opts = build_adaptor(asset_dir, tmp_path / f'o{int(overlap)}', gd)
+        ad.teacher.eval()                                  # deterministic teacher (no dropout masks)
+        ad.fused_eval = 'none'
+        stream = synthetic.SyntheticStream(length=6, batch_size=opts.batch_size)
+        outs = []
+        for t in range(6):
+            batch = {k: v.cuda() if torch.is_tensor(v) else v for k, v in stream[t].items()}
+            ad.global_step, ad.fit_losses = t, {}
+            ad.adapt(batch)
+            if overlap:
+                pred, ev = ad.predict_async(batch['image'])
+                outs.append((pred, ev))
+            else:
+                outs.append((ad.predict(batch['image']), None))
+        torch.cuda.synchronize()
+        runs.append((ad.model.module.arena.clone(), [{k: v.clone() for k, v in p.items()} for p, _ in outs]))
+    (theta_s, out_s), (theta_a, out_a) = runs
+    assert torch.equal(theta_s, theta_a)
+    for a, b in zip(out_s, out_a):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
