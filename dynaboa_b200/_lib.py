@@ -73,6 +73,8 @@ SIGNATURES = {
     'dboa_ema_update': (I, [P, P, L, F, P]),
     'dboa_cosine_pairs': (I, [C.POINTER(P), C.POINTER(P), C.POINTER(L), I, P, L, P, F, P]),
     'dboa_retrieval_nearest': (I, [P, P, I, I, P, P, P]),
+    'dboa_eval_scratch_floats': (L, [I, I]),
+    'dboa_eval_metrics': (I, [P, P, P, P, I, I, P, I, P, P, I, P]),
 }
 
 _ERRORS = {-1: 'DBOA_ERR_ARG', -2: 'DBOA_ERR_SHAPE', -3: 'DBOA_ERR_CUDA', -4: 'DBOA_ERR_UNSUPPORTED'}

@@ -15,9 +15,8 @@ import os.path as osp
 import numpy as np
 import torch
 
-from . import constants
+from . import _lib, constants
 from .base_adaptor import BaseAdaptor
-from .pose_utils import compute_similarity_transform_batch
 
 
 class Adaptor(BaseAdaptor):
@@ -143,20 +142,14 @@ class Adaptor(BaseAdaptor):
             out = model(image, need_feature)
             pred_rotmat, pred_shape, pred_cam = out[0], out[1], out[2]
             pred_vertices = self.decode_smpl_params(pred_rotmat, pred_shape)['vts']
-            J = self.J_regressor.to(self.device)
             gt_vertices = self.smpl_male(global_orient=gt_pose[:, :3], body_pose=gt_pose[:, 3:], betas=gt_betas).vertices
             gt_vertices_f = self.smpl_female(global_orient=gt_pose[:, :3], body_pose=gt_pose[:, 3:], betas=gt_betas).vertices
             gt_vertices = torch.where((gender == 1).view(-1, 1, 1), gt_vertices_f, gt_vertices)
-            gt_k = torch.matmul(J, gt_vertices)
-            gt_k = gt_k[:, self.joint_mapper_h36m] - gt_k[:, [0]]
-            pr_k = torch.matmul(J, pred_vertices)
-            pr_k = pr_k[:, self.joint_mapper_h36m] - pr_k[:, [0]]
-            mpjpe = torch.sqrt(((pr_k - gt_k) ** 2).sum(-1)).mean(-1).cpu().numpy()
-            S1, S2 = pr_k.cpu().numpy(), gt_k.cpu().numpy()
-            S1_hat = compute_similarity_transform_batch(S1, S2)
-            pampjpe = np.sqrt(((S1_hat - S2) ** 2).sum(-1)).mean(-1)
             gt_neutral = self.smpl_neutral(betas=gt_betas, body_pose=gt_pose[:, 3:], global_orient=gt_pose[:, :3], pose2rot=True).vertices
-            pve = torch.sqrt(((gt_neutral - pred_vertices) ** 2).sum(2)).mean().item()
+            # H36M-regressor joints, MPJPE, Procrustes PA-MPJPE and PVE in two launches; ONE 3-float read-back per sample
+            # (the reference copies joints and both meshes to the host and runs a numpy SVD per sample: :217-240)
+            metrics = self.eval_metrics(pred_vertices, gt_vertices, gt_neutral).cpu().numpy()
+            mpjpe, pampjpe, pve = metrics[:, 0], metrics[:, 1], float(metrics[:, 2].mean())
         if getattr(self.options, 'cache_results', 0):
             cam_t = torch.stack([pred_cam[:, 1], pred_cam[:, 2], 2 * 5000. / (constants.IMG_RES * pred_cam[:, 0] + 1e-9)], dim=-1)
             torch.save({'verts': pred_vertices.cpu().numpy(), 'cam': cam_t.cpu().numpy(), 'rotmat': pred_rotmat.cpu().numpy(),
@@ -164,6 +157,21 @@ class Adaptor(BaseAdaptor):
         if need_feature:
             return mpjpe * 1000, pampjpe * 1000, pve * 1000, out[3]
         return mpjpe * 1000, pampjpe * 1000, pve * 1000
+
+    def eval_metrics(self, pred_vertices, gt_vertices, gt_vertices_neutral):
+        """(B,3) device tensor: MPJPE, PA-MPJPE, PVE (metres) of each sample -- ``dboa_eval_metrics``."""
+        B, dev = pred_vertices.shape[0], pred_vertices.device
+        if getattr(self, '_eval_consts', None) is None or self._eval_consts[0].device != dev:
+            self._eval_consts = (self.J_regressor.to(dev).contiguous().float(),
+                                 torch.as_tensor(np.asarray(self.joint_mapper_h36m), dtype=torch.int32, device=dev))
+        J, jmap = self._eval_consts
+        _lib.require_cuda(pred_vertices, gt_vertices, gt_vertices_neutral)
+        scratch = torch.empty(_lib.load().dboa_eval_scratch_floats(B, J.shape[0]), dtype=torch.float32, device=dev)
+        out = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        keep = [t.contiguous().float() for t in (pred_vertices, gt_vertices, gt_vertices_neutral)]
+        _lib.call('dboa_eval_metrics', _lib.ptr(keep[0]), _lib.ptr(keep[1]), _lib.ptr(keep[2]), _lib.ptr(J), int(J.shape[0]),
+                  int(pred_vertices.shape[1]), _lib.ptr(jmap), int(jmap.numel()), _lib.ptr(scratch), _lib.ptr(out), B, _lib.stream())
+        return out
 
     def adapt(self, batch):
         from .fused import fused_adapt

@@ -10,7 +10,9 @@
 namespace dboa {
 
 // ---------------------------------------------------------------------------------------------
-// forward: one warp per output neuron, up to 8 batch rows per pass
+// forward: FOUR warps per output neuron (each a quarter of K, all its loads in flight at once), two neurons per
+// CTA, up to 8 batch rows per pass.  At batch 1-3 this is a weight-streaming GEMV whose time is the number of
+// dependent load round trips per warp, not bytes: one warp per neuron walked K in 17 serial steps.
 // ---------------------------------------------------------------------------------------------
 template <int BT>
 __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ W, int ldw,
@@ -18,60 +20,75 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ mask, float* __restrict__ pre,
                                                          float* __restrict__ post, int ld_out, float* __restrict__ post2, int ld_out2,
                                                          int b0, int nb, int N, int K) {
+    __shared__ float sred[8][BT];
     pdl_wait();
     pdl_trigger();
-    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (n >= N) return;
-    const float* wr = W + (size_t)n * ldw;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, part = warp & 3;
+    const int n = blockIdx.x * 2 + (warp >> 2);
     float acc[BT];
 #pragma unroll
     for (int b = 0; b < BT; ++b) acc[b] = 0.f;
-    const bool vec = ((ldw & 3) == 0) && ((ldx & 3) == 0);
-    int kdone = 0;
-    if (vec) {
-        const int K4 = K >> 2;
-        for (int k4 = lane; k4 < K4; k4 += 32) {
-            float4 wv = ldg4(wr + k4 * 4);
+    if (n < N) {
+        const float* wr = W + (size_t)n * ldw;
+        const bool vec = ((ldw & 3) == 0) && ((ldx & 3) == 0);
+        int kdone = 0;
+        if (vec) {
+            const int K4 = K >> 2, per = (K4 + 3) >> 2;
+            const int kbeg = part * per, kend = min(K4, kbeg + per);
+            for (int base = kbeg; base < kend; base += 160) {          // 5 float4 per lane and pass, issued together
+                float4 wv[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    const int k4 = base + lane + 32 * i;
+                    wv[i] = k4 < kend ? ldg4(wr + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int b = 0; b < BT; ++b)
+                    if (b < nb) {
+                        float4 xv[5];
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            const int k4 = base + lane + 32 * i;
+                            xv[i] = k4 < kend ? ldg4(x + (size_t)(b0 + b) * ldx + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 5; ++i)
+                            acc[b] += (wv[i].x * xv[i].x + wv[i].y * xv[i].y) + (wv[i].z * xv[i].z + wv[i].w * xv[i].w);
+                    }
+            }
+            kdone = K4 * 4;
+        }
+        // scalar remainder (K % 4, or everything when the pitches are not 16-byte multiples): split over the four warps too
+        for (int k = kdone + part * 32 + lane; k < K; k += 128) {
+            const float wv = __ldg(wr + k);
 #pragma unroll
             for (int b = 0; b < BT; ++b)
-                if (b < nb) {
-                    float4 xv = ldg4(x + (size_t)(b0 + b) * ldx + k4 * 4);
-                    acc[b] += (wv.x * xv.x + wv.y * xv.y) + (wv.z * xv.z + wv.w * xv.w);
-                }
+                if (b < nb) acc[b] += wv * __ldg(x + (size_t)(b0 + b) * ldx + k);
         }
-        kdone = K4 * 4;
-    }
-    for (int k = kdone + lane; k < K; k += 32) {
-        float wv = __ldg(wr + k);
-#pragma unroll
-        for (int b = 0; b < BT; ++b)
-            if (b < nb) acc[b] += wv * __ldg(x + (size_t)(b0 + b) * ldx + k);
     }
 #pragma unroll
-    for (int b = 0; b < BT; ++b) acc[b] = warp_sum(acc[b]);
-    if (lane == 0) {
-        const float bn = bias ? bias[n] : 0.f;
-#pragma unroll
-        for (int b = 0; b < BT; ++b)
-            if (b < nb) {
-                const int bb = b0 + b;
-                float y = acc[b] + bn;
-                if (addend) y += addend[(size_t)bb * ld_add + n];
-                if (pre) pre[(size_t)bb * ld_out + n] = y;
-                float m = mask ? mask[(size_t)bb * N + n] : 1.0f;
-                float o = y * m;
-                if (post) post[(size_t)bb * ld_out + n] = o;
-                if (post2) post2[(size_t)bb * ld_out2 + n] = o;
-            }
+    for (int b = 0; b < BT; ++b) {
+        acc[b] = warp_sum(acc[b]);
+        if (lane == 0) sred[warp][b] = acc[b];
+    }
+    __syncthreads();
+    if (n < N && part == 0 && lane < nb) {                 // lane b finishes batch row b: the four K-quarters in fixed order
+        const int b = lane, bb = b0 + b;
+        float y = ((sred[warp][b] + sred[warp + 1][b]) + (sred[warp + 2][b] + sred[warp + 3][b])) + (bias ? bias[n] : 0.f);
+        if (addend) y += addend[(size_t)bb * ld_add + n];
+        if (pre) pre[(size_t)bb * ld_out + n] = y;
+        const float m = mask ? mask[(size_t)bb * N + n] : 1.0f;
+        const float o = y * m;
+        if (post) post[(size_t)bb * ld_out + n] = o;
+        if (post2) post2[(size_t)bb * ld_out2 + n] = o;
     }
 }
 
 int linear_fwd(const float* x, int ldx, const float* W, int ldw, const float* bias, const float* addend, int ld_add, const float* mask,
                float* pre, float* post, int ld_out, float* post2, int ld_out2, int B, int N, int K, cudaStream_t st) {
-    const int warps_per_block = 8;
     for (int b0 = 0; b0 < B; b0 += 8) {
         int nb = B - b0 < 8 ? B - b0 : 8;
-        DBOA_TRY(launch_ex(linear_fwd_kernel<8>, dim3(ceil_div(N, warps_per_block)), dim3(256), 0, st, dim3(1, 1, 1), true, x, ldx, W, ldw, bias, addend, ld_add, mask, pre, post, ld_out, post2, ld_out2, b0, nb, N, K));
+        DBOA_TRY(launch_ex(linear_fwd_kernel<8>, dim3(ceil_div(N, 2)), dim3(256), 0, st, dim3(1, 1, 1), true, x, ldx, W, ldw, bias, addend, ld_add, mask, pre, post, ld_out, post2, ld_out2, b0, nb, N, K));
     }
     return DBOA_OK;
 }
@@ -96,6 +113,7 @@ __global__ void __launch_bounds__(256) linear_dgrad_kernel(const float* __restri
         }
         __syncthreads();
         if (k < K) {
+#pragma unroll 8
             for (int j = 0; j < cnt; ++j) {
                 float wv = __ldg(W + (size_t)(n0 + j) * ldw + k);
 #pragma unroll
@@ -114,17 +132,19 @@ __global__ void linear_dgrad_reduce_kernel(const float* __restrict__ part, float
     if (i >= B * K) return;
     int b = i / K, k = i - b * K;
     float s = 0.f;
+#pragma unroll 8
     for (int z = 0; z < nsplit; ++z) s += part[((size_t)z * B + b) * K + k];
     dx[(size_t)b * ldx + k] = s;
 }
 
 int linear_dgrad(const float* dy, int ldy, const float* W, int ldw, float* dx, int ldx, int B, int N, int K, float* ws, size_t ws_floats,
                  cudaStream_t st) {
-    int nsplit = N >= 512 ? 16 : (N >= 128 ? 2 : 1);
-    while (nsplit > 1 && (size_t)nsplit * B * K > ws_floats) nsplit >>= 1;
+    // 32 rows of W per CTA: at batch 1-3 the kernel is a chain of dependent weight loads, so many short CTAs beat few long ones
+    int nsplit = ceil_div(N, 32);
+    while (nsplit > 1 && (size_t)nsplit * B * K > ws_floats) nsplit = (nsplit + 1) >> 1;
     if ((size_t)nsplit * B * K > ws_floats) return DBOA_ERR_ARG;
     int nlen = ceil_div(N, nsplit);
-    nlen = (nlen + 127) / 128 * 128;
+    nlen = (nlen + 31) / 32 * 32;
     nsplit = ceil_div(N, nlen);
     for (int b0 = 0; b0 < B; b0 += 8) {
         int nb = B - b0 < 8 ? B - b0 : 8;

@@ -185,7 +185,7 @@ struct Scratch {
         dxc = take((long long)B * HEAD_LD);
         dxf = take((long long)B * 2048);
         tmp1024 = take((long long)B * HID);
-        lin_ws_floats = 16LL * B * HEAD_LD;
+        lin_ws_floats = 32LL * B * HEAD_LD;
         lin_ws = take(lin_ws_floats);
         total = off;
     }

@@ -60,4 +60,9 @@ int rot6d_bwd_launch(const float* pose6d, const float* drot, float* dpose, int n
 int ew_mul(const float* a, const float* b, float* out, size_t n, cudaStream_t st);
 int ew_add_rows(float* dst, int ld_dst, const float* a, int lda, const float* b, int ldb, int B, int n, cudaStream_t st);
 
+// ---- eval.cu (evaluation metrics on the device)
+size_t eval_scratch_floats(int B, int NJ);
+int eval_metrics(const float* pred_verts, const float* gt_verts_joints, const float* gt_verts_pve, const float* Jreg, int NJ, int NV,
+                 const int* joint_map, int n_map, float* scratch, float* out, int B, cudaStream_t st);
+
 }  // namespace dboa

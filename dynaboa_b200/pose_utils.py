@@ -1,6 +1,7 @@
 """Evaluation metrics used by the driver (reference utils/pose_utils.py:9-64): Procrustes-aligned
 error.  Host-side numpy, as in the reference: PA-MPJPE is the parity metric, not a kernel target
-("CPU numpy stays"; a batched GPU SVD is the N1 follow-up)."""
+(SURVEY.md §2).  The driver itself evaluates on the device (`Adaptor.eval_metrics` -> `dboa_eval_metrics`);
+these numpy functions remain for API compatibility (`utils.pose_utils` of the drop-in tree)."""
 import numpy as np
 
 

@@ -156,6 +156,16 @@ int dboa_cosine_pairs(const float* const* a, const float* const* b, const long l
 /* retrieval :82-84: index of the centre with the smallest cosine distance to feat (D,) among centers (K,D) */
 int dboa_retrieval_nearest(const float* feat, const float* centers, int K, int D, int* best, float* dists, dboa_stream_t stream);
 
+/* ---- evaluation metrics (dynaboa_benchmark.py:217-240, utils/pose_utils.py:9-64) -----------------
+ * pred_verts, gt_verts_joints (gender-selected SMPL mesh), gt_verts_pve (neutral mesh): (B,NV,3);
+ * J_regressor (NJ,NV) dense; joint_map (n_map,) int32 indices into the NJ regressed joints (H36M_TO_J14).
+ * Joints are centred on regressed joint 0 (pelvis) like the reference.  out (B,3) = MPJPE, PA-MPJPE (similarity
+ * Procrustes, 3x3 SVD on the device) and PVE per sample, in the unit of the meshes (metres).
+ * scratch: dboa_eval_scratch_floats(B, NJ) floats.  NJ, n_map <= 32. */
+long long dboa_eval_scratch_floats(int B, int NJ);
+int dboa_eval_metrics(const float* pred_verts, const float* gt_verts_joints, const float* gt_verts_pve, const float* J_regressor, int NJ,
+                      int NV, const int* joint_map, int n_map, float* scratch, float* out, int B, dboa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,7 +34,7 @@ OUT = os.path.join(REPO, 'tests', 'golden')
 sys.path.insert(0, REPO)
 
 from dynaboa_b200 import constants as C, synthetic  # noqa: E402
-from oracle import adaptor_ref, geometry_ref, hmr_ref, l2l_ref, prior_ref, smplx_ref  # noqa: E402
+from oracle import adaptor_ref, eval_ref, geometry_ref, hmr_ref, l2l_ref, prior_ref, smplx_ref  # noqa: E402
 
 
 def _load_by_path(name, path):
@@ -410,6 +410,42 @@ def golden_adapt(workdir, tag, n_frames, **over):
     print(f'adapt {tag} ok')
 
 
+def golden_eval():
+    """Evaluation metrics: the reference's own Procrustes (utils/pose_utils.py) inside the arithmetic of
+    dynaboa_benchmark.py:217-240, on seeded meshes (small vertex count keeps the fixture small).  Sample 2 is a mirrored
+    copy of its ground truth (det(U V^T) < 0: the orientation fix is exercised), sample 3 a similarity transform of it."""
+    ref = _load_by_path('ref_pose_utils', os.path.join(REF, 'utils', 'pose_utils.py'))
+    rng = np.random.RandomState(5)
+    B, NV, NJ = 5, 640, 17
+    jmap = np.asarray(C.H36M_TO_J14, dtype=np.int64)
+    J = rng.rand(NJ, NV).astype(np.float32) ** 8
+    J /= J.sum(1, keepdims=True)
+    gt = (rng.randn(B, NV, 3) * 0.4).astype(np.float32)
+    pred = (gt + rng.randn(B, NV, 3) * 0.05).astype(np.float32)
+    pred[2] = gt[2] * np.array([-1.0, 1.0, 1.0], dtype=np.float32)
+    q, _ = np.linalg.qr(rng.randn(3, 3))
+    q *= np.sign(np.linalg.det(q))
+    pred[3] = (1.7 * gt[3].dot(q.T) + np.array([0.3, -0.2, 0.1])).astype(np.float32)
+    gt_neutral = (gt + rng.randn(B, NV, 3) * 0.01).astype(np.float32)
+    # reference arithmetic with the reference's own Procrustes
+    gt_k = np.matmul(J[None], gt)
+    gt_k = gt_k[:, jmap] - gt_k[:, [0]]
+    pr_k = np.matmul(J[None], pred)
+    pr_k = pr_k[:, jmap] - pr_k[:, [0]]
+    mpjpe = np.sqrt(((pr_k - gt_k) ** 2).sum(-1)).mean(-1)
+    hat = ref.compute_similarity_transform_batch(pr_k, gt_k)
+    pampjpe = np.sqrt(((hat - gt_k) ** 2).sum(-1)).mean(-1)
+    pve = np.sqrt(np.sum((gt_neutral - pred) ** 2, axis=2)).mean()
+    m2, p2, v2 = eval_ref.eval_metrics(pred, gt, gt_neutral, J, jmap)
+    _same(m2, mpjpe, 'eval mpjpe', 1e-6)
+    _same(p2, pampjpe, 'eval pampjpe', 1e-5)
+    _same(v2, pve, 'eval pve', 1e-6)
+    assert pampjpe[3] < 1e-5 * np.abs(gt_k[3]).max() * 50, 'a similarity transform must align exactly'
+    np.savez_compressed(os.path.join(OUT, 'eval_metrics.npz'), pred=pred, gt=gt, gt_neutral=gt_neutral, J=J, joint_map=jmap,
+                        mpjpe=mpjpe, pampjpe=pampjpe, pve=np.float64(pve))
+    print('eval_metrics.npz', mpjpe, pampjpe, pve)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -418,7 +454,7 @@ def main():
         synthetic.write_asset_dir(os.path.join(workdir, 'data'))
         os.makedirs(os.path.join(workdir, 'data/spin_data'), exist_ok=True)
         os.symlink(os.path.join(REF, 'data/gmm_08.pkl'), os.path.join(workdir, 'data/spin_data/gmm_08.pkl'))
-        which = sys.argv[1:] or ['geometry', 'prior', 'hmr', 'smpl', 'c2', 'c3', 'c5']
+        which = sys.argv[1:] or ['geometry', 'prior', 'hmr', 'smpl', 'eval', 'c2', 'c3', 'c5']
         if 'geometry' in which:
             golden_geometry()
         if 'prior' in which:
@@ -427,6 +463,8 @@ def main():
             golden_hmr(workdir)
         if 'smpl' in which:
             golden_smpl()
+        if 'eval' in which:
+            golden_eval()
         _install_stubs()
         if 'c2' in which:   # BASELINE.json configs[1]
             golden_adapt(workdir, 'c2', 8, inner_step=1, retrieval=0, lower_level_mixtrain=0,

@@ -343,3 +343,37 @@ def test_cosine_and_retrieval(L):
     refd = 1 - F.cosine_similarity(feat.unsqueeze(0), centers)
     assert int(best.item()) == int(torch.argsort(refd)[0]) == 6
     assert rel_err(d, refd) < 1e-5
+
+
+def test_eval_metrics_on_device(L, golden):
+    """dboa_eval_metrics (H36M joints, MPJPE, 3x3-SVD Procrustes, PVE) against the reference's numpy path (golden) and,
+    on fresh random meshes with the real 6890-vertex size, against the oracle restatement."""
+    from oracle import eval_ref
+    gd = golden('eval_metrics')
+
+    def run(pred, gt, gtn, J, jmap):
+        B, NV, NJ = pred.shape[0], pred.shape[1], J.shape[0]
+        pd, gd_, gn, Jd = dev(torch.from_numpy(pred)), dev(torch.from_numpy(gt)), dev(torch.from_numpy(gtn)), dev(torch.from_numpy(J))
+        jm = torch.from_numpy(jmap.astype(np.int32)).cuda()
+        scratch = torch.empty(L.load().dboa_eval_scratch_floats(B, NJ), device='cuda')
+        out = torch.empty(B, 3, device='cuda')
+        L.call('dboa_eval_metrics', L.ptr(pd), L.ptr(gd_), L.ptr(gn), L.ptr(Jd), NJ, NV, L.ptr(jm), jm.numel(), L.ptr(scratch), L.ptr(out), B,
+               L.stream())
+        return out.cpu().numpy()
+
+    out = run(gd['pred'], gd['gt'], gd['gt_neutral'], gd['J'], gd['joint_map'])
+    scale = gd['mpjpe'].max()
+    assert np.abs(out[:, 0] - gd['mpjpe']).max() <= 2e-5 * scale
+    assert np.abs(out[:, 1] - gd['pampjpe']).max() <= 5e-5 * scale          # includes the mirrored and the exact-similarity sample
+    assert abs(out[:, 2].mean() - gd['pve']) <= 2e-5 * gd['pve']
+    rng = np.random.RandomState(11)
+    B, NV, NJ = 3, 6890, 17
+    J = (rng.rand(NJ, NV) ** 12).astype(np.float32)
+    J /= J.sum(1, keepdims=True)
+    gt = (rng.randn(B, NV, 3) * 0.5).astype(np.float32)
+    pred = (gt * 1.1 + rng.randn(B, NV, 3) * 0.08).astype(np.float32)
+    gtn = (gt + 0.02).astype(np.float32)
+    m, p, v = eval_ref.eval_metrics(pred, gt, gtn, J, gd['joint_map'])
+    out = run(pred, gt, gtn, J, gd['joint_map'])
+    assert np.abs(out[:, 0] - m).max() <= 5e-5 * m.max() and np.abs(out[:, 1] - p).max() <= 1e-4 * m.max()
+    assert abs(out[:, 2].mean() - v) <= 5e-5 * v

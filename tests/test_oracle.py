@@ -121,3 +121,15 @@ def test_adaptation_golden_c2_first_frames(golden):
         pred = ora.predict(stream[t]['image'])
         assert rel_err(pred['rotmat'], gd['rotmat'][t]) < 1e-3 and rel_err(pred['joints'], gd['joints'][t]) < 1e-3
         assert abs(rec['metrics'][-1][1].mean() - gd['metrics'][t][1].mean()) <= 1e-3 * gd['metrics'][t][1].mean()
+
+
+def test_eval_metrics_golden(golden):
+    """Evaluation arithmetic (MPJPE / Procrustes PA-MPJPE / PVE) against the outputs of the reference's own
+    utils/pose_utils.py recorded by oracle/make_golden.py, including a mirrored sample and an exact similarity."""
+    from oracle import eval_ref
+    gd = golden('eval_metrics')
+    m, p, v = eval_ref.eval_metrics(gd['pred'], gd['gt'], gd['gt_neutral'], gd['J'], gd['joint_map'])
+    assert np.abs(m - gd['mpjpe']).max() <= 1e-6 * gd['mpjpe'].max()
+    assert np.abs(p - gd['pampjpe']).max() <= 1e-5 * gd['pampjpe'].max()
+    assert abs(v - gd['pve']) <= 1e-6 * gd['pve']
+    assert p[3] < 1e-6 and p[2] > 3 * p[0]         # similarity aligns exactly; a mirror image cannot be rotated away
