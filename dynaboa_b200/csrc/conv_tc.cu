@@ -30,6 +30,7 @@
 // Accumulators live in TMEM (64 columns x 128 lanes), never in registers.
 #include <cooperative_groups.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -501,8 +502,11 @@ template <int MODE>
 static int launch(const float* p, const float* q, float* o, const ConvDims& d, int rows, int cols, int kred, int accumulate, cudaStream_t st) {
     const int nkb = (kred + BK - 1) / BK;
     const int tiles = ceil_div(rows, BM) * (cols / BN);
+    // K-slices per tile (cluster size): a power of two <= 16.  A k-block costs ~0.4 us, the cluster barrier + DSMEM reduction
+    // of a split tile ~3 us (profiles/r01b_summary.md section 6), so a split must leave at least `min_kb` k-blocks per CTA.
+    static const int min_kb = [] { const char* e = getenv("DBOA_TC_MINKB"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
     int ns = 1;
-    while (ns < 16 && tiles * ns * 2 <= 296 + tiles && nkb / (ns * 2) >= 2) ns *= 2;
+    while (ns < 16 && tiles * ns * 2 <= 296 + tiles && nkb / (ns * 2) >= min_kb) ns *= 2;
     const int per = (nkb + ns - 1) / ns;
     const size_t smem = sizeof(Smem) + 128;
     return launch_ex(conv_tf32x3_kernel<MODE>, dim3(ceil_div(rows, BM), cols / BN, ns), dim3(NT), smem, st, dim3(1, 1, ns), true, p, q, o, d, per,

@@ -31,6 +31,15 @@ def _side_stream(device):
     return _SIDE[device.index]
 
 
+def _mark(ad, name):
+    """Diagnostics (scripts/phase_times.py): when ``ad.phase_events`` is a list, record a CUDA event on the caller's stream."""
+    ev_list = getattr(ad, 'phase_events', None)
+    if ev_list is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        ev_list.append((name, ev))
+
+
 class _Pred:
     """Everything one forward graph produces (kept for its backward)."""
     __slots__ = ('image', 'rot', 'shape', 'cam', 'tape', 'verts', 'joints', 'smpl_tape', 'p2d', 'B', 'masked')
@@ -148,6 +157,7 @@ def level_backward(ad, arena, buffers, image, kp, lower, grad_arena, main=None):
         tw = o.teacherloss_weight
         w[3], w[4], w[5], w[6] = 5 * tw, 5 * tw, 0.001 * tw, 1 * tw
         targets = dict(t_p2d=t.p2d, t_j3d=t.joints, t_beta=t.shape, t_R=t.rot)
+    _mark(ad, f'{tag}: forward(s) issued')
     batched = main.B > nb
     grads = (torch.zeros_like(main.p2d), torch.zeros_like(main.joints), torch.zeros_like(main.rot), torch.zeros_like(main.shape)) \
         if batched else None
@@ -167,7 +177,9 @@ def level_backward(ad, arena, buffers, image, kp, lower, grad_arena, main=None):
                            grad_arena)
         total = total + mterm[0] * o.motionloss_weight
         ad.fit_losses['ul/motion_loss'] = mterm[0]
+    _mark(ad, f'{tag}: loss head')
     backward_graph(ad, arena, main, dp2d, dj3d, dR, dbeta, grad_arena)
+    _mark(ad, f'{tag}: backward')
     if o.retrieval:
         ex = ad.retrieval(hmr_mod._feature_views(main.tape, main.B)[5][:nb])
         if (o.lower_level_mixtrain if lower else o.upper_level_mixtrain):
@@ -200,7 +212,9 @@ def fused_adapt(ad, batch):
     teacher = ad.teacher if o.use_meanteacher else None
     evaluate = getattr(ad, 'fused_eval', 'final')
     with torch.no_grad():
+        _mark(ad, 'start')
         probe = forward_graph(ad, theta, buffers, image)            # init_features (reference :132-133)
+        _mark(ad, 'probe forward')
         if not o.use_boa:
             G.zero_()
             ad.last_upper_loss, _ = level_backward(ad, theta, buffers, image, kp, True, G, main=probe)
@@ -213,14 +227,18 @@ def fused_adapt(ad, batch):
         for i in range(o.inner_step):
             ad._inner_grad.zero_()
             level_backward(ad, fast, buffers, image, kp, True, ad._inner_grad, main=cur if i == 0 else None)
+            _mark(ad, 'lower level (loss + backward)')
             nxt = ad._fast_bufs[i % 2]
             _lib.call('dboa_sgd_update', ptr(fast), ptr(ad._inner_grad), ptr(nxt), float(o.fastlr), theta.numel(), stream())
             fast = nxt
+            _mark(ad, 'inner SGD step')
             if evaluate == 'all':
                 ad.inference(batch, _ArenaModel(model, fast))
         G.zero_()
         ad.last_upper_loss, _ = level_backward(ad, fast, buffers, image, kp, False, G)
+        _mark(ad, 'upper level (forward + loss + backward)')
         opt.step(teacher=teacher, alpha=o.alpha)                    # Adam + EMA teacher, one sweep
+        _mark(ad, 'Adam + EMA')
         result = None
         if evaluate == 'all' or (evaluate == 'final' and not o.dynamic_boa):
             result = ad.inference(batch, ad.model)
