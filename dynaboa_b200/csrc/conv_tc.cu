@@ -152,6 +152,20 @@ __device__ __forceinline__ void split_store_t(uint8_t* hi_tile, uint8_t* lo_tile
     }
 }
 
+// same, with the 4 element stores issued in the order (e + rot) & 3: when the lanes of a warp are (k & 3, (row0 >> 2) & 1, rot)
+// the 32 scalar stores of one instruction fall into 32 different banks (the plain version is an 8-way conflict)
+__device__ __forceinline__ void split_store_t_rot(uint8_t* hi_tile, uint8_t* lo_tile, int row0, int k, float4 v, int rot) {
+    const uint32_t off = (uint32_t)(row0 >> 3) * GROUP_BYTES + (uint32_t)(k >> 2) * CORE_BYTES + (uint32_t)(row0 & 7) * 16 + (uint32_t)(k & 3) * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int ee = (e + rot) & 3;
+        const float x = ee == 0 ? v.x : (ee == 1 ? v.y : (ee == 2 ? v.z : v.w));
+        const float h = tf32_hi(x);
+        *reinterpret_cast<float*>(hi_tile + off + ee * 16) = h;
+        *reinterpret_cast<float*>(lo_tile + off + ee * 16) = x - h;
+    }
+}
+
 struct Smem {
     // stage tiles in UMMA canonical layout: [row_group][k_chunk][8 rows][16 B]; after the last MMA the A tiles are
     // re-used as the 128 x RED_LD fp32 partial tile of the cluster split-K reduction
@@ -175,13 +189,46 @@ __global__ void __launch_bounds__(NT, 2) conv_tf32x3_kernel(const float* __restr
     DBOA_TL(0);
     const int Ktaps = d.kh * d.kw, Kfull = Ktaps * d.Cin;
     // GEMM extents of this mode
-    const int Mrows = MODE == FWD ? d.B * d.Ho * d.Wo : (MODE == DGRAD ? d.B * d.Hi * d.Wi : d.Cout);
+    // Stride-2 data gradient: an input pixel (hi, wi) only receives the filter taps r = hi + pad (mod 2), s = wi + pad (mod 2).
+    // The rows are therefore enumerated per PARITY CLASS (hi & 1, wi & 1): blockIdx.x = class * tiles_per_class + tile, every
+    // tile holds rows of one class and reduces over that class's taps only (3x3: 1, 2, 2, 4 of 9 taps; 1x1: one class, the
+    // other three receive nothing).  Without this 3/4 of the rows of every 128-row tile were zero-filled.
+    const bool par = MODE == DGRAD && d.stride == 2;
+    int py = 0, px = 0, Hh = d.Hi, Wh = d.Wi, r0 = 0, s0 = 0, nr = d.kh, nsx = d.kw, tstep = 1, mtile = blockIdx.x;
+    if (par) {
+        // a 1-tap filter axis has ONE non-empty parity (the epilogue zero-fills the sibling pixels); classes = npy * npx
+        const int npy = d.kh >= 2 ? 2 : 1, npx = d.kw >= 2 ? 2 : 1;
+        const int tpc = gridDim.x / (npy * npx), cls = blockIdx.x / tpc;
+        mtile = blockIdx.x - cls * tpc;
+        py = npy == 2 ? cls / npx : (d.pad & 1); px = npx == 2 ? cls % npx : (d.pad & 1); Hh = d.Hi >> 1; Wh = d.Wi >> 1;
+        r0 = (py + d.pad) & 1; s0 = (px + d.pad) & 1;
+        nr = (d.kh - r0 + 1) >> 1; nsx = (d.kw - s0 + 1) >> 1; tstep = 2;
+    }
+    const int Mrows = MODE == FWD ? d.B * d.Ho * d.Wo : (MODE == DGRAD ? d.B * Hh * Wh : d.Cout);
     const int ldo = MODE == FWD ? d.Cout : (MODE == DGRAD ? d.Cin : Kfull);
-    const int Kred = MODE == FWD ? Kfull : (MODE == DGRAD ? Ktaps * d.Cout : d.B * d.Ho * d.Wo);
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int Kred = MODE == FWD ? Kfull : (MODE == DGRAD ? nr * nsx * d.Cout : d.B * d.Ho * d.Wo);
+    const int m0 = mtile * BM, n0 = blockIdx.y * BN;
     const int nkb_total = (Kred + BK - 1) / BK;
+    if (par) kb_per_split = (nkb_total + (int)gridDim.z - 1) / (int)gridDim.z;      // the classes have different reduction lengths
     const int kb_begin = blockIdx.z * kb_per_split;
     const int nkb = max(0, min(kb_begin + kb_per_split, nkb_total) - kb_begin);
+    // output row of tile row `row` (identity except for the parity classes)
+    auto out_row = [&](int row) {
+        if (!par) return row;
+        const int b = row / (Hh * Wh), rem = row - b * (Hh * Wh);
+        const int hh = rem / Wh, wh = rem - hh * Wh;
+        return (b * d.Hi + 2 * hh + py) * d.Wi + 2 * wh + px;
+    };
+    // input pixels of the parities no tap reaches get zeros (non-accumulating calls): written by the thread that stores
+    // the sibling pixel of the same 2x2 cell
+    const bool fill_y = par && d.kh < 2 && !accumulate, fill_x = par && d.kw < 2 && !accumulate;
+    auto zero_siblings = [&](int orow, int col) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int dyr = (py ? -1 : 1) * d.Wi, dxr = px ? -1 : 1;
+        if (fill_x) *reinterpret_cast<float4*>(O + (size_t)(orow + dxr) * ldo + col) = z;
+        if (fill_y) *reinterpret_cast<float4*>(O + (size_t)(orow + dyr) * ldo + col) = z;
+        if (fill_x && fill_y) *reinterpret_cast<float4*>(O + (size_t)(orow + dyr + dxr) * ldo + col) = z;
+    };
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], NPW); mbar_init(&sm.empty[s], 1); }
@@ -251,7 +298,7 @@ __global__ void __launch_bounds__(NT, 2) conv_tf32x3_kernel(const float* __restr
         int ph[2] = {0, 0}, pw[2] = {0, 0};                // FWD: hi0, wi0 (top-left of the window); DGRAD: hi, wi
         const float* pb[2] = {P, P};
         if (MODE != WGRAD) {
-            const int HW = MODE == FWD ? d.Ho * d.Wo : d.Hi * d.Wi, Wd = MODE == FWD ? d.Wo : d.Wi;
+            const int HW = MODE == FWD ? d.Ho * d.Wo : Hh * Wh, Wd = MODE == FWD ? d.Wo : Wh;
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int arow = m0 + (warp * 2 + q) * 8 + lr8;
@@ -260,7 +307,7 @@ __global__ void __launch_bounds__(NT, 2) conv_tf32x3_kernel(const float* __restr
                     const int b = arow / HW, rem = arow - b * HW;
                     const int h = rem / Wd, w_ = rem - h * Wd;
                     if (MODE == FWD) { ph[q] = h * d.stride - d.pad; pw[q] = w_ * d.stride - d.pad; pb[q] = P + (size_t)b * d.Hi * d.Wi * d.Cin; }
-                    else { ph[q] = h; pw[q] = w_; pb[q] = P + (size_t)b * d.Ho * d.Wo * d.Cout; }
+                    else { ph[q] = tstep * h + py; pw[q] = tstep * w_ + px; pb[q] = P + (size_t)b * d.Ho * d.Wo * d.Cout; }
                 }
             }
         }
@@ -275,8 +322,9 @@ __global__ void __launch_bounds__(NT, 2) conv_tf32x3_kernel(const float* __restr
         // so the im2col decode is an increment, not a division, per k-block
         const int Cred = MODE == DGRAD ? d.Cout : d.Cin;
         struct Cursor { int r, s, c; };
-        auto make_cursor = [&](int kb) { Cursor c; const int k0 = kb * BK, tap = k0 / Cred; c.c = k0 - tap * Cred; c.r = tap / d.kw; c.s = tap - c.r * d.kw; return c; };
-        auto advance = [&](Cursor& c) { c.c += BK; if (c.c >= Cred) { c.c = 0; if (++c.s == d.kw) { c.s = 0; ++c.r; } } };
+        // (r, s) count the taps of this CTA's tap set: filter tap = (r0 + tstep * r, s0 + tstep * s), nsx taps per filter row
+        auto make_cursor = [&](int kb) { Cursor c; const int k0 = kb * BK, tap = k0 / Cred; c.c = k0 - tap * Cred; c.r = tap / max(nsx, 1); c.s = tap - c.r * max(nsx, 1); return c; };
+        auto advance = [&](Cursor& c) { c.c += BK; if (c.c >= Cred) { c.c = 0; if (++c.s == nsx) { c.s = 0; ++c.r; } } };
         Cursor ca = make_cursor(kb_begin), cb = ca;
         int kb_a = kb_begin, kb_b = kb_begin;              // next k-block of each stream
 
@@ -293,7 +341,7 @@ __global__ void __launch_bounds__(NT, 2) conv_tf32x3_kernel(const float* __restr
             } else if (MODE == DGRAD) {
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const int th = ph[q] + d.pad - ca.r, tw = pw[q] + d.pad - ca.s;
+                    const int th = ph[q] + d.pad - (r0 + tstep * ca.r), tw = pw[q] + d.pad - (s0 + tstep * ca.s);
                     bool inb = avalid[q] && th >= 0 && tw >= 0;
                     int ho = th, wo = tw;
                     if (d.stride != 1) {
@@ -326,10 +374,11 @@ __global__ void __launch_bounds__(NT, 2) conv_tf32x3_kernel(const float* __restr
                 rb[1] = ldg4(wrow + 16);
             } else if (MODE == DGRAD) {
                 // B[n=ci][k=co] = W[co][tap][ci]: rows of 64 consecutive ci, one row per co (transposed by the store)
-                const int tap = cb.r * d.kw + cb.s;
+                // thread = (k = warp*4 + (lane & 3), nv = j*8 + (lane >> 3)*2 + ((lane >> 2) & 1)): bank-conflict-free transposing store
+                const int tap = (r0 + tstep * cb.r) * d.kw + (s0 + tstep * cb.s);
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const int idx = tid + NPROD * j, k = idx >> 4, nv = idx & 15;
+                    const int k = warp * 4 + (lane & 3), nv = j * 8 + (lane >> 3) * 2 + ((lane >> 2) & 1);
                     rb[j] = ldg4(Q + (size_t)(cb.c + k) * Kfull + (size_t)tap * d.Cin + n0 + nv * 4);
                 }
             } else {
@@ -367,6 +416,12 @@ __global__ void __launch_bounds__(NT, 2) conv_tf32x3_kernel(const float* __restr
             if (MODE == FWD) {
                 split_store4(sm.b_hi[s], sm.b_lo[s], b_off, rb[0]);
                 split_store4(sm.b_hi[s], sm.b_lo[s], b_off + 4 * CORE_BYTES, rb[1]);
+            } else if (MODE == DGRAD) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int k = warp * 4 + (lane & 3), nv = j * 8 + (lane >> 3) * 2 + ((lane >> 2) & 1);
+                    split_store_t_rot(sm.b_hi[s], sm.b_lo[s], nv * 4, k, rb[j], lane >> 3);
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -458,9 +513,11 @@ __global__ void __launch_bounds__(NT, 2) conv_tf32x3_kernel(const float* __restr
             const int row = m0 + lr;
             if (row < Mrows) {
                 float4 q = *reinterpret_cast<const float4*>(red + lr * RED_LD + c4);
-                float4* dst = reinterpret_cast<float4*>(O + (size_t)row * ldo + n0 + c4);
+                const int orow = out_row(row);
+                float4* dst = reinterpret_cast<float4*>(O + (size_t)orow * ldo + n0 + c4);
                 if (accumulate) { const float4 c = *dst; q.x += c.x; q.y += c.y; q.z += c.z; q.w += c.w; }
                 *dst = q;
+                if (fill_x || fill_y) zero_siblings(orow, n0 + c4);
             }
         }
     } else {
@@ -473,7 +530,9 @@ __global__ void __launch_bounds__(NT, 2) conv_tf32x3_kernel(const float* __restr
             const int lr = rank * rows_per + (v >> 4), c4 = (v & 15) * 4;
             const int row = m0 + lr;
             if (row >= Mrows) continue;
-            float4* dst = reinterpret_cast<float4*>(O + (size_t)row * ldo + n0 + c4);
+            const int orow = out_row(row);
+            float4* dst = reinterpret_cast<float4*>(O + (size_t)orow * ldo + n0 + c4);
+            if (fill_x || fill_y) zero_siblings(orow, n0 + c4);
             float4 sacc = accumulate ? *dst : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int zb = 0; zb < 16; zb += 8) {                      // 8 remote loads in flight, then added in the order z = 0..nz-1
@@ -500,8 +559,14 @@ __global__ void __launch_bounds__(NT, 2) conv_tf32x3_kernel(const float* __restr
 
 template <int MODE>
 static int launch(const float* p, const float* q, float* o, const ConvDims& d, int rows, int cols, int kred, int accumulate, cudaStream_t st) {
+    int mtiles = ceil_div(rows, BM);
+    if (MODE == DGRAD && d.stride == 2) {                // parity classes of B*Hi/2*Wi/2 rows, longest tap set decides the split
+        const int ncls = (d.kh >= 2 ? 2 : 1) * (d.kw >= 2 ? 2 : 1);
+        mtiles = ncls * ceil_div(d.B * (d.Hi / 2) * (d.Wi / 2), BM);
+        kred = ((d.kh + 1) / 2) * ((d.kw + 1) / 2) * d.Cout;
+    }
     const int nkb = (kred + BK - 1) / BK;
-    const int tiles = ceil_div(rows, BM) * (cols / BN);
+    const int tiles = mtiles * (cols / BN);
     // K-slices per tile (cluster size): a power of two <= 16.  A k-block costs ~0.4 us, the cluster barrier + DSMEM reduction
     // of a split tile ~3 us (profiles/r01b_summary.md section 6), so a split must leave at least `min_kb` k-blocks per CTA.
     static const int min_kb = [] { const char* e = getenv("DBOA_TC_MINKB"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
@@ -509,7 +574,7 @@ static int launch(const float* p, const float* q, float* o, const ConvDims& d, i
     while (ns < 16 && tiles * ns * 2 <= 296 + tiles && nkb / (ns * 2) >= min_kb) ns *= 2;
     const int per = (nkb + ns - 1) / ns;
     const size_t smem = sizeof(Smem) + 128;
-    return launch_ex(conv_tf32x3_kernel<MODE>, dim3(ceil_div(rows, BM), cols / BN, ns), dim3(NT), smem, st, dim3(1, 1, ns), true, p, q, o, d, per,
+    return launch_ex(conv_tf32x3_kernel<MODE>, dim3(mtiles, cols / BN, ns), dim3(NT), smem, st, dim3(1, 1, ns), true, p, q, o, d, per,
                      accumulate);
 }
 
@@ -531,6 +596,7 @@ int conv_tc_fwd(const float* x, const float* w, float* y, const ConvDims& d, cud
 }
 int conv_tc_dgrad(const float* dy, const float* w, float* dx, const ConvDims& d, int accumulate, cudaStream_t st) {
     if (g_tc_mode < 2 || !tc::shape_ok(d)) return DBOA_ERR_UNSUPPORTED;
+    if (d.stride == 2 && ((d.Hi | d.Wi) & 1)) return DBOA_ERR_UNSUPPORTED;       // the parity-class enumeration needs even extents
     return tc::launch<tc::DGRAD>(dy, w, dx, d, d.B * d.Hi * d.Wi, d.Cin, d.kh * d.kw * d.Cout, accumulate, st);
 }
 int conv_tc_wgrad(const float* dy, const float* x, float* dw, const ConvDims& d, cudaStream_t st) {

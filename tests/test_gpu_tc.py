@@ -62,7 +62,7 @@ def test_matches_fp32_cuda_core_path(L):
 
 CONV_SHAPES = [  # B, H, Cin, Cout, k, stride, pad
     (1, 56, 64, 64, 3, 1, 1), (2, 28, 128, 128, 3, 2, 1), (1, 56, 256, 512, 1, 2, 0), (1, 7, 512, 512, 3, 1, 1), (3, 14, 256, 256, 3, 1, 1),
-    (1, 14, 1024, 256, 1, 1, 0), (2, 7, 2048, 512, 1, 1, 0)]
+    (1, 14, 1024, 256, 1, 1, 0), (2, 7, 2048, 512, 1, 1, 0), (1, 14, 512, 512, 3, 2, 1), (2, 28, 512, 1024, 1, 2, 0)]
 
 
 @pytest.mark.parametrize('case', CONV_SHAPES)
