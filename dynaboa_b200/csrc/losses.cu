@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(256) pose_prior_kernel(const float* __restrict
     __syncwarp();
     float accT[3] = {0.f, 0.f, 0.f}, quad = 0.f;
     const float* P = prec + (size_t)m * 69 * 69;
-    for (int i = 0; i < 69; ++i) {
+#pragma unroll 8
+    for (int i = 0; i < 69; ++i) {                             // 8 rows of the precision matrix in flight per warp
         const float di = sd[m][i];
         float rowdot = 0.f;
 #pragma unroll

@@ -16,7 +16,7 @@
 
 namespace dboa {
 
-constexpr int NV = 6890, NV3 = NV * 3, NROW = 217, NSPLIT = 3, ROWS_PER_SPLIT = 73;
+constexpr int NV = 6890, NV3 = NV * 3, NROW = 217, NSPLIT = (int)SMPL_NSPLIT, ROWS_PER_SPLIT = (NROW + NSPLIT - 1) / NSPLIT;
 
 // coefficient vector c[b] = [betas(10); (R[1:] - I)(207)]
 __device__ __forceinline__ float blend_coeff(const float* betas, const float* rot, int b, int row) {
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) smpl_blend_fwd_kernel(const float* __rest
     const float base = (s == 0) ? vt[idx] : 0.f;
 #pragma unroll
     for (int b = 0; b < 8; ++b) acc[b] = base;
-#pragma unroll 4
+#pragma unroll 8
     for (int r = rbeg; r < rend; ++r) {
         float d = __ldg(D + (size_t)r * NV3 + idx);
 #pragma unroll
@@ -127,9 +127,9 @@ __global__ void __launch_bounds__(128) smpl_skin_fwd_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// 49 joints: grid (49, B), 128 threads
+// 49 joints: grid (49, B), 512 threads
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) smpl_joints_fwd_kernel(const float* __restrict__ verts, const float* __restrict__ Jtr,
+__global__ void __launch_bounds__(512) smpl_joints_fwd_kernel(const float* __restrict__ verts, const float* __restrict__ Jtr,
                                                               const float* __restrict__ Jx, const int* __restrict__ joint_map,
                                                               const int* __restrict__ vertex_ids, float* __restrict__ joints) {
     pdl_wait();
@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(128) smpl_joints_fwd_kernel(const float* __res
     } else {
         const float* jr = Jx + (size_t)(src - 45) * NV;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        for (int v = threadIdx.x; v < NV; v += 128) {
+#pragma unroll 4
+        for (int v = threadIdx.x; v < NV; v += 512) {         // 14 steps, 4 in flight: the dense regressor rows are latency-bound
             float w = __ldg(jr + v);
             const float* p = verts + (size_t)b * NV3 + v * 3;
             s0 = fmaf(w, p[0], s0); s1 = fmaf(w, p[1], s1); s2 = fmaf(w, p[2], s2);
@@ -165,7 +166,7 @@ int smpl_forward(const dboa_smpl_model& m, const float* betas, const float* rot,
     }
     DBOA_TRY(launch_ex(smpl_chain_fwd_kernel, dim3(B), dim3(32), 0, st, dim3(1, 1, 1), true, m.J_template, m.J_shapedirs, m.parents, betas, rot, t.A, t.Gr, t.J, t.Jtr));
     DBOA_TRY(launch_ex(smpl_skin_fwd_kernel, dim3(ceil_div(NV, 128), B), dim3(128), 0, st, dim3(1, 1, 1), true, t.partial, t.A, m.lbs_weights, t.vposed, verts, B));
-    return launch_ex(smpl_joints_fwd_kernel, dim3(49, B), dim3(128), 0, st, dim3(1, 1, 1), true, verts, t.Jtr, m.J_extra, m.joint_map, m.vertex_ids, joints);
+    return launch_ex(smpl_joints_fwd_kernel, dim3(49, B), dim3(512), 0, st, dim3(1, 1, 1), true, verts, t.Jtr, m.J_extra, m.joint_map, m.vertex_ids, joints);
 }
 
 // =============================================================================================
@@ -267,15 +268,16 @@ __global__ void __launch_bounds__(128) smpl_skin_bwd_kernel(const float* __restr
     }
 }
 
-// blend backward: dc[b][row] = sum_idx D[row][idx] dvposed[b][idx]; grid (217), 256 threads
-__global__ void __launch_bounds__(256) smpl_blend_bwd_kernel(const float* __restrict__ D, const float* __restrict__ dvposed,
+// blend backward: dc[b][row] = sum_idx D[row][idx] dvposed[b][idx]; grid (217), 1024 threads
+__global__ void __launch_bounds__(1024) smpl_blend_bwd_kernel(const float* __restrict__ D, const float* __restrict__ dvposed,
                                                              float* __restrict__ dc, int b0, int nb) {
     pdl_wait();
     pdl_trigger();
     __shared__ float red[32];
     const int row = blockIdx.x;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int idx = threadIdx.x; idx < NV3; idx += 256) {
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < NV3; idx += 1024) {     // 21 steps, 4 in flight (was 81 dependent steps of 256 threads)
         float d = __ldg(D + (size_t)row * NV3 + idx);
 #pragma unroll
         for (int b = 0; b < 8; ++b)
@@ -332,7 +334,7 @@ int smpl_backward(const dboa_smpl_model& m, const float* rot, int B, const float
     DBOA_TRY(launch_ex(smpl_skin_bwd_kernel, dim3(nparts, B), dim3(128), 0, st, dim3(1, 1, 1), true, s.dverts, t.vposed, t.A, m.lbs_weights, s.dvposed, s.dA_part));
     for (int b0 = 0; b0 < B; b0 += 8) {
         int nb = B - b0 < 8 ? B - b0 : 8;
-        DBOA_TRY(launch_ex(smpl_blend_bwd_kernel, dim3(NROW), dim3(256), 0, st, dim3(1, 1, 1), true, m.blend_dirs, s.dvposed, s.dc, b0, nb));
+        DBOA_TRY(launch_ex(smpl_blend_bwd_kernel, dim3(NROW), dim3(1024), 0, st, dim3(1, 1, 1), true, m.blend_dirs, s.dvposed, s.dc, b0, nb));
     }
     return launch_ex(smpl_chain_bwd_kernel, dim3(B), dim3(32), 0, st, dim3(1, 1, 1), true, m.J_shapedirs, m.parents, rot, t.J, t.Gr, s.dA_part, nparts, s.dJtr, s.dc, drot, dbetas, accumulate);
 }

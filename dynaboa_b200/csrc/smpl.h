@@ -8,19 +8,20 @@ namespace dboa {
 
 constexpr size_t SMPL_NV3 = 6890 * 3;
 constexpr size_t SMPL_SKIN_CTAS = (6890 + 127) / 128;   // 54
+constexpr size_t SMPL_NSPLIT = 7;                       // row splits of the blend-shape product (7 x 31 = 217 rows)
 
-// saved by the forward for the backward: per body 4*20670 + 648 floats
+// saved by the forward for the backward: per body (SMPL_NSPLIT + 1) * 20670 + 648 floats
 struct SmplTape {
     float *partial, *vposed, *A, *Gr, *J, *Jtr;
     SmplTape(float* base, int B) {
-        partial = base;                       // [3][B][20670]
-        vposed = partial + 3 * (size_t)B * SMPL_NV3;
+        partial = base;                       // [SMPL_NSPLIT][B][20670]
+        vposed = partial + SMPL_NSPLIT * (size_t)B * SMPL_NV3;
         A = vposed + (size_t)B * SMPL_NV3;    // [B][24][12]
         Gr = A + (size_t)B * 288;             // [B][24][9]
         J = Gr + (size_t)B * 216;             // [B][24][3] rest joints
         Jtr = J + (size_t)B * 72;             // [B][24][3] posed joints
     }
-    static size_t floats(int B) { return (size_t)B * (4 * SMPL_NV3 + 288 + 216 + 72 + 72); }
+    static size_t floats(int B) { return (size_t)B * ((SMPL_NSPLIT + 1) * SMPL_NV3 + 288 + 216 + 72 + 72); }
 };
 
 struct SmplScratch {
