@@ -29,6 +29,7 @@ WORKLOADS = {
     'c2': dict(inner_step=1, retrieval=0, lower_level_mixtrain=0, upper_level_mixtrain=0, dynamic_boa=0, sample_num=1),
     'c3': dict(inner_step=3, retrieval=1, lower_level_mixtrain=1, upper_level_mixtrain=1, dynamic_boa=0, sample_num=8),
 }
+N_EXEMPLARS = 256        # synthetic exemplar bank of the retrieval workloads: 10 clusters of ~25 items >= sample_num
 W_MB = 107.91            # fp32 parameters
 FWD_MB = lambda b: 107.91 + 89.51 * b
 BWD_MB = lambda b: 215.8 + 133.4 * b
@@ -115,8 +116,8 @@ def build_oracle(workload, n_frames):
     from oracle import adaptor_ref
     opts = adaptor_ref.default_options(**WORKLOADS[workload])
     gmm = dict(np.load(os.path.join(REPO, 'dynaboa_b200', 'assets', 'gmm_08.npz')))
-    bank = synthetic.make_exemplar_bank() if opts.retrieval else None
-    clusters = synthetic.make_clusters() if opts.retrieval else None
+    bank = synthetic.make_exemplar_bank(n=N_EXEMPLARS) if opts.retrieval else None
+    clusters = synthetic.make_clusters(n_items=N_EXEMPLARS) if opts.retrieval else None
     ora = adaptor_ref.OracleAdaptor(opts, synthetic.make_basemodel(),
                                     {g: synthetic.make_smpl_model(g) for g in ('neutral', 'male', 'female')},
                                     synthetic.make_extra_regressors(), gmm, bank=bank, clusters=clusters,
@@ -213,7 +214,7 @@ def run_ours(args, rank, world, local):
     if args.tc >= 0:
         lib.dboa_set_tensor_core_conv(args.tc)
     work = tempfile.mkdtemp(prefix=f'dboa_bench_r{rank}_')
-    synthetic.write_asset_dir(os.path.join(work, 'data'))
+    synthetic.write_asset_dir(os.path.join(work, 'data'), n_exemplars=N_EXEMPLARS if WORKLOADS[args.workload]['retrieval'] else 64)
     config.set_data_root(os.path.join(work, 'data'))
     PRELUDE = 7          # untimed frames so that the history ring is full and the motion loss is live (step - interval > 0)
     n_frames = PRELUDE + args.steps + args.warmup
