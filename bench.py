@@ -48,8 +48,8 @@ def default_options(**over):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML, every 2 ms from a
-    thread (the timed region is ~0.2 s: `nvidia-smi -lms` starts too slowly to see it)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML, every 5 ms from a
+    thread (the timed region is ~0.15 s: `nvidia-smi -lms` starts too slowly to see it)."""
     REASONS = (('hw_slowdown', 0x8), ('sw_thermal_slowdown', 0x20), ('hw_thermal_slowdown', 0x40), ('sw_power_cap', 0x4))
 
     def __init__(self, device_index):
@@ -83,7 +83,7 @@ class ClockSampler:
             except Exception as e:      # noqa: BLE001
                 self.err = str(e)
                 return
-            time.sleep(0.002)
+            time.sleep(0.005)
 
     def start(self):
         if self.h is None:
@@ -216,7 +216,9 @@ def run_ours(args, rank, world, local):
     work = tempfile.mkdtemp(prefix=f'dboa_bench_r{rank}_')
     synthetic.write_asset_dir(os.path.join(work, 'data'), n_exemplars=N_EXEMPLARS if WORKLOADS[args.workload]['retrieval'] else 64)
     config.set_data_root(os.path.join(work, 'data'))
-    PRELUDE = 7          # untimed frames so that the history ring is full and the motion loss is live (step - interval > 0)
+    # untimed frames so that the history ring is full and the motion loss is live (step - interval > 0); with several ranks a few
+    # more, so that NCCL's channels and both ranks' allocators are in steady state before the W warm-up steps
+    PRELUDE = 7 if world == 1 else 15
     n_frames = PRELUDE + args.steps + args.warmup
     opts = default_options(expdir=work, expname='bench', model_file=config.BASE_MODEL, synthetic_frames=n_frames, rank=rank,
                            **WORKLOADS[args.workload])
