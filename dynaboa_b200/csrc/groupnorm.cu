@@ -5,8 +5,8 @@
 //
 // At batch 1 every layer is a few-microsecond problem: what sets the time is the number of DEPENDENT
 // steps (memory round trips, barriers) and the number of instructions each thread issues with few
-// warps to hide their latency -- not bytes (profiles/r02_trace.md: the first version of these kernels
-// spent 8 / 16 us on tensors that stream in well under 1 us).  Hence:
+// warps to hide their latency -- not bytes (profiles/r01b_summary.md sections 3-4: the first version of these
+// kernels spent 8 / 16 us on tensors that stream in well under 1 us).  Hence:
 //   * one (sample, group) is handled by ONE thread-block cluster of <= 16 CTAs x 1024 threads; every
 //     thread owns <= 4 float4 (same channels, rows a fixed stride apart: no integer division, the
 //     channels-per-group count is a power of two);
@@ -16,8 +16,9 @@
 //   * statistics are (count, mean, M2) per CTA merged with the pairwise formula, robust to large means;
 //   * the affine-parameter gradients are reduced per channel inside the CTA (shuffles + one shared
 //     pass), across the cluster through DSMEM, and added to dgamma / dbeta directly at batch 1; with
-//     several samples the per-sample rows go through global memory and the last cluster of a group
-//     sums them in sample order (still deterministic).
+//     several samples the per-sample rows go through global memory and are summed in sample order
+//     (deterministic) -- by the last cluster of a group (stand-alone call), or for the whole network by
+//     ONE gn_param_finish launch at the end of the backward (`defer`: no fence / ticket per layer).
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(GN_NT, 1) gn_bwd_fused_kernel(const float* __r
                                                              const float* __restrict__ gamma, float* __restrict__ dy,
                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                              float* __restrict__ rows_g, float* __restrict__ rows_b, unsigned* pcounters,
-                                                             int HW, int C, int R, int lg) {
+                                                             int HW, int C, int R, int lg, int defer) {
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ float red1[64];
     __shared__ float part[2];
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(GN_NT, 1) gn_bwd_fused_kernel(const float* __r
         }
     }
     cluster.barrier_arrive();
-    if (B > 1) {                                             // last CTA of group g (over samples and chunks) adds the rows in order
+    if (B > 1 && !defer) {                                   // last CTA of group g (over samples and chunks) adds the rows in order
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -306,13 +307,34 @@ __global__ void __launch_bounds__(GN_NT, 1) gn_bwd_fused_kernel(const float* __r
 }
 
 int gn_bwd_fused(const float* dout, const float* mask_src, const float* y, const float* stats, const float* gamma, float* dy,
-                 float* dgamma, float* dbeta, float* partial, int B, int HW, int C, cudaStream_t st) {
+                 float* dgamma, float* dbeta, float* partial, int B, int HW, int C, cudaStream_t st, int defer) {
     GnPlan pl;
     if (!gn_plan(HW, C, &pl) || (C / 16) > 128) return DBOA_ERR_SHAPE;
     unsigned* cnt = sync_words();
     if (!cnt) return DBOA_ERR_CUDA;
     return launch_ex(gn_bwd_fused_kernel, dim3(pl.chunks, GN_G, B), dim3(GN_NT), 0, st, dim3(pl.chunks, 1, 1), true, dout, mask_src, y, stats,
-                     gamma, dy, dgamma, dbeta, partial, partial + (size_t)B * C, cnt, HW, C, pl.rows, pl.lg);
+                     gamma, dy, dgamma, dbeta, partial, partial + (size_t)B * C, cnt, HW, C, pl.rows, pl.lg, defer);
+}
+
+// Deferred affine-parameter gradients of a whole network (B > 1): every GroupNorm backward left its per-sample rows
+// [B][C] (dgamma) | [B][C] (dbeta) at rows + 2 * B * item.cum_channels; ONE launch adds them to the gradient arena in sample
+// order.  This keeps the per-layer kernels free of the fence + ticket + last-CTA pass that B > 1 otherwise needs.
+__global__ void __launch_bounds__(256) gn_param_finish_kernel(const GnFinishItem* __restrict__ items, const float* __restrict__ rows,
+                                                              float* __restrict__ G, int B) {
+    pdl_wait();
+    pdl_trigger();
+    const GnFinishItem it = items[blockIdx.x];
+    const float* rg = rows + 2 * (size_t)B * it.cum_channels;
+    const float* rb = rg + (size_t)B * it.C;
+    for (int c = threadIdx.x; c < it.C; c += 256) {
+        float a = 0.f, bsum = 0.f;
+        for (int r = 0; r < B; ++r) { a += rg[(size_t)r * it.C + c]; bsum += rb[(size_t)r * it.C + c]; }
+        G[it.g_off + c] += a; G[it.b_off + c] += bsum;
+    }
+}
+
+int gn_param_finish(const GnFinishItem* items_dev, int n_items, const float* rows, float* G, int B, cudaStream_t st) {
+    return launch_ex(gn_param_finish_kernel, dim3(n_items), dim3(256), 0, st, dim3(1, 1, 1), true, items_dev, rows, G, B);
 }
 
 }  // namespace dboa

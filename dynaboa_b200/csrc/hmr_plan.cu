@@ -173,12 +173,9 @@ struct Scratch {
         auto take = [&](long long cnt) { float* p = base ? base + off : nullptr; off = align32(off + cnt); return p; };
         ws = take(kConvWs);
         g0 = take(S); g1 = take(S); t1 = take(S); t2 = take(S); t3 = take(S); t4 = take(S); t5 = take(S); t6 = take(S);
-        long long gmax = 0;
-        for (const ConvLayer& c : net().convs) {
-            long long v = (long long)gn_bwd_partial_floats(B, c.hout * c.hout, c.cout);
-            gmax = v > gmax ? v : gmax;
-        }
-        gnp = take(gmax);
+        long long gsum = 0;                               // per-sample dgamma / dbeta rows of EVERY GroupNorm (reduced once, at the end)
+        for (const ConvLayer& c : net().convs) gsum += (long long)gn_bwd_partial_floats(B, c.hout * c.hout, c.cout);
+        gnp = take(gsum);
         dP = take((long long)B * DEC_LD);
         dy_dec = take(3LL * B * DEC_LD);
         d_h2 = take(3LL * B * HID); d_h1 = take(3LL * B * HID);
@@ -228,6 +225,28 @@ void hmr_set_async_wgrad(bool on) { g_async_enabled = on; }
 static const int g_wgrad_streams = [] { const char* e = getenv("DBOA_WGRAD_STREAMS"); return (e && e[0] == '1') ? 1 : BwdAsync::NSIDE; }();
 
 static ConvDims dims_of(const ConvLayer& c, int B);
+
+// table for gn_param_finish: where each GroupNorm's affine gradients live and where its per-sample rows start
+struct GnItems { std::vector<long long> cum; GnFinishItem* dev = nullptr; };
+static const GnItems& gn_items() {
+    static GnItems gi = [] {
+        GnItems g;
+        const Net& n = net();
+        std::vector<GnFinishItem> host;
+        long long cum = 0;
+        for (const ConvLayer& c : n.convs) {
+            g.cum.push_back(cum);
+            host.push_back(GnFinishItem{c.g_off, c.b_off, cum, c.cout});
+            cum += c.cout;
+        }
+        void* p = nullptr;
+        if (cudaMalloc(&p, host.size() * sizeof(GnFinishItem)) == cudaSuccess &&
+            cudaMemcpy(p, host.data(), host.size() * sizeof(GnFinishItem), cudaMemcpyHostToDevice) == cudaSuccess)
+            g.dev = static_cast<GnFinishItem*>(p);
+        return g;
+    }();
+    return gi;
+}
 // backward convolutions: tcgen05 implicit GEMM when enabled and the shape is taken, else the fp32 CUDA-core kernels
 static int conv_backward_data(const ConvLayer& c, int B, const float* dy, const float* w, float* dx, int accumulate, float* ws, cudaStream_t st);
 static int conv_backward_weight(const ConvLayer& c, int B, const float* dy, const float* x, float* dw, float* ws, cudaStream_t st);
@@ -456,8 +475,8 @@ int hmr_backward(const float* P, const float* T, int B, int masked_in, const flo
     };
     auto gnb = [&](int ci, const float* dout, const float* mask_src, float* dy) {
         const ConvLayer& c = n.convs[ci];
-        return gn_bwd_fused(dout, mask_src, T + t.conv[ci].y, T + t.conv[ci].stats, P + c.g_off, dy, G + c.g_off, G + c.b_off, sc.gnp, B,
-                            c.hout * c.hout, c.cout, st);
+        return gn_bwd_fused(dout, mask_src, T + t.conv[ci].y, T + t.conv[ci].stats, P + c.g_off, dy, G + c.g_off, G + c.b_off,
+                            sc.gnp + 2 * (size_t)B * gn_items().cum[ci], B, c.hout * c.hout, c.cout, st, /*defer=*/1);
     };
     // weight gradient of conv `c` from dy held in temp k
     auto wgrad = [&](const ConvLayer& c, int k, const float* xin_) {
@@ -501,6 +520,11 @@ int hmr_backward(const float* P, const float* T, int B, int masked_in, const flo
     DBOA_TRY(maxpool3x3s2_bwd(dOut, reinterpret_cast<const unsigned char*>(T + t.p0_idx), dIn, B, 112, 112, 64, st));
     DBOA_TRY(gnb(0, dIn, T + t.conv[0].a, claim(0)));
     int rc = conv_wgrad(tmp[0], T + t.x0, G + n.convs[0].w_off, dims_of(n.convs[0], B), sc.ws, (size_t)kConvWs, st);
+    if (rc == DBOA_OK && B > 1) {                          // affine-parameter gradients of all 53 GroupNorms, summed over the samples
+        const GnItems& gi = gn_items();
+        if (gi.dev == nullptr) return DBOA_ERR_CUDA;
+        rc = gn_param_finish(gi.dev, (int)n.convs.size(), sc.gnp, G, B, st);
+    }
     if (async) {                                   // join: nothing of this call is left running when the caller's stream continues
         for (int i = 0; i < BwdAsync::NSIDE; ++i) {
             cudaEventRecord(A.ev_join[i], A.side[i]);

@@ -34,8 +34,11 @@ size_t gn_bwd_partial_floats(int B, int HW, int C); // backward scratch: per-sam
 // backward: dz = dout * (mask_src > 0 if mask_src else 1); dy = GN backward; dgamma/dbeta accumulate (+=)
 int gn_fwd_fused(const float* y, const float* gamma, const float* beta, const float* res, float* out, float* stats, float* partial,
                  int B, int HW, int C, int relu, cudaStream_t st);
+// defer = 1 (B > 1 only): leave the per-sample dgamma / dbeta rows in `partial` for gn_param_finish instead of reducing them here
 int gn_bwd_fused(const float* dout, const float* mask_src, const float* y, const float* stats, const float* gamma, float* dy,
-                 float* dgamma, float* dbeta, float* partial, int B, int HW, int C, cudaStream_t st);
+                 float* dgamma, float* dbeta, float* partial, int B, int HW, int C, cudaStream_t st, int defer = 0);
+struct GnFinishItem { long long g_off, b_off, cum_channels; int C; };
+int gn_param_finish(const GnFinishItem* items_dev, int n_items, const float* rows, float* G, int B, cudaStream_t st);
 // ---- norm_pool.cu
 int relu_mask(const float* dout, const float* mask_src, float* dz, size_t n, cudaStream_t st);
 int nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, cudaStream_t st);
