@@ -79,32 +79,27 @@ __global__ void __launch_bounds__(256) pose_prior_kernel(const float* __restrict
     __syncthreads();
     for (int c = lane; c < 69; c += 32) sd[m][c] = sx[c] - means[m * 69 + c];
     __syncwarp();
-    float accT[3] = {0.f, 0.f, 0.f}, quad = 0.f;
+    // pass 1 (one warp per Gaussian): P^T d by columns -- coalesced rows, no shuffles inside the loop, 8 rows in flight;
+    // d^T P d = d . (P^T d).  The row products P d are only needed for the gradient of the selected component (pass 2).
+    float accT[3] = {0.f, 0.f, 0.f};
     const float* P = prec + (size_t)m * 69 * 69;
 #pragma unroll 8
-    for (int i = 0; i < 69; ++i) {                             // 8 rows of the precision matrix in flight per warp
+    for (int i = 0; i < 69; ++i) {
         const float di = sd[m][i];
-        float rowdot = 0.f;
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            int c = lane + q * 32;
-            if (c < 69) {
-                float p = __ldg(P + i * 69 + c);
-                rowdot = fmaf(p, sd[m][c], rowdot);
-                accT[q] = fmaf(di, p, accT[q]);
-            }
+            const int c = lane + q * 32;
+            if (c < 69) accT[q] = fmaf(di, __ldg(P + i * 69 + c), accT[q]);
         }
-        rowdot = warp_sum(rowdot);
-        quad = fmaf(di, rowdot, quad);
-        if (lane == 0) sPd[m][i] = rowdot;
     }
-    __syncwarp();
-    if (lane == 0) sll[m] = 0.5f * quad + neg_log_w[m];
+    float quad = 0.f;
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-        int c = lane + q * 32;
-        if (c < 69) sg[m][c] = 0.5f * (sPd[m][c] + accT[q]);       // d(0.5 d^T P d) = 0.5 (P + P^T) d
+        const int c = lane + q * 32;
+        if (c < 69) { quad = fmaf(sd[m][c], accT[q], quad); sg[m][c] = accT[q]; }
     }
+    quad = warp_sum(quad);
+    if (lane == 0) sll[m] = 0.5f * quad + neg_log_w[m];
     __syncthreads();
     if (t == 0) {
         int best = 0;
@@ -114,18 +109,33 @@ __global__ void __launch_bounds__(256) pose_prior_kernel(const float* __restrict
         prior_b[b] = sll[best];
     }
     __syncthreads();
+    if (d_in != nullptr) {                                     // pass 2: rows of the selected precision matrix, 8 warps x 9 rows
+        const int k = sbest;
+        const float* Pk = prec + (size_t)k * 69 * 69;
+        for (int i = m; i < 69; i += 8) {
+            float rowdot = 0.f;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int c = lane + q * 32;
+                if (c < 69) rowdot = fmaf(__ldg(Pk + i * 69 + c), sd[k][c], rowdot);
+            }
+            rowdot = warp_sum(rowdot);
+            if (lane == 0) sPd[0][i] = 0.5f * (rowdot + sg[k][i]);     // d(0.5 d^T P d) = 0.5 (P + P^T) d
+        }
+    }
+    __syncthreads();
     if (d_in != nullptr) {
         if (FROM_ROT) {
             if (t < 9) d_in[(size_t)b * 216 + t] = 0.f;            // root joint carries no prior
             if (t < 23) {
                 float R[9], daa[3], dR[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 for (int k = 0; k < 9; ++k) R[k] = in[(size_t)b * 216 + (t + 1) * 9 + k];
-                for (int k = 0; k < 3; ++k) daa[k] = sg[sbest][t * 3 + k] * scale;
+                for (int k = 0; k < 3; ++k) daa[k] = sPd[0][t * 3 + k] * scale;
                 r2aa_bwd(R, daa, dR);
                 for (int k = 0; k < 9; ++k) d_in[(size_t)b * 216 + (t + 1) * 9 + k] = dR[k];
             }
         } else {
-            if (t < 69) d_in[(size_t)b * 69 + t] = sg[sbest][t] * scale;
+            if (t < 69) d_in[(size_t)b * 69 + t] = sPd[0][t] * scale;
         }
     }
 }

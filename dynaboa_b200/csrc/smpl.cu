@@ -58,9 +58,10 @@ __global__ void __launch_bounds__(256) smpl_blend_fwd_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// rest joints + kinematic chain: one 32-thread block per body
+// rest joints + kinematic chain: one 288-thread block per body (all loads of the set-up in flight at once; the chain
+// itself is serial in thread 0)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) smpl_chain_fwd_kernel(const float* __restrict__ Jt, const float* __restrict__ Js,
+__global__ void __launch_bounds__(288) smpl_chain_fwd_kernel(const float* __restrict__ Jt, const float* __restrict__ Js,
                                                             const int* __restrict__ parents, const float* __restrict__ betas,
                                                             const float* __restrict__ rot, float* __restrict__ A_out,
                                                             float* __restrict__ Gr_out, float* __restrict__ J_out,
@@ -70,9 +71,10 @@ __global__ void __launch_bounds__(32) smpl_chain_fwd_kernel(const float* __restr
     __shared__ float sR[216], sJ[72], sGr[216], sGt[72], sA[288];
     __shared__ int sp[24];
     const int b = blockIdx.x, t = threadIdx.x;
-    for (int i = t; i < 216; i += 32) sR[i] = rot[(size_t)b * 216 + i];
-    for (int i = t; i < 72; i += 32) {
+    for (int i = t; i < 216; i += 288) sR[i] = rot[(size_t)b * 216 + i];
+    for (int i = t; i < 72; i += 288) {
         float v = Jt[i];
+#pragma unroll
         for (int l = 0; l < 10; ++l) v = fmaf(Js[i * 10 + l], betas[b * 10 + l], v);
         sJ[i] = v;
     }
@@ -80,9 +82,9 @@ __global__ void __launch_bounds__(32) smpl_chain_fwd_kernel(const float* __restr
     __syncthreads();
     if (t == 0) chain_fwd(sR, sJ, sp, sGr, sGt, sA);
     __syncthreads();
-    for (int i = t; i < 288; i += 32) A_out[(size_t)b * 288 + i] = sA[i];
-    for (int i = t; i < 216; i += 32) Gr_out[(size_t)b * 216 + i] = sGr[i];
-    for (int i = t; i < 72; i += 32) { J_out[(size_t)b * 72 + i] = sJ[i]; Jtr_out[(size_t)b * 72 + i] = sGt[i]; }
+    for (int i = t; i < 288; i += 288) A_out[(size_t)b * 288 + i] = sA[i];
+    for (int i = t; i < 216; i += 288) Gr_out[(size_t)b * 216 + i] = sGr[i];
+    for (int i = t; i < 72; i += 288) { J_out[(size_t)b * 72 + i] = sJ[i]; Jtr_out[(size_t)b * 72 + i] = sGt[i]; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -164,7 +166,7 @@ int smpl_forward(const dboa_smpl_model& m, const float* betas, const float* rot,
         dim3 g(ceil_div(NV3, 256), NSPLIT);
         DBOA_TRY(launch_ex(smpl_blend_fwd_kernel, dim3(g), dim3(256), 0, st, dim3(1, 1, 1), true, m.blend_dirs, m.v_template, betas, rot, t.partial, b0, nb, B));
     }
-    DBOA_TRY(launch_ex(smpl_chain_fwd_kernel, dim3(B), dim3(32), 0, st, dim3(1, 1, 1), true, m.J_template, m.J_shapedirs, m.parents, betas, rot, t.A, t.Gr, t.J, t.Jtr));
+    DBOA_TRY(launch_ex(smpl_chain_fwd_kernel, dim3(B), dim3(288), 0, st, dim3(1, 1, 1), true, m.J_template, m.J_shapedirs, m.parents, betas, rot, t.A, t.Gr, t.J, t.Jtr));
     DBOA_TRY(launch_ex(smpl_skin_fwd_kernel, dim3(ceil_div(NV, 128), B), dim3(128), 0, st, dim3(1, 1, 1), true, t.partial, t.A, m.lbs_weights, t.vposed, verts, B));
     return launch_ex(smpl_joints_fwd_kernel, dim3(49, B), dim3(512), 0, st, dim3(1, 1, 1), true, verts, t.Jtr, m.J_extra, m.joint_map, m.vertex_ids, joints);
 }
@@ -289,8 +291,9 @@ __global__ void __launch_bounds__(1024) smpl_blend_bwd_kernel(const float* __res
     }
 }
 
-// chain backward + assembly of the final gradients; one 32-thread block per body
-__global__ void __launch_bounds__(32) smpl_chain_bwd_kernel(const float* __restrict__ Js, const int* __restrict__ parents,
+// chain backward + assembly of the final gradients; one 288-thread block per body (one thread per entry of the 24 x 12
+// joint-transform gradient while the 54 skinning partials are summed; the chain itself is serial in thread 0)
+__global__ void __launch_bounds__(288) smpl_chain_bwd_kernel(const float* __restrict__ Js, const int* __restrict__ parents,
                                                             const float* __restrict__ rot, const float* __restrict__ J,
                                                             const float* __restrict__ Gr, const float* __restrict__ dA_part, int nparts,
                                                             const float* __restrict__ dJtr, const float* __restrict__ dc,
@@ -300,10 +303,11 @@ __global__ void __launch_bounds__(32) smpl_chain_bwd_kernel(const float* __restr
     __shared__ float sR[216], sJ[72], sGr[216], sdA[288], sdJt[72], sdGr[216], sdGt[72], sdR[216], sdJ[72];
     __shared__ int sp[24];
     const int b = blockIdx.x, t = threadIdx.x;
-    for (int i = t; i < 216; i += 32) { sR[i] = rot[(size_t)b * 216 + i]; sGr[i] = Gr[(size_t)b * 216 + i]; }
-    for (int i = t; i < 72; i += 32) { sJ[i] = J[(size_t)b * 72 + i]; sdJt[i] = dJtr[(size_t)b * 72 + i]; }
-    for (int i = t; i < 288; i += 32) {
+    for (int i = t; i < 216; i += 288) { sR[i] = rot[(size_t)b * 216 + i]; sGr[i] = Gr[(size_t)b * 216 + i]; }
+    for (int i = t; i < 72; i += 288) { sJ[i] = J[(size_t)b * 72 + i]; sdJt[i] = dJtr[(size_t)b * 72 + i]; }
+    for (int i = t; i < 288; i += 288) {
         float s = 0.f;
+#pragma unroll 6
         for (int p = 0; p < nparts; ++p) s += dA_part[((size_t)b * nparts + p) * 288 + i];
         sdA[i] = s;
     }
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(32) smpl_chain_bwd_kernel(const float* __restr
     __syncthreads();
     if (t == 0) chain_bwd(sR, sJ, sp, sGr, sdA, sdJt, sdGr, sdGt, sdR, sdJ);
     __syncthreads();
-    for (int i = t; i < 216; i += 32) {
+    for (int i = t; i < 216; i += 288) {
         float g = sdR[i];
         if (i >= 9) g += dc[(size_t)b * NROW + 10 + (i - 9)];       // pose-blend feature gradient
         size_t o = (size_t)b * 216 + i;
@@ -336,7 +340,7 @@ int smpl_backward(const dboa_smpl_model& m, const float* rot, int B, const float
         int nb = B - b0 < 8 ? B - b0 : 8;
         DBOA_TRY(launch_ex(smpl_blend_bwd_kernel, dim3(NROW), dim3(1024), 0, st, dim3(1, 1, 1), true, m.blend_dirs, s.dvposed, s.dc, b0, nb));
     }
-    return launch_ex(smpl_chain_bwd_kernel, dim3(B), dim3(32), 0, st, dim3(1, 1, 1), true, m.J_shapedirs, m.parents, rot, t.J, t.Gr, s.dA_part, nparts, s.dJtr, s.dc, drot, dbetas, accumulate);
+    return launch_ex(smpl_chain_bwd_kernel, dim3(B), dim3(288), 0, st, dim3(1, 1, 1), true, m.J_shapedirs, m.parents, rot, t.J, t.Gr, s.dA_part, nparts, s.dJtr, s.dc, drot, dbetas, accumulate);
 }
 
 // axis-angle -> rotation matrix, kind 0 = reference quaternion route, 1 = smplx Rodrigues formula
