@@ -53,7 +53,7 @@ def test_layout_matches_reference_contract(lib):
 def test_size_queries(lib):
     assert lib.dboa_hmr_tape_floats(1) > 20_000_000 and lib.dboa_hmr_tape_floats(0) < 0
     assert lib.dboa_hmr_scratch_floats(2) > 0
-    assert lib.dboa_smpl_tape_floats(2) == 2 * (4 * 20670 + 648)
+    assert lib.dboa_smpl_tape_floats(2) == 2 * (8 * 20670 + 648)      # 7 blend-shape row splits + posed vertices, chain state
 
 
 def test_argument_errors_do_not_need_a_gpu(lib):
