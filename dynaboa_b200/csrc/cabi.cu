@@ -1,4 +1,6 @@
 // extern "C" surface of libdynaboa_b200 (see include/dynaboa_b200.h for the contract of each entry).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "losses.h"
@@ -46,6 +48,14 @@ static ConvDims make_dims(int B, int Hi, int Wi, int Cin, int Cout, int k, int s
     d.B = B; d.Hi = Hi; d.Wi = Wi; d.Cin = Cin; d.Cout = Cout; d.kh = k; d.kw = k; d.stride = stride; d.pad = pad; d.Kpitch = Kpitch;
     d.Ho = (Hi + 2 * pad - k) / stride + 1; d.Wo = (Wi + 2 * pad - k) / stride + 1;
     return d;
+}
+
+// The tensor-core kernels prefetch weight tiles before their dependency wait, which is only safe when the caller knows that
+// the preceding kernel in the stream does not write the weights (the network plan does).  The stand-alone entry points are
+// therefore launched with ordinary stream serialization; DBOA_CABI_PDL=1 opts in (scripts/conv_microbench.py chains).
+static bool cabi_pdl() {
+    static const bool on = [] { const char* e = getenv("DBOA_CABI_PDL"); return e && e[0] == '1'; }();
+    return on;
 }
 
 extern "C" {
@@ -98,22 +108,22 @@ int dboa_conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin
                         dboa_stream_t stream) {
     if (!x || !w || !y) return DBOA_ERR_ARG;
     conv_tc_set_workspace(ws, ws ? (size_t)ws_floats : 0);
-    return conv1x1_tc_fwd(x, w, y, M, Cin, Cout, ST(stream));
+    return conv1x1_tc_fwd(x, w, y, M, Cin, Cout, ST(stream), cabi_pdl());
 }
 int dboa_conv2d_tc_fwd(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
                        int Kpitch, dboa_stream_t stream) {
     if (!x || !w || !y) return DBOA_ERR_ARG;
-    return conv_tc_fwd(x, w, y, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), ST(stream));
+    return conv_tc_fwd(x, w, y, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), ST(stream), cabi_pdl());
 }
 int dboa_conv2d_tc_dgrad(const float* dy, const float* w, float* dx, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
                          int Kpitch, int accumulate, dboa_stream_t stream) {
     if (!dy || !w || !dx) return DBOA_ERR_ARG;
-    return conv_tc_dgrad(dy, w, dx, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), accumulate, ST(stream));
+    return conv_tc_dgrad(dy, w, dx, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), accumulate, ST(stream), cabi_pdl());
 }
 int dboa_conv2d_tc_wgrad(const float* dy, const float* x, float* dw, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
                          int Kpitch, dboa_stream_t stream) {
     if (!dy || !x || !dw) return DBOA_ERR_ARG;
-    return conv_tc_wgrad(dy, x, dw, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), ST(stream));
+    return conv_tc_wgrad(dy, x, dw, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), ST(stream), cabi_pdl());
 }
 long long dboa_gn_partial_floats(int B, int HW, int C) { return (long long)gn_partial_floats(B, HW, C); }
 long long dboa_gn_bwd_partial_floats(int B, int HW, int C) { return (long long)gn_bwd_partial_floats(B, HW, C); }

@@ -558,7 +558,8 @@ __global__ void __launch_bounds__(NT, 2) conv_tf32x3_kernel(const float* __restr
 }
 
 template <int MODE>
-static int launch(const float* p, const float* q, float* o, const ConvDims& d, int rows, int cols, int kred, int accumulate, cudaStream_t st) {
+static int launch(const float* p, const float* q, float* o, const ConvDims& d, int rows, int cols, int kred, int accumulate, cudaStream_t st,
+                  bool pdl) {
     int mtiles = ceil_div(rows, BM);
     if (MODE == DGRAD && d.stride == 2) {                // parity classes of B*Hi/2*Wi/2 rows, longest tap set decides the split
         const int ncls = (d.kh >= 2 ? 2 : 1) * (d.kw >= 2 ? 2 : 1);
@@ -574,7 +575,7 @@ static int launch(const float* p, const float* q, float* o, const ConvDims& d, i
     while (ns < 16 && tiles * ns * 2 <= 296 + tiles && nkb / (ns * 2) >= min_kb) ns *= 2;
     const int per = (nkb + ns - 1) / ns;
     const size_t smem = sizeof(Smem) + 128;
-    return launch_ex(conv_tf32x3_kernel<MODE>, dim3(mtiles, cols / BN, ns), dim3(NT), smem, st, dim3(1, 1, ns), true, p, q, o, d, per,
+    return launch_ex(conv_tf32x3_kernel<MODE>, dim3(mtiles, cols / BN, ns), dim3(NT), smem, st, dim3(1, 1, ns), pdl, p, q, o, d, per,
                      accumulate);
 }
 
@@ -590,24 +591,24 @@ extern "C" int dboa_debug_set_timeline(unsigned long long* buf) {
 }
 #endif
 
-int conv_tc_fwd(const float* x, const float* w, float* y, const ConvDims& d, cudaStream_t st) {
+int conv_tc_fwd(const float* x, const float* w, float* y, const ConvDims& d, cudaStream_t st, bool pdl) {
     if (g_tc_mode == 0 || !tc::shape_ok(d)) return DBOA_ERR_UNSUPPORTED;
-    return tc::launch<tc::FWD>(x, w, y, d, d.B * d.Ho * d.Wo, d.Cout, d.kh * d.kw * d.Cin, 0, st);
+    return tc::launch<tc::FWD>(x, w, y, d, d.B * d.Ho * d.Wo, d.Cout, d.kh * d.kw * d.Cin, 0, st, pdl);
 }
-int conv_tc_dgrad(const float* dy, const float* w, float* dx, const ConvDims& d, int accumulate, cudaStream_t st) {
+int conv_tc_dgrad(const float* dy, const float* w, float* dx, const ConvDims& d, int accumulate, cudaStream_t st, bool pdl) {
     if (g_tc_mode < 2 || !tc::shape_ok(d)) return DBOA_ERR_UNSUPPORTED;
     if (d.stride == 2 && ((d.Hi | d.Wi) & 1)) return DBOA_ERR_UNSUPPORTED;       // the parity-class enumeration needs even extents
-    return tc::launch<tc::DGRAD>(dy, w, dx, d, d.B * d.Hi * d.Wi, d.Cin, d.kh * d.kw * d.Cout, accumulate, st);
+    return tc::launch<tc::DGRAD>(dy, w, dx, d, d.B * d.Hi * d.Wi, d.Cin, d.kh * d.kw * d.Cout, accumulate, st, pdl);
 }
-int conv_tc_wgrad(const float* dy, const float* x, float* dw, const ConvDims& d, cudaStream_t st) {
+int conv_tc_wgrad(const float* dy, const float* x, float* dw, const ConvDims& d, cudaStream_t st, bool pdl) {
     if (g_tc_mode < 2 || !tc::shape_ok(d)) return DBOA_ERR_UNSUPPORTED;
-    return tc::launch<tc::WGRAD>(dy, x, dw, d, d.Cout, d.kh * d.kw * d.Cin, d.B * d.Ho * d.Wo, 1, st);
+    return tc::launch<tc::WGRAD>(dy, x, dw, d, d.Cout, d.kh * d.kw * d.Cin, d.B * d.Ho * d.Wo, 1, st, pdl);
 }
 
-int conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin, int Cout, cudaStream_t st) {
+int conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin, int Cout, cudaStream_t st, bool pdl) {
     ConvDims d;
     d.B = 1; d.Hi = M; d.Wi = 1; d.Cin = Cin; d.Ho = M; d.Wo = 1; d.Cout = Cout; d.kh = 1; d.kw = 1; d.stride = 1; d.pad = 0; d.Kpitch = Cin;
-    return conv_tc_fwd(x, w, y, d, st);
+    return conv_tc_fwd(x, w, y, d, st, pdl);
 }
 
 }  // namespace dboa

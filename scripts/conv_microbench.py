@@ -2,13 +2,17 @@
 batch B, for the fp32 CUDA-core kernels and the tcgen05 TF32x3 kernel, through the C ABI.
 
 Each shape is launched `iters` times back to back on one stream (inputs stay in L2, as inside the running step);
-the figure is the mean time per launch in microseconds, launch gaps included (run with DBOA_PDL=0/1 to see the gap).
+the figure is the mean time per launch in microseconds, launch gaps included.  The stand-alone tensor-core entry points are
+launched without programmatic dependent launch unless DBOA_CABI_PDL=1 (which this script sets: chains of the same kernel on
+fixed weights are safe); DBOA_PDL=0 switches PDL off everywhere.
 
     python scripts/conv_microbench.py [--batch 1] [--iters 60]
 """
 import argparse
 import os
 import sys
+
+os.environ.setdefault('DBOA_CABI_PDL', '1')
 
 import torch
 

@@ -14,6 +14,8 @@ import ctypes as C
 import os
 import sys
 
+os.environ.setdefault('DBOA_CABI_PDL', '1')      # chains of the same kernel on fixed weights: PDL is safe for the stand-alone entry points
+
 import torch
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
