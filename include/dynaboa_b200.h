@@ -70,7 +70,11 @@ int dboa_conv2d_wgrad(const float* dy, const float* x, float* dw, int B, int Hi,
  * needs dboa_set_tensor_core_conv(1); returns DBOA_ERR_UNSUPPORTED for shapes it does not take (Cin % 32, Cout % 64) */
 int dboa_conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin, int Cout, float* ws, long long ws_floats,
                         dboa_stream_t stream);
-/* general convolution forward as a tcgen05 TF32x3 implicit GEMM (same arguments as dboa_conv2d_fwd; Cin % 32 == 0) */
+/* general convolution forward as a tcgen05 TF32x3 implicit GEMM (same arguments as dboa_conv2d_fwd; Cin % 64 == 0,
+ * Cout % 64 == 0, Kpitch == k*k*Cin).  The stand-alone tensor-core entry points are launched with ordinary stream
+ * serialization (inside dboa_hmr_forward/backward the same kernels use programmatic dependent launch and prefetch
+ * weight tiles before their dependency wait, which needs the plan's guarantee that the preceding kernel does not write
+ * the weights); DBOA_CABI_PDL=1 in the environment opts in for callers that can give that guarantee. */
 int dboa_conv2d_tc_fwd(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
                        int Kpitch, dboa_stream_t stream);
 /* data / weight gradient on the same tensor-core kernel (needs dboa_set_tensor_core_conv(2 or 3)); dw is accumulated (+=) */
