@@ -13,6 +13,8 @@ algorithm of the reference's per-frame hot path:
                        MAML.clone / MAML.adapt, first-order
 * ``adaptor_ref``   -- reference base_adaptor.py losses/adaptation + dynaboa_benchmark.py
                        ``Adaptor.adaptation`` / ``inference`` orchestration
+* ``eval_ref``      -- reference dynaboa_benchmark.py:217-240 + utils/pose_utils.py:9-64 (H36M joints, MPJPE,
+                       Procrustes PA-MPJPE, PVE), pinned against the reference's own numpy Procrustes
 
 Pinning status (see DESIGN.md "Oracle"):
 
