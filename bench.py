@@ -283,6 +283,8 @@ def run_ours(args, rank, world, local):
         e0.record()
         for t in range(PRELUDE + args.warmup, n_frames):
             step(t, from_host)
+        if getattr(ad, 'output_stream', None) is not None:        # the interval ends when the LAST frame's output forward (and its
+            torch.cuda.current_stream().wait_stream(ad.output_stream)   # copy-back) on the side stream has finished, not before
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
