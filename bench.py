@@ -42,7 +42,7 @@ def default_options(**over):
              use_frame_losses_upper=1, use_temporal_losses_lower=0, use_temporal_losses_upper=1, sample_num=1, retrieval=1,
              dynamic_boa=1, cos_sim_threshold=3.1e-4, optim_steps=7, lower_level_mixtrain=1, upper_level_mixtrain=1,
              labelloss_weight=0.1, use_meanteacher=1, alpha=0.1, teacherloss_weight=0.1, use_motion=1, interval=5,
-             motionloss_weight=0.8, teacher_dropout=1, dataset='3dpw', save_res=0, tensorboard=0)
+             motionloss_weight=0.8, teacher_dropout=1, dataset='3dpw', save_res=0, tensorboard=0, cache_results=0)
     o.update(over)
     return SimpleNamespace(**o)
 

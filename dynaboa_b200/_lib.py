@@ -26,12 +26,22 @@ class LossArgsStruct(C.Structure):
                 + [('w', F * 8), ('terms', P), ('dp2d', P), ('dj3d', P), ('dR', P), ('dbeta', P), ('dR_accumulate', I)])
 
 
+class FusedConvStruct(C.Structure):
+    _fields_ = ([(n, P) for n in ('x', 'res', 'w', 'a_out', 'stats_out', 'stats2_out', 'part_in', 'part2_in', 'gamma', 'beta',
+                                  'gamma2', 'beta2', 'y', 'part_out')]
+                + [(n, I) for n in ('mode', 'slots_in', 'slots2_in', 'Hi', 'Cin', 'Cout', 'k', 'stride', 'pad')])
+
+
 # name -> (restype, argtypes); mirrors include/dynaboa_b200.h one to one
 SIGNATURES = {
     'dboa_version': (C.c_char_p, []),
     'dboa_last_cuda_error': (I, []),
     'dboa_launch_count': (L, []),
     'dboa_set_tensor_core_conv': (I, [I]),
+    'dboa_set_fused_forward': (I, [I]),
+    'dboa_get_fused_forward': (I, []),
+    'dboa_conv_fused_part_floats': (L, [I, I, I]),
+    'dboa_conv_fused_fwd': (I, [C.POINTER(FusedConvStruct), I, I, C.POINTER(I), P]),
     'dboa_hmr_num_params': (I, []),
     'dboa_hmr_arena_floats': (L, []),
     'dboa_hmr_param_info': (I, [I, C.c_char_p, I, C.POINTER(L), C.POINTER(I), C.POINTER(L), C.POINTER(L)]),
@@ -72,6 +82,8 @@ SIGNATURES = {
     'dboa_adam_ema': (I, [P, P, P, P, P, L, F, F, F, F, I, F, P]),
     'dboa_ema_update': (I, [P, P, L, F, P]),
     'dboa_cosine_pairs': (I, [C.POINTER(P), C.POINTER(P), C.POINTER(L), I, P, L, P, F, P]),
+    'dboa_cosine_partial_floats': (L, [C.POINTER(L), I]),
+    'dboa_cosine_terms': (I, [C.POINTER(P), C.POINTER(P), C.POINTER(L), I, P, L, P, P]),
     'dboa_retrieval_nearest': (I, [P, P, I, I, P, P, P]),
     'dboa_eval_scratch_floats': (L, [I, I]),
     'dboa_eval_metrics': (I, [P, P, P, P, I, I, P, I, P, P, I, P]),

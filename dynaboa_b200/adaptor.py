@@ -150,7 +150,7 @@ class Adaptor(BaseAdaptor):
             # (the reference copies joints and both meshes to the host and runs a numpy SVD per sample: :217-240)
             metrics = self.eval_metrics(pred_vertices, gt_vertices, gt_neutral).cpu().numpy()
             mpjpe, pampjpe, pve = metrics[:, 0], metrics[:, 1], float(metrics[:, 2].mean())
-        if getattr(self.options, 'cache_results', 0):
+        if getattr(self.options, 'cache_results', 1):        # the reference always dumps Pred_<step>.pt (:250-254); 0 turns the disk write off
             cam_t = torch.stack([pred_cam[:, 1], pred_cam[:, 2], 2 * 5000. / (constants.IMG_RES * pred_cam[:, 0] + 1e-9)], dim=-1)
             torch.save({'verts': pred_vertices.cpu().numpy(), 'cam': cam_t.cpu().numpy(), 'rotmat': pred_rotmat.cpu().numpy(),
                         'beta': pred_shape.cpu().numpy()}, osp.join(self.exppath, 'result', f'Pred_{self.global_step}.pt'))

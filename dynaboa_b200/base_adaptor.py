@@ -71,7 +71,8 @@ class BaseAdaptor:
         self.setup_smpl()
         self.history, self.fit_losses, self.global_step = {}, {}, 0
         self.kp2dlosses_lower, self.kp2dlosses_upper = [], {}
-        self._cos_partial = torch.empty(3 * 4096, dtype=torch.float32, device=self.device)
+        self._cos_partial = None                     # scratch of the feature test, sized from the features on first use
+        self.dp_group = None                         # torch.distributed group of the data-parallel ranks (None: default group)
 
     # ------------------------------------------------------------------ set-up (reference :70-158)
     def seed_everything(self, seed):
@@ -132,7 +133,7 @@ class BaseAdaptor:
         if self.options.dataset == '3dpw':
             dataset, self.imgdir = PW3D(self.options), config.PW3D_ROOT
         else:
-            dataset, self.imgdir = Internet_dataset(), osp.join(config.InternetData_ROOT, 'images')
+            dataset, self.imgdir = Internet_dataset(self.options), osp.join(config.InternetData_ROOT, 'images')
         self.dataloader = DataLoader(dataset, batch_size=self.options.batch_size, shuffle=False, num_workers=0)
 
     def set_criterion(self):
@@ -180,16 +181,27 @@ class BaseAdaptor:
         pass
 
     def cal_feature_diff(self, features_i, features_j):
+        """reference :211-219.  One launch pair returns, per feature, the sums (a.b, |a|^2, |b|^2); under data-parallel
+        adaptation they are all-reduced over the ranks first (the reference flattens across the batch, :215), so every
+        rank sees the same cosines and takes the same number of dynamic steps -- the gradient all-reduce inside those
+        steps would dead-lock otherwise."""
         import ctypes as C
+        import torch.distributed as dist
         n = len(features_i)
         fa = [_dense_ptr_tensor(t) for t in features_i]
         fb = [_dense_ptr_tensor(t) for t in features_j]
         pa = (C.c_void_p * n)(*[t.data_ptr() for t in fa])
         pb = (C.c_void_p * n)(*[t.data_ptr() for t in fb])
         ln = (C.c_longlong * n)(*[t.numel() for t in fa])
-        out = torch.empty(n, dtype=torch.float32, device=self.device)
-        _lib.call('dboa_cosine_pairs', pa, pb, ln, n, ptr(self._cos_partial), self._cos_partial.numel(), ptr(out), 1e-12, stream())
-        cos = out.cpu()                                                   # the one host sync of the dynamic test
+        need = _lib.load().dboa_cosine_partial_floats(ln, n)
+        if self._cos_partial is None or self._cos_partial.numel() < need:
+            self._cos_partial = torch.empty(need, dtype=torch.float32, device=self.device)
+        terms = torch.empty(n, 3, dtype=torch.float64, device=self.device)
+        _lib.call('dboa_cosine_terms', pa, pb, ln, n, ptr(self._cos_partial), self._cos_partial.numel(), ptr(terms), stream())
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.dp_group) > 1:
+            dist.all_reduce(terms, op=dist.ReduceOp.SUM, group=self.dp_group)
+        t = terms.cpu()                                                   # the one host sync of the dynamic test
+        cos = (t[:, 0] / (t[:, 1].sqrt().clamp_min(1e-12) * t[:, 2].sqrt().clamp_min(1e-12))).float()
         self.fit_losses['feat_sim/cos_sim'] = cos.sum() / (n - 1)        # reference :218 divides by the last index
         return {i: {'cos': float(cos[i])} for i in range(n)}
 

@@ -14,6 +14,8 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
                 cudaStream_t st);
 int hmr_backward(const float* P, const float* T, int B, int masked, const float* d_rotmat, const float* d_shape, const float* d_cam,
                  float* G, float* scratch, cudaStream_t st);
+void hmr_set_fused_forward(bool on);
+bool hmr_fused_forward();
 int hmr_num_params();
 long long hmr_arena_floats();
 int hmr_param_info(int i, char* name, int cap, long long* off, int* ndim, long long shape[4], long long stride[4]);
@@ -64,6 +66,9 @@ const char* dboa_version(void) { return "dynaboa_b200 0.1 (sm_100a)"; }
 int dboa_last_cuda_error(void) { return g_last_cuda_error; }
 long long dboa_launch_count(void) { return g_launch_count; }
 int dboa_set_tensor_core_conv(int enable) { conv_tc_set_mode(enable); return DBOA_OK; }
+
+int dboa_set_fused_forward(int enable) { hmr_set_fused_forward(enable != 0); return DBOA_OK; }
+int dboa_get_fused_forward(void) { return hmr_fused_forward() ? 1 : 0; }
 
 int dboa_hmr_num_params(void) { return hmr_num_params(); }
 long long dboa_hmr_arena_floats(void) { return hmr_arena_floats(); }
@@ -124,6 +129,32 @@ int dboa_conv2d_tc_wgrad(const float* dy, const float* x, float* dw, int B, int 
                          int Kpitch, dboa_stream_t stream) {
     if (!dy || !x || !dw) return DBOA_ERR_ARG;
     return conv_tc_wgrad(dy, x, dw, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), ST(stream), cabi_pdl());
+}
+long long dboa_conv_fused_part_floats(int B, int Ho, int Cout) {
+    const long long tps = (Ho * Ho + 127) / 128, ntg = Cout / 4 >= 64 ? Cout / 4 / 64 : 1;
+    return (long long)B * 4 * tps * ntg * 16 * 4;
+}
+int dboa_conv_fused_fwd(const dboa_fused_conv* probs, int nprob, int B, int* slots_out, dboa_stream_t stream) {
+    if (!probs || nprob < 1 || nprob > 2 || B < 1) return DBOA_ERR_ARG;
+    FusedConv d[2];
+    for (int i = 0; i < nprob; ++i) {
+        const dboa_fused_conv& c = probs[i];
+        if (!c.x || !c.w || !c.y || !c.part_out) return DBOA_ERR_ARG;
+        if (c.mode >= 1 && (!c.part_in || !c.gamma || !c.beta)) return DBOA_ERR_ARG;
+        if (c.mode >= 2 && !c.res) return DBOA_ERR_ARG;
+        if (c.mode == 3 && (!c.part2_in || !c.gamma2 || !c.beta2)) return DBOA_ERR_ARG;
+        FusedConv& f = d[i];
+        f.x = c.x; f.res = c.res; f.w = c.w; f.a_out = c.a_out; f.stats_out = c.stats_out; f.stats2_out = c.stats2_out;
+        f.part_in = c.part_in; f.part2_in = c.part2_in; f.gamma = c.gamma; f.beta = c.beta; f.gamma2 = c.gamma2; f.beta2 = c.beta2;
+        f.y = c.y; f.part_out = c.part_out; f.mode = c.mode; f.S_in = c.slots_in; f.S2_in = c.slots2_in;
+        f.Hi = c.Hi; f.Cin = c.Cin; f.Cout = c.Cout; f.k = c.k; f.stride = c.stride; f.pad = c.pad;
+        f.Ho = (c.Hi + 2 * c.pad - c.k) / c.stride + 1;
+        if (!conv_fused_ok(f)) return DBOA_ERR_UNSUPPORTED;
+    }
+    const int nz = conv_fused_plan(d, nprob, B);
+    if (slots_out)
+        for (int i = 0; i < nprob; ++i) slots_out[i] = conv_fused_slots(d[i], nz);
+    return conv_fused_launch(d, nprob, B, nz, ST(stream), cabi_pdl());
 }
 long long dboa_gn_partial_floats(int B, int HW, int C) { return (long long)gn_partial_floats(B, HW, C); }
 long long dboa_gn_bwd_partial_floats(int B, int HW, int C) { return (long long)gn_bwd_partial_floats(B, HW, C); }
@@ -233,7 +264,19 @@ int dboa_cosine_pairs(const float* const* a, const float* const* b, const long l
     CosinePairs cp;
     cp.npairs = npairs;
     for (int i = 0; i < npairs; ++i) { cp.a[i] = a[i]; cp.b[i] = b[i]; cp.n[i] = n[i]; }
-    return cosine_pairs(cp, partial, (size_t)partial_floats, out, eps, ST(stream));
+    return cosine_pairs(cp, partial, (size_t)partial_floats, out, nullptr, eps, ST(stream));
+}
+long long dboa_cosine_partial_floats(const long long* n, int npairs) {
+    if (!n || npairs < 1 || npairs > 16) return DBOA_ERR_ARG;
+    return cosine_partial_floats(n, npairs);
+}
+int dboa_cosine_terms(const float* const* a, const float* const* b, const long long* n, int npairs, float* partial, long long partial_floats,
+                      double* terms, dboa_stream_t stream) {
+    if (!a || !b || !n || !partial || !terms || npairs < 1 || npairs > 16) return DBOA_ERR_ARG;
+    CosinePairs cp;
+    cp.npairs = npairs;
+    for (int i = 0; i < npairs; ++i) { cp.a[i] = a[i]; cp.b[i] = b[i]; cp.n[i] = n[i]; }
+    return cosine_pairs(cp, partial, (size_t)partial_floats, nullptr, terms, 0.f, ST(stream));
 }
 int dboa_retrieval_nearest(const float* feat, const float* centers, int K, int D, int* best, float* dists, dboa_stream_t stream) {
     if (!feat || !centers || !best || !dists) return DBOA_ERR_ARG;

@@ -132,7 +132,10 @@ static Tape build_tape(int B) {
         const ConvLayer& c = n.convs[i];
         long long sz = (long long)B * c.hout * c.hout * c.cout;
         t.conv[i].y = take(sz);
-        t.conv[i].part = take((long long)gn_partial_floats(B, c.hout * c.hout, c.cout));
+        {   // partial GroupNorm statistics left by the fused convolution: float4 slots [B][4][tiles/sample x n-tiles/group x <= 16 K-slices]
+            const long long tps = (c.hout * c.hout + 127) / 128, ntg = c.cout / 4 >= 64 ? c.cout / 4 / 64 : 1;
+            t.conv[i].part = take((long long)B * 4 * tps * ntg * 16 * 4);
+        }
         t.conv[i].stats = take((long long)B * 8);
         t.conv[i].a = -1;
     }
@@ -225,6 +228,12 @@ void hmr_set_async_wgrad(bool on) { g_async_enabled = on; }
 static const int g_wgrad_streams = [] { const char* e = getenv("DBOA_WGRAD_STREAMS"); return (e && e[0] == '1') ? 1 : BwdAsync::NSIDE; }();
 
 static ConvDims dims_of(const ConvLayer& c, int B);
+
+// DBOA_FUSED_FWD=0 in the environment (or dboa_set_fused_forward(0)) selects the round-1 forward: one convolution launch and
+// one GroupNorm launch per layer (kept as the A/B reference of the fused path; both fill the same tape)
+static bool g_fused_fwd = [] { const char* e = getenv("DBOA_FUSED_FWD"); return !(e && e[0] == '0'); }();
+void hmr_set_fused_forward(bool on) { g_fused_fwd = on; }
+bool hmr_fused_forward() { return g_fused_fwd; }
 
 // table for gn_param_finish: where each GroupNorm's affine gradients live and where its per-sample rows start
 struct GnItems { std::vector<long long> cum; GnFinishItem* dev = nullptr; };
@@ -374,6 +383,63 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
     DBOA_TRY(gn_plain(0, T + t.conv[0].a, 1, nullptr));
     DBOA_TRY(maxpool3x3s2_fwd(T + t.conv[0].a, T + t.p0, reinterpret_cast<unsigned char*>(T + t.p0_idx), B, 112, 112, 64, st));
     const float* x = T + t.p0;
+    if (g_fused_fwd && conv_tc_enabled()) {
+        // ---- fused plan: 3 launches per bottleneck (conv1 [+ down-sampling conv], conv2, conv3); every GroupNorm is applied by
+        // the consumer of its tensor on load, its statistics come out of the producer's epilogue (conv_fused.cu)
+        std::vector<int> S(n.convs.size(), 0);
+        auto base_desc = [&](int ci) {
+            const ConvLayer& c = n.convs[ci];
+            FusedConv f;
+            memset(&f, 0, sizeof f);
+            f.w = P + c.w_off; f.y = T + t.conv[ci].y; f.part_out = T + t.conv[ci].part;
+            f.Hi = c.hin; f.Cin = c.cin; f.Cout = c.cout; f.k = c.k; f.stride = c.stride; f.pad = c.pad; f.Ho = c.hout;
+            return f;
+        };
+        auto gn_of = [&](FusedConv& f, int src) {                  // operand = relu(gn(y[src]))
+            const ConvLayer& c = n.convs[src];
+            f.mode = 1; f.x = T + t.conv[src].y; f.part_in = T + t.conv[src].part; f.S_in = S[src];
+            f.gamma = P + c.g_off; f.beta = P + c.b_off;
+            f.a_out = T + t.conv[src].a; f.stats_out = T + t.conv[src].stats;
+        };
+        auto run = [&](FusedConv* d, int np, const int* ci) {
+            const int nz = conv_fused_plan(d, np, B);
+            int rc = conv_fused_launch(d, np, B, nz, st, true);
+            for (int i = 0; i < np; ++i) S[ci[i]] = conv_fused_slots(d[i], nz);
+            return rc;
+        };
+        for (size_t bi = 0; bi < n.blocks.size(); ++bi) {
+            const Block& b = n.blocks[bi];
+            FusedConv d[2];
+            int ci[2] = {b.c1, b.cd};
+            const int np = b.cd >= 0 ? 2 : 1;
+            for (int i = 0; i < np; ++i) {
+                FusedConv& f = d[i];
+                f = base_desc(ci[i]);
+                if (bi == 0) { f.mode = 0; f.x = T + t.p0; continue; }
+                const Block& pb = n.blocks[bi - 1];                  // operand = output of the previous block, formed on load
+                gn_of(f, pb.c3);
+                if (pb.cd >= 0) {
+                    const ConvLayer& pd = n.convs[pb.cd];
+                    f.mode = 3; f.res = T + t.conv[pb.cd].y; f.part2_in = T + t.conv[pb.cd].part; f.S2_in = S[pb.cd];
+                    f.gamma2 = P + pd.g_off; f.beta2 = P + pd.b_off; f.stats2_out = T + t.conv[pb.cd].stats;
+                } else {
+                    f.mode = 2; f.res = T + t.conv[n.blocks[bi - 2].c3].a;
+                }
+                if (i == 1) { f.a_out = nullptr; f.stats_out = nullptr; f.stats2_out = nullptr; }     // conv1 is the writer
+            }
+            DBOA_TRY(run(d, np, ci));
+            d[0] = base_desc(b.c2); gn_of(d[0], b.c1); ci[0] = b.c2;
+            DBOA_TRY(run(d, 1, ci));
+            d[0] = base_desc(b.c3); gn_of(d[0], b.c2); ci[0] = b.c3;
+            DBOA_TRY(run(d, 1, ci));
+        }
+        const Block& lb = n.blocks.back();
+        const ConvLayer& l3 = n.convs[lb.c3];
+        if (lb.cd >= 0) return DBOA_ERR_UNSUPPORTED;
+        DBOA_TRY(gn_res_avgpool(T + t.conv[lb.c3].y, T + t.conv[n.blocks[n.blocks.size() - 2].c3].a, T + t.conv[lb.c3].part, S[lb.c3],
+                                P + l3.g_off, P + l3.b_off, T + t.conv[lb.c3].a, T + t.conv[lb.c3].stats, T + t.xc, B, 49, 2048, HEAD_LD, 3,
+                                (size_t)B * HEAD_LD, st));
+    } else {
     for (const Block& b : n.blocks) {
         const ConvLayer &c1 = n.convs[b.c1], &c2 = n.convs[b.c2], &c3 = n.convs[b.c3];
         DBOA_TRY(conv_forward(c1, B, x, P + c1.w_off, T + t.conv[b.c1].y, sc.ws, st));
@@ -395,6 +461,7 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
     }
     // pooled feature goes straight into the three regressor input rows
     DBOA_TRY(avgpool_fwd(x, T + t.xc, B, 49, 2048, HEAD_LD, 3, (size_t)B * HEAD_LD, st));
+    }
     DBOA_TRY(launch_ex(head_init_kernel, dim3(ceil_div(B * NDEC, 128)), dim3(128), 0, st, dim3(1, 1, 1), true, init_pose, init_shape, init_cam, T + t.params, T + t.xc, B));
     if (drop_masks) cudaMemcpyAsync(T + t.masks, drop_masks, 6ULL * B * HID * sizeof(float), cudaMemcpyDeviceToDevice, st);
     for (int it = 0; it < 3; ++it) {

@@ -115,18 +115,25 @@ __global__ void __launch_bounds__(256) cosine_partial_kernel(CosinePairs cp, flo
     ab = block_sum(ab, red); aa = block_sum(aa, red); bb = block_sum(bb, red);
     if (threadIdx.x == 0) { partial[blockIdx.x * 3] = ab; partial[blockIdx.x * 3 + 1] = aa; partial[blockIdx.x * 3 + 2] = bb; }
 }
-__global__ void cosine_finish_kernel(CosinePairs cp, const float* __restrict__ partial, float* __restrict__ out, float eps) {
+__global__ void cosine_finish_kernel(CosinePairs cp, const float* __restrict__ partial, float* __restrict__ out, double* __restrict__ terms,
+                                     float eps) {
     pdl_wait();
     pdl_trigger();
     int pair = threadIdx.x;
     if (pair >= cp.npairs) return;
     double ab = 0, aa = 0, bb = 0;
     for (int k = cp.blk_off[pair]; k < cp.blk_off[pair + 1]; ++k) { ab += partial[k * 3]; aa += partial[k * 3 + 1]; bb += partial[k * 3 + 2]; }
+    if (terms != nullptr) { terms[pair * 3] = ab; terms[pair * 3 + 1] = aa; terms[pair * 3 + 2] = bb; }
     double na = sqrt(aa), nb = sqrt(bb);
     na = na < eps ? eps : na; nb = nb < eps ? eps : nb;
-    out[pair] = (float)(ab / (na * nb));
+    if (out != nullptr) out[pair] = (float)(ab / (na * nb));
 }
-int cosine_pairs(const CosinePairs& cp_in, float* partial, size_t partial_floats, float* out, float eps, cudaStream_t st) {
+long long cosine_partial_floats(const long long* n, int npairs) {
+    long long blocks = 0;
+    for (int i = 0; i < npairs; ++i) blocks += ceil_div(n[i], COS_CHUNK);
+    return 3 * blocks;
+}
+int cosine_pairs(const CosinePairs& cp_in, float* partial, size_t partial_floats, float* out, double* terms, float eps, cudaStream_t st) {
     CosinePairs cp = cp_in;
     if (cp.npairs < 1 || cp.npairs > 16) return DBOA_ERR_ARG;
     cp.blk_off[0] = 0;
@@ -134,7 +141,7 @@ int cosine_pairs(const CosinePairs& cp_in, float* partial, size_t partial_floats
     const int nblk = cp.blk_off[cp.npairs];
     if ((size_t)nblk * 3 > partial_floats) return DBOA_ERR_ARG;
     DBOA_TRY(launch_ex(cosine_partial_kernel, dim3(nblk), dim3(256), 0, st, dim3(1, 1, 1), true, cp, partial));
-    return launch_ex(cosine_finish_kernel, dim3(1), dim3(32), 0, st, dim3(1, 1, 1), true, cp, partial, out, eps);
+    return launch_ex(cosine_finish_kernel, dim3(1), dim3(32), 0, st, dim3(1, 1, 1), true, cp, partial, out, terms, eps);
 }
 
 // nearest cluster centre by cosine distance: one block, warp per centre (round robin)

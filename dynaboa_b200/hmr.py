@@ -22,6 +22,9 @@ from . import _lib
 from ._lib import ptr, stream
 
 _LAYOUT = None
+# callable(B, device) -> (3,2,B,1024) scaled keep-masks used by every HMR in train mode that has no mask_provider of its own
+# (parity tests replay the reference's recorded teacher dropout masks through the UNCHANGED driver this way)
+DEFAULT_MASK_PROVIDER = None
 
 
 class ArenaLayout:
@@ -263,6 +266,8 @@ class HMR(nn.Module):
             return None
         if self.mask_provider is not None:
             return self.mask_provider(B, device)
+        if DEFAULT_MASK_PROVIDER is not None:
+            return DEFAULT_MASK_PROVIDER(B, device)
         return (torch.rand(3, 2, B, 1024, device=device) >= 0.5).float() * 2.0      # nn.Dropout(p=0.5)
 
     def forward(self, x, need_feature=False, init_pose=None, init_shape=None, init_cam=None, n_iter=3):

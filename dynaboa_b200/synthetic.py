@@ -231,7 +231,7 @@ def make_exemplar_bank(n=64, seed=SEED):
     )
 
 
-def make_clusters(n_items=64, k=10, seed=SEED):
+def make_clusters(n_items=64, k=6, seed=SEED):
     """Cluster centres (K,2048) and per-cluster item lists (reference base_adaptor.py:74-80)."""
     rng = np.random.default_rng(seed * 1000 + 404)
     centers = np.abs(rng.normal(0.5, 0.3, size=(k, 2048))).astype(np.float32)
@@ -291,7 +291,7 @@ class SyntheticStream:
         return iter(self.frames)
 
 
-def write_asset_dir(root, seed=SEED, n_exemplars=64, k=10):
+def write_asset_dir(root, seed=SEED, n_exemplars=64, k=6):
     """Materialise every asset file ``BaseAdaptor.__init__`` loads (paths in ``config``)."""
     import os
     os.makedirs(os.path.join(root, 'smpl'), exist_ok=True)

@@ -34,6 +34,12 @@ long long dboa_launch_count(void);         /* kernels launched by this library s
  * 2: forward + dgrad + wgrad; 3 (default): forward + dgrad, weight gradients on CUDA cores */
 int dboa_set_tensor_core_conv(int mode);
 
+/* 1 (default): dboa_hmr_forward runs the fused plan -- every GroupNorm applied by the consuming convolution on load, its
+ * statistics produced by the epilogue of the producing one (3 launches per bottleneck); 0: one convolution and one
+ * GroupNorm launch per layer (round-1 plan, kept as the A/B reference).  Both fill the same tape. */
+int dboa_set_fused_forward(int enable);
+int dboa_get_fused_forward(void);
+
 /* ---- HMR regressor: parameter arena and tape layout ----------------------------------------
  * replaces: model/hmr.py:67-124 (HMR.__init__/_make_layer state_dict contract).
  * The 169 parameters live in ONE flat fp32 arena; entry i (in nn.Module.parameters() order) is the
@@ -82,6 +88,25 @@ int dboa_conv2d_tc_dgrad(const float* dy, const float* w, float* dx, int B, int 
                          int Kpitch, int accumulate, dboa_stream_t stream);
 int dboa_conv2d_tc_wgrad(const float* dy, const float* x, float* dw, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
                          int Kpitch, dboa_stream_t stream);
+/* Fused tcgen05 convolution, the unit the forward plan is made of (csrc/conv_fused.cu).
+ * replaces: nn.Conv2d + the nn.GroupNorm(4, C) / ReLU / residual add that PRECEDES it in Bottleneck.forward
+ * (model/hmr.py:40-60), + the statistics pass of the GroupNorm that follows it.
+ *   y = conv(T(x), w);  part_out <- per-tile (count, mean, M2) of y per (sample, group)  [float4 slots, B x 4 x slots]
+ *   mode 0: T(x) = x;  1: relu(gn(x));  2: relu(gn(x) + res);  3: relu(gn(x) + gn2(res))
+ * gn statistics come from `part_in` (`slots_in` slots per (sample, group), as a previous call reported through slots_out).
+ * a_out / stats_out / stats2_out (optional): T(x) materialised, (mean, rstd) [B][4][2] of the GroupNorm(s).
+ * Up to 2 problems of equal mode and reduction length k*k*Cin share one launch.  Cin % 64 == 0, Cout % 64 == 0, k in {1, 3}. */
+typedef struct dboa_fused_conv {
+    const float *x, *res, *w;
+    float *a_out, *stats_out, *stats2_out;
+    const float *part_in, *part2_in, *gamma, *beta, *gamma2, *beta2;
+    float *y, *part_out;
+    int mode, slots_in, slots2_in;
+    int Hi, Cin, Cout, k, stride, pad;
+} dboa_fused_conv;
+long long dboa_conv_fused_part_floats(int B, int Ho, int Cout);   /* capacity of part_out in floats */
+int dboa_conv_fused_fwd(const dboa_fused_conv* probs, int nprob, int B, int* slots_out, dboa_stream_t stream);
+
 /* replaces: nn.GroupNorm(4, C) + ReLU (+ residual) forward / backward (model/hmr.py:14-18,40-60).
  * C / 16 must be a power of two; one launch each (thread-block clusters).  `partial` is caller-provided scratch of
  * dboa_gn_*partial_floats() floats; the forward size is 0 in this version and the pointer may then be NULL. */
@@ -157,6 +182,13 @@ int dboa_ema_update(float* teacher, const float* p, long long n, float alpha, db
 /* cal_feature_diff :211-219: cosine similarity of npairs (<=16) flattened tensor pairs; host arrays of device pointers */
 int dboa_cosine_pairs(const float* const* a, const float* const* b, const long long* n, int npairs, float* partial,
                       long long partial_floats, float* out, float eps, dboa_stream_t stream);
+/* the same reduction, returning per pair the three sums (a.b, |a|^2, |b|^2) in double, [npairs][3]: under data-parallel
+ * adaptation they are all-reduced before the cosine is formed, so that every rank takes the same branch of the
+ * dynamic loop (dynaboa_benchmark.py:161-192; cal_feature_diff flattens across the batch, base_adaptor.py:215).
+ * partial: dboa_cosine_partial_floats(n, npairs) floats of scratch. */
+long long dboa_cosine_partial_floats(const long long* n, int npairs);
+int dboa_cosine_terms(const float* const* a, const float* const* b, const long long* n, int npairs, float* partial,
+                      long long partial_floats, double* terms, dboa_stream_t stream);
 /* retrieval :82-84: index of the centre with the smallest cosine distance to feat (D,) among centers (K,D) */
 int dboa_retrieval_nearest(const float* feat, const float* centers, int K, int D, int* best, float* dists, dboa_stream_t stream);
 

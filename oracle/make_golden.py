@@ -469,8 +469,8 @@ def main():
         if 'c2' in which:   # BASELINE.json configs[1]
             golden_adapt(workdir, 'c2', 8, inner_step=1, retrieval=0, lower_level_mixtrain=0,
                          upper_level_mixtrain=0, dynamic_boa=0)
-        if 'c3' in which:   # configs[2] at reduced exemplar count (fixture size / CPU time)
-            golden_adapt(workdir, 'c3', 2, inner_step=3, retrieval=1, sample_num=2, lower_level_mixtrain=1,
+        if 'c3' in which:   # BASELINE.json configs[2]: 3 inner steps, retrieval minibatch of 8 exemplars
+            golden_adapt(workdir, 'c3', 2, inner_step=3, retrieval=1, sample_num=8, lower_level_mixtrain=1,
                          upper_level_mixtrain=1, dynamic_boa=0)
         if 'c5' in which:   # dynamic loop exercised (threshold lowered so it fires on random weights)
             golden_adapt(workdir, 'c5', 2, inner_step=1, retrieval=1, sample_num=1, lower_level_mixtrain=1,

@@ -1,0 +1,214 @@
+"""Fused tcgen05 convolution (csrc/conv_fused.cu): GroupNorm of the operand applied on load, GroupNorm statistics of the
+output from the epilogue, weights through TMA.  Checked against torch (fp64 convolution, F.group_norm) on the device,
+one problem and two problems per launch, every transform mode, and end to end against the unfused plan."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def L():
+    from dynaboa_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def wmat(w):
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+def merged_stats(part, B, slots):
+    """(count, mean, M2) slots [B][4][slots] -> mean, biased variance per (b, g) in fp64 (Chan merge on the host)."""
+    p = part.view(-1, 4)[:B * 4 * slots].view(B, 4, slots, 4).double().cpu()
+    n, m, M2 = p[..., 0], p[..., 1], p[..., 2]
+    N = n.sum(-1)
+    mean = (n * m).sum(-1) / N
+    var = (M2 + n * (m - mean[..., None]) ** 2).sum(-1) / N
+    return N, mean, var
+
+
+def group_stats(y_nchw):
+    B, Cc = y_nchw.shape[:2]
+    g = y_nchw.double().reshape(B, 4, -1)
+    return g.mean(-1).cpu(), g.var(-1, unbiased=False).cpu()
+
+
+class Prob:
+    """One problem of a fused launch: keeps every tensor alive and builds the C struct."""
+
+    def __init__(self, L, B, Hi, Cin, Cout, k, stride, pad, mode, x, w, res=None, part_in=None, slots_in=0, gamma=None, beta=None,
+                 part2_in=None, slots2_in=0, gamma2=None, beta2=None, want_a=True):
+        self.L, self.B, self.mode = L, B, mode
+        self.Ho = (Hi + 2 * pad - k) // stride + 1
+        dev = 'cuda'
+        self.x, self.w, self.res = x, w, res
+        self.y = torch.full((B, self.Ho, self.Ho, Cout), float('nan'), device=dev)
+        self.part_out = torch.zeros(L.load().dboa_conv_fused_part_floats(B, self.Ho, Cout), device=dev)
+        self.a_out = torch.full_like(x, float('nan')) if (mode >= 1 and want_a) else None
+        self.stats_out = torch.full((B, 4, 2), float('nan'), device=dev) if mode >= 1 and want_a else None
+        self.stats2_out = torch.full((B, 4, 2), float('nan'), device=dev) if mode == 3 and want_a else None
+        self.keep = (part_in, gamma, beta, part2_in, gamma2, beta2)
+        s = L.FusedConvStruct()
+        for name, t in (('x', x), ('res', res), ('w', w), ('a_out', self.a_out), ('stats_out', self.stats_out), ('stats2_out', self.stats2_out),
+                        ('part_in', part_in), ('part2_in', part2_in), ('gamma', gamma), ('beta', beta), ('gamma2', gamma2), ('beta2', beta2),
+                        ('y', self.y), ('part_out', self.part_out)):
+            setattr(s, name, None if t is None else t.data_ptr())
+        s.mode, s.slots_in, s.slots2_in = mode, slots_in, slots2_in
+        s.Hi, s.Cin, s.Cout, s.k, s.stride, s.pad = Hi, Cin, Cout, k, stride, pad
+        self.struct = s
+        self.slots = None
+
+
+def launch(L, probs):
+    B = probs[0].B
+    arr = (L.FusedConvStruct * len(probs))(*[p.struct for p in probs])
+    slots = (C.c_int * 2)()
+    L.call('dboa_conv_fused_fwd', arr, len(probs), B, slots, L.stream())
+    torch.cuda.synchronize()
+    for i, p in enumerate(probs):
+        p.slots = slots[i]
+
+
+def check_output(p, a_nchw, w_nchw, stride, pad, tag):
+    ref = F.conv2d(a_nchw.double(), w_nchw.double(), stride=stride, padding=pad)
+    assert torch.isfinite(p.y).all(), tag
+    assert rel_err(p.y.permute(0, 3, 1, 2), ref) < 5e-6, tag
+    N, mean, var = merged_stats(p.part_out, p.B, p.slots)
+    rm, rv = group_stats(ref)
+    assert torch.equal(N, torch.full_like(N, ref[0].numel() / 4)), tag
+    assert (mean - rm).abs().max() <= 1e-5 * rv.sqrt().max() + 1e-6, tag
+    assert ((var - rv).abs() / rv).max() < 2e-5, tag
+
+
+CASES = [  # B, H, Cin, Cout, k, stride, pad
+    (1, 56, 64, 64, 1, 1, 0), (1, 56, 64, 256, 1, 1, 0), (1, 56, 64, 64, 3, 1, 1), (2, 28, 128, 128, 3, 2, 1), (1, 28, 512, 128, 1, 1, 0),
+    (1, 14, 256, 256, 3, 1, 1), (3, 14, 1024, 256, 1, 1, 0), (1, 14, 512, 512, 3, 2, 1), (1, 7, 512, 2048, 1, 1, 0), (2, 7, 2048, 512, 1, 1, 0),
+    (1, 7, 512, 512, 3, 1, 1), (9, 7, 512, 512, 3, 1, 1), (1, 28, 512, 1024, 1, 2, 0)]
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_plain_operand_and_statistics(L, case):
+    """mode 0: convolution of an existing activation; output and the per-group statistics its epilogue leaves."""
+    B, H, Cin, Cout, k, s, pd = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, H, H, generator=g).cuda() + 0.3
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (k * k * Cin) ** 0.5).cuda()
+    p = Prob(L, B, H, Cin, Cout, k, s, pd, 0, nhwc(x), wmat(w))
+    launch(L, [p])
+    check_output(p, x, w, s, pd, case)
+
+
+CHAINS = [  # B, H, C0 (input of the producer), C1 (its output = operand channels), C2, k, stride of the consumer
+    (1, 56, 64, 64, 64, 3, 1), (2, 56, 64, 128, 128, 3, 2), (1, 28, 128, 128, 512, 1, 1), (2, 14, 256, 256, 256, 3, 1), (1, 14, 256, 1024, 256, 1, 1),
+    (1, 14, 128, 512, 512, 3, 2), (3, 7, 512, 512, 2048, 1, 1), (1, 7, 512, 2048, 512, 1, 1)]
+
+
+@pytest.mark.parametrize('case', CHAINS)
+def test_groupnorm_on_load(L, case):
+    """producer (mode 0) -> consumer (mode 1): the consumer normalises with the producer's partial statistics, writes the
+    activation and (mean, rstd) to the tape, and convolves the normalised operand."""
+    B, H, C0, C1, C2, k, s = case
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    x = torch.randn(B, C0, H, H, generator=g).cuda()
+    w0 = (torch.randn(C1, C0, 1, 1, generator=g) / C0 ** 0.5).cuda()
+    gamma = (1 + 0.3 * torch.randn(C1, generator=g)).cuda()
+    beta = (0.2 * torch.randn(C1, generator=g)).cuda()
+    w1 = (torch.randn(C2, C1, k, k, generator=g) / (k * k * C1) ** 0.5).cuda()
+    p0 = Prob(L, B, H, C0, C1, 1, 1, 0, 0, nhwc(x), wmat(w0))
+    launch(L, [p0])
+    p1 = Prob(L, B, H, C1, C2, k, s, k // 2, 1, p0.y, wmat(w1), part_in=p0.part_out, slots_in=p0.slots, gamma=gamma, beta=beta)
+    launch(L, [p1])
+    y0 = p0.y.permute(0, 3, 1, 2)
+    a_ref = F.relu(F.group_norm(y0.double(), 4, gamma.double(), beta.double(), eps=1e-5))
+    assert torch.isfinite(p1.a_out).all(), case
+    assert rel_err(p1.a_out.permute(0, 3, 1, 2), a_ref) < 1e-5, case
+    rm, rv = group_stats(y0)
+    assert (p1.stats_out[..., 0].double().cpu() - rm).abs().max() < 1e-5 * rv.sqrt().max() + 1e-6
+    assert rel_err(p1.stats_out[..., 1], 1.0 / (rv + 1e-5).sqrt()) < 2e-5
+    check_output(p1, p1.a_out.permute(0, 3, 1, 2), w1, s, k // 2, case)
+
+
+@pytest.mark.parametrize('B,H,C,planes,stride', [(1, 56, 256, 128, 2), (2, 14, 1024, 512, 2), (1, 28, 512, 128, 1), (1, 7, 2048, 512, 1)])
+@pytest.mark.parametrize('mode', [2, 3])
+def test_block_output_on_load_two_problems(L, B, H, C, planes, stride, mode):
+    """conv1 (+ the down-sampling 1x1 conv, second problem of the launch) of a bottleneck: the operand is the previous block's
+    output relu(gn(y3) + shortcut), formed on load from y3 and either the materialised shortcut (mode 2) or the raw output
+    of the previous block's down-sampling convolution and ITS GroupNorm (mode 3)."""
+    g = torch.Generator().manual_seed(B + H + C + mode)
+    Cq = C // 4
+    xin = torch.randn(B, Cq, H, H, generator=g).cuda()
+    w3 = (torch.randn(C, Cq, 1, 1, generator=g) / Cq ** 0.5).cuda()
+    wd = (torch.randn(C, Cq, 1, 1, generator=g) / Cq ** 0.5).cuda()
+    ga3, be3 = (1 + 0.3 * torch.randn(C, generator=g)).cuda(), (0.2 * torch.randn(C, generator=g)).cuda()
+    gad, bed = (1 + 0.3 * torch.randn(C, generator=g)).cuda(), (0.2 * torch.randn(C, generator=g)).cuda()
+    p3 = Prob(L, B, H, Cq, C, 1, 1, 0, 0, nhwc(xin), wmat(w3))
+    pdn = Prob(L, B, H, Cq, C, 1, 1, 0, 0, nhwc(xin), wmat(wd))
+    launch(L, [p3, pdn])                                            # two problems, mode 0
+    y3, yd = p3.y.permute(0, 3, 1, 2).double(), pdn.y.permute(0, 3, 1, 2).double()
+    if mode == 2:
+        res = torch.randn(B, H, H, C, generator=g).cuda().abs()
+        block_out = F.relu(F.group_norm(y3, 4, ga3.double(), be3.double(), eps=1e-5) + res.permute(0, 3, 1, 2).double())
+        extra = dict(res=res)
+    else:
+        block_out = F.relu(F.group_norm(y3, 4, ga3.double(), be3.double(), eps=1e-5) + F.group_norm(yd, 4, gad.double(), bed.double(), eps=1e-5))
+        extra = dict(res=pdn.y, part2_in=pdn.part_out, slots2_in=pdn.slots, gamma2=gad, beta2=bed)
+    w1 = (torch.randn(planes, C, 1, 1, generator=g) / C ** 0.5).cuda()
+    wds = (torch.randn(planes * 4, C, 1, 1, generator=g) / C ** 0.5).cuda()
+    common = dict(part_in=p3.part_out, slots_in=p3.slots, gamma=ga3, beta=be3, **extra)
+    c1 = Prob(L, B, H, C, planes, 1, 1, 0, mode, p3.y, wmat(w1), **common)
+    ds = Prob(L, B, H, C, planes * 4, 1, stride, 0, mode, p3.y, wmat(wds), want_a=False, **common)
+    launch(L, [c1, ds])
+    assert rel_err(c1.a_out.permute(0, 3, 1, 2), block_out) < 1e-5
+    check_output(c1, block_out, w1, 1, 0, 'conv1')
+    check_output(ds, block_out, wds, stride, 0, 'downsample')
+    if mode == 3:
+        rm, rv = group_stats(yd)
+        assert rel_err(c1.stats2_out[..., 1], 1.0 / (rv + 1e-5).sqrt()) < 2e-5
+
+
+def test_fused_forward_fills_the_same_tape_as_the_unfused_plan(L):
+    """Whole HMR forward: fused plan (3 launches per bottleneck) against the round-1 plan (conv + GroupNorm launches);
+    outputs, all 15 features and the complete tape (y, statistics, activations: what the backward reads)."""
+    from dynaboa_b200 import hmr as hmr_mod, synthetic
+    from oracle import hmr_ref
+    m = hmr_mod.hmr(synthetic.make_mean_params()).cuda()
+    m.load_state_dict(hmr_ref.strip_prefix(synthetic.make_basemodel()['model']), strict=True)
+    m.eval()
+    lib = L.load()
+    for B in (1, 2, 9):
+        x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(B)).cuda()
+        outs = {}
+        for fused in (0, 1):
+            lib.dboa_set_fused_forward(fused)
+            try:
+                n0 = lib.dboa_launch_count()
+                outs[fused] = hmr_mod.raw_forward(m.arena, m._buffers, x)
+                torch.cuda.synchronize()
+                outs[fused] += (lib.dboa_launch_count() - n0,)
+            finally:
+                lib.dboa_set_fused_forward(1)
+        (r0, s0, c0, p0, t0, n_un), (r1, s1, c1, p1, t1, n_fu) = outs[0], outs[1]
+        print(f'B={B}: launches unfused {n_un} fused {n_fu}')
+        assert n_fu <= n_un - 50
+        assert rel_err(r1, r0) < 1e-4 and rel_err(s1, s0) < 1e-4 and rel_err(c1, c0) < 1e-4
+        f0, f1 = hmr_mod._feature_views(t0, B), hmr_mod._feature_views(t1, B)
+        for i in range(15):
+            assert rel_err(f1[i], f0[i]) < 2e-4, (B, i)
+        # the tape holds per-layer partial-statistics slots the unfused plan never writes: compare everything else through the
+        # backward, which reads y, (mean, rstd) and the activations of every layer
+        G0, G1 = torch.zeros_like(m.arena), torch.zeros_like(m.arena)
+        dr, dsh, dc = torch.randn_like(r0), torch.randn_like(s0), torch.randn_like(c0)
+        hmr_mod.raw_backward(m.arena, t0, B, False, dr, dsh, dc, G0)
+        hmr_mod.raw_backward(m.arena, t1, B, False, dr, dsh, dc, G1)
+        torch.cuda.synchronize()
+        assert ((G1 - G0).norm() / G0.norm()).item() < 2e-3, B

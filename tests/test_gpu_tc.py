@@ -16,7 +16,7 @@ def L():
     from dynaboa_b200 import _lib
     lib = _lib.load()
     yield _lib
-    lib.dboa_set_tensor_core_conv(0)
+    lib.dboa_set_tensor_core_conv(3)          # the library default: later test modules must not inherit this module's mode
 
 
 def run_tc(L, mode, M, Cin, Cout, x, w, ws):
@@ -133,4 +133,4 @@ def test_hmr_forward_with_tensor_core_convs(L, golden):
                 gflat = params[key[5:]].grad.contiguous().flatten().double().cpu()
                 assert abs(gflat.norm().item() - gd[key][0]) <= 2e-3 * gd[key][0], key
     finally:
-        L.load().dboa_set_tensor_core_conv(0)
+        L.load().dboa_set_tensor_core_conv(3)
