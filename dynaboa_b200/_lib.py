@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdynaboa_b200.so')
+LIB_PATH = os.environ.get('DBOA_LIB_PATH') or os.path.join(_HERE, 'libdynaboa_b200.so')     # the override is for A/B experiments
 
 P, I, L, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
@@ -29,7 +29,7 @@ class LossArgsStruct(C.Structure):
 class FusedConvStruct(C.Structure):
     _fields_ = ([(n, P) for n in ('x', 'res', 'w', 'a_out', 'stats_out', 'stats2_out', 'part_in', 'part2_in', 'gamma', 'beta',
                                   'gamma2', 'beta2', 'y', 'part_out')]
-                + [(n, I) for n in ('mode', 'slots_in', 'slots2_in', 'Hi', 'Cin', 'Cout', 'k', 'stride', 'pad')])
+                + [(n, I) for n in ('mode', 'Hi', 'Cin', 'Cout', 'k', 'stride', 'pad')])
 
 
 # name -> (restype, argtypes); mirrors include/dynaboa_b200.h one to one
@@ -40,8 +40,9 @@ SIGNATURES = {
     'dboa_set_tensor_core_conv': (I, [I]),
     'dboa_set_fused_forward': (I, [I]),
     'dboa_get_fused_forward': (I, []),
+    'dboa_set_forward_cta_budget': (I, [I]),
     'dboa_conv_fused_part_floats': (L, [I, I, I]),
-    'dboa_conv_fused_fwd': (I, [C.POINTER(FusedConvStruct), I, I, C.POINTER(I), P]),
+    'dboa_conv_fused_fwd': (I, [C.POINTER(FusedConvStruct), I, I, P]),
     'dboa_hmr_num_params': (I, []),
     'dboa_hmr_arena_floats': (L, []),
     'dboa_hmr_param_info': (I, [I, C.c_char_p, I, C.POINTER(L), C.POINTER(I), C.POINTER(L), C.POINTER(L)]),

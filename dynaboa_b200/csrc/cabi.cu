@@ -1,5 +1,6 @@
 // extern "C" surface of libdynaboa_b200 (see include/dynaboa_b200.h for the contract of each entry).
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -69,6 +70,7 @@ int dboa_set_tensor_core_conv(int enable) { conv_tc_set_mode(enable); return DBO
 
 int dboa_set_fused_forward(int enable) { hmr_set_fused_forward(enable != 0); return DBOA_OK; }
 int dboa_get_fused_forward(void) { return hmr_fused_forward() ? 1 : 0; }
+int dboa_set_forward_cta_budget(int n) { conv_wide_set_cta_budget(n < 0 ? 0 : n); return DBOA_OK; }
 
 int dboa_hmr_num_params(void) { return hmr_num_params(); }
 long long dboa_hmr_arena_floats(void) { return hmr_arena_floats(); }
@@ -130,11 +132,8 @@ int dboa_conv2d_tc_wgrad(const float* dy, const float* x, float* dw, int B, int 
     if (!dy || !x || !dw) return DBOA_ERR_ARG;
     return conv_tc_wgrad(dy, x, dw, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), ST(stream), cabi_pdl());
 }
-long long dboa_conv_fused_part_floats(int B, int Ho, int Cout) {
-    const long long tps = (Ho * Ho + 127) / 128, ntg = Cout / 4 >= 64 ? Cout / 4 / 64 : 1;
-    return (long long)B * 4 * tps * ntg * 16 * 4;
-}
-int dboa_conv_fused_fwd(const dboa_fused_conv* probs, int nprob, int B, int* slots_out, dboa_stream_t stream) {
+long long dboa_conv_fused_part_floats(int B, int Ho, int Cout) { (void)Ho; (void)Cout; return (long long)B * 16; }
+int dboa_conv_fused_fwd(const dboa_fused_conv* probs, int nprob, int B, dboa_stream_t stream) {
     if (!probs || nprob < 1 || nprob > 2 || B < 1) return DBOA_ERR_ARG;
     FusedConv d[2];
     for (int i = 0; i < nprob; ++i) {
@@ -144,17 +143,16 @@ int dboa_conv_fused_fwd(const dboa_fused_conv* probs, int nprob, int B, int* slo
         if (c.mode >= 2 && !c.res) return DBOA_ERR_ARG;
         if (c.mode == 3 && (!c.part2_in || !c.gamma2 || !c.beta2)) return DBOA_ERR_ARG;
         FusedConv& f = d[i];
+        memset(&f, 0, sizeof f);
         f.x = c.x; f.res = c.res; f.w = c.w; f.a_out = c.a_out; f.stats_out = c.stats_out; f.stats2_out = c.stats2_out;
         f.part_in = c.part_in; f.part2_in = c.part2_in; f.gamma = c.gamma; f.beta = c.beta; f.gamma2 = c.gamma2; f.beta2 = c.beta2;
-        f.y = c.y; f.part_out = c.part_out; f.mode = c.mode; f.S_in = c.slots_in; f.S2_in = c.slots2_in;
+        f.y = c.y; f.part_out = c.part_out; f.mode = c.mode;
         f.Hi = c.Hi; f.Cin = c.Cin; f.Cout = c.Cout; f.k = c.k; f.stride = c.stride; f.pad = c.pad;
         f.Ho = (c.Hi + 2 * c.pad - c.k) / c.stride + 1;
-        if (!conv_fused_ok(f)) return DBOA_ERR_UNSUPPORTED;
+        if (!conv_wide_ok(f)) return DBOA_ERR_UNSUPPORTED;
     }
-    const int nz = conv_fused_plan(d, nprob, B);
-    if (slots_out)
-        for (int i = 0; i < nprob; ++i) slots_out[i] = conv_fused_slots(d[i], nz);
-    return conv_fused_launch(d, nprob, B, nz, ST(stream), cabi_pdl());
+    const int nz = conv_wide_plan(d, nprob, B);
+    return conv_wide_launch(d, nprob, B, nz, nullptr, 0, ST(stream), cabi_pdl());
 }
 long long dboa_gn_partial_floats(int B, int HW, int C) { return (long long)gn_partial_floats(B, HW, C); }
 long long dboa_gn_bwd_partial_floats(int B, int HW, int C) { return (long long)gn_bwd_partial_floats(B, HW, C); }

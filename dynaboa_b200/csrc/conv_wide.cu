@@ -1,0 +1,730 @@
+// Fused forward convolution, second generation ("wide" CTA): BOTH operands arrive through TMA, and the GroupNorm / residual /
+// ReLU transform of the activation operand plus the TF32x3 hi/lo split of both operands are ONE elementwise pass over the
+// landed shared-memory tiles, spread over 16 warps.
+//
+//      y = conv( T(x), W )   and   per (sample, group) statistics of y         (interface: FusedConv, kernels.h)
+//
+// Why (measured, profiles/r02_summary.md): at batch 1 a backbone layer is a ~10 us problem and the time of a CTA is
+// the number of instructions on its critical warp times ~15 cycles (few warps, dependent chains: ncu "one instruction every
+// 13..31 cycles per warp").  The first fused kernel of this round (not kept) used the register path of conv_tc.cu for activations --
+// per k-block and thread ~300 instructions of address arithmetic, loads, transform and split -- and a per-CTA merge of
+// partial statistics; it ran SLOWER than the unfused plan.  Here:
+//   * activations: 4-D TMA boxes (32 channels x W x rows x 1 sample) with the filter tap as a coordinate offset and
+//     hardware zero fill for the padding: no address arithmetic, no bounds logic, any prefetch depth without registers;
+//   * the transform pass handles a tile with 512 threads: 2 float4 of activations + 1 float4 of weights per thread and
+//     k-block (~85 instructions), writing hi in place and lo to a second tile at the same (swizzled) offsets;
+//   * GroupNorm statistics leave the epilogue as TWO 64-bit fixed-point atomics per (tile, group) (sum, sum of squares
+//     scaled by 2^24: integer addition is associative, so the result is exact and order independent, hence deterministic);
+//     the consumer reads 8 integers instead of merging hundreds of partial triples;
+//   * output tiles are whole image rows (W x rows <= 128 pixels), so a tile is a rectangle the TMA box can address.
+// Stride-1 convolutions only (1x1, 3x3): the six stride-2 layers of the backbone run on conv_tc.cu + groupnorm.cu and hand
+// a materialised activation to the next fused layer (mode 0).
+#include <cooperative_groups.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <tuple>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace dboa {
+namespace wz {
+
+constexpr int BM = 128, BN = 64, BK = 32;
+constexpr int NTW = 16, NTT = NTW * 32;              // transform warps / threads
+constexpr int W_MMA = 16, W_TMA = 17, NT = 576;
+constexpr int DMAX = 4;                               // raw-tile ring depth
+constexpr int NACC = 4;                               // TMEM accumulators a reduction chain rotates over (see the MMA issuer)
+constexpr uint32_t A_TILE = BM * BK * 4, B_TILE = BN * BK * 4;
+constexpr int RED_LD = BN + 4;
+constexpr float GN_EPS = 1e-5f;
+constexpr double FIX = 16777216.0;                    // 2^24 fixed-point scale of the statistics accumulators
+
+struct Problem {
+    const float* res_dummy;      // unused (kept for layout clarity)
+    float* a_out;                // materialised transformed operand [B][Hi][Wi][Cin] or NULL
+    float* stats_out;            // (mean, rstd) [B][4][2] of the operand's GroupNorm or NULL
+    float* stats2_out;
+    const long long* acc_in;     // modes 1-3: fixed-point (sum, sum of squares) [B][4][2] of x
+    const long long* acc2_in;    // mode 3: of res
+    const float* gamma; const float* beta; const float* gamma2; const float* beta2;
+    float* y;                    // output [B][Ho][Wo][Cout]
+    unsigned long long* acc_out; // [B][4][2]
+    int Hi, Wi, Cin, Ho, Wo, Cout, k, pad;
+    int bh, tps, ntiles, nclusters;
+};
+struct Launch {
+    Problem p[2];
+    int nprob, nz, per, D, tabc;
+    const float* next_w;         // weights of the NEXT launch: prefetched into L2 by this one
+    unsigned long long next_bytes;
+    int launch_id;
+};
+
+// Diagnostic build (-DDBOA_TIMELINE, scripts/fused_timeline.py): %globaltimer stamps of thread 0 of the first 256 CTAs of every
+// launch at the phase boundaries, g_ftl[launch][cta][16], and per-k-block stamps of CTA 0; compiled out of the product library.
+#ifdef DBOA_TIMELINE
+__device__ unsigned long long* g_ftl = nullptr;
+#define FTL(i)                                                                                          \
+    do {                                                                                                \
+        if (threadIdx.x == 0 && g_ftl != nullptr && blockIdx.x < 256 && L.launch_id < 128) {           \
+            unsigned long long t_;                                                                      \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                      \
+            g_ftl[((size_t)L.launch_id * 256 + blockIdx.x) * 16 + (i)] = t_;                            \
+        }                                                                                               \
+    } while (0)
+#define FTI(it, j)                                                                                      \
+    do {                                                                                                \
+        if (g_ftl != nullptr && blockIdx.x == 0 && L.launch_id < 128 && (it) < 16) {                    \
+            unsigned long long t_;                                                                      \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                      \
+            g_ftl[(size_t)128 * 256 * 16 + ((size_t)L.launch_id * 16 + (it)) * 8 + (j)] = t_;           \
+        }                                                                                               \
+    } while (0)
+#else
+#define FTL(i)
+#define FTI(it, j)
+#endif
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, layout_type 2)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((1024 >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol error traps (the launch fails) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0, addr = smem_u32(bar);
+    long long t0 = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+#define PW(field) (second ? L.p[1].field : L.p[0].field)
+
+// tensor maps: tmx = operand x of problem 0 / 1, tmr = second operand (modes 2, 3), tmw = weights
+template <int MODE>
+__global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant__ Launch L, const __grid_constant__ CUtensorMap tmx0,
+                                                          const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmr,
+                                                          const __grid_constant__ CUtensorMap tmw0, const __grid_constant__ CUtensorMap tmw1) {
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nz = L.nz, D = L.D;
+    FTL(0);
+    const int cidx = blockIdx.x / nz, rank = blockIdx.x - cidx * nz;
+    const bool second = L.nprob > 1 && cidx >= L.p[0].nclusters;
+    const int tix = second ? cidx - L.p[0].nclusters : cidx;
+    const CUtensorMap* tmx = second ? &tmx1 : &tmx0;
+    const CUtensorMap* tmw = second ? &tmw1 : &tmw0;
+    const int Hi = PW(Hi), Wi = PW(Wi), Cin = PW(Cin), Ho = PW(Ho), Wo = PW(Wo), Cout = PW(Cout), ks = PW(k), pad = PW(pad);
+    const int bh = PW(bh), tps = PW(tps), ntiles = PW(ntiles);
+    const int nt = tix % ntiles, bm = tix / ntiles, mt = bm % tps, b = bm / tps;
+    const int h0 = mt * bh, n0 = nt * BN;
+    const int rows_valid = min(bh, Ho - h0) * Wo;          // output pixels of this tile (whole image rows)
+    const int m0 = h0 * Wo;                                // first output pixel of the tile inside the sample
+    const int nkb_total = (ks * ks * Cin) / BK;
+    const int kb_begin = rank * L.per;
+    const int nkb = max(0, min(L.per, nkb_total - kb_begin));
+    constexpr bool HAS_RES = MODE >= 2;
+    const uint32_t slot_bytes = A_TILE * (HAS_RES ? 2 : 1) + B_TILE;
+    const uint32_t a_bytes = (uint32_t)(bh * Wo) * 128u;   // bytes one activation box delivers
+
+    // ---- shared memory (1024-byte aligned): D raw slots {A [, R], B}, 2 lo sets {A, B}, tables, barriers
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* slots = base;
+    uint8_t* lo_a = slots + (size_t)D * slot_bytes;        // 2 x 16 KB
+    uint8_t* lo_b = lo_a + 2 * A_TILE;                     // 2 x 8 KB
+    float* tab = reinterpret_cast<float*>(lo_b + 2 * B_TILE);                 // gamma | beta [| gamma2 | beta2], tabc floats each
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tab + (MODE == 3 ? 4 : (MODE >= 1 ? 2 : 0)) * (size_t)L.tabc);
+    uint64_t* s_full = bars;               // [DMAX] TMA -> transform warps
+    uint64_t* s_empty = bars + DMAX;       // [DMAX] tcgen05.commit -> TMA warp
+    uint64_t* l_full = bars + 2 * DMAX;    // [2] transform warps -> MMA issuer
+    uint64_t* l_empty = l_full + 2;        // [2] tcgen05.commit -> transform warps
+    uint64_t* done = l_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    float4* wpart = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 128);     // [NTW][4]
+    float* sstat = reinterpret_cast<float*>(wpart + NTW * 4);                                // [16]
+    float* red = reinterpret_cast<float*>(lo_a);           // 128 x RED_LD fp32 partial tile over the lo sets after the last MMA (34 KB <= 48 KB)
+
+    if (tid == 0) {
+        for (int s = 0; s < DMAX; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&l_full[s], NTW); mbar_init(&l_empty[s], 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN * NACC) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    const int tc0 = ks == 1 ? kb_begin * BK : 0, tcn = ks == 1 ? nkb * BK : Cin;
+    if (MODE >= 1) {
+        const float* ga = PW(gamma); const float* be = PW(beta);
+        for (int i = tid; i < tcn; i += NT) { tab[i] = __ldg(ga + tc0 + i); tab[L.tabc + i] = __ldg(be + tc0 + i); }
+        if (MODE == 3) {
+            const float* ga2 = PW(gamma2); const float* be2 = PW(beta2);
+            for (int i = tid; i < tcn; i += NT) { tab[2 * L.tabc + i] = __ldg(ga2 + tc0 + i); tab[3 * L.tabc + i] = __ldg(be2 + tc0 + i); }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+    FTL(1);
+
+    // reduction cursor of k-block kb: filter tap (r, s) and channel offset
+    auto tap_of = [&](int kb, int& r, int& s, int& c) {
+        const int k0 = kb * BK, tap = k0 / Cin;
+        c = k0 - tap * Cin; r = tap / ks; s = tap - r * ks;
+    };
+
+    if (warp == W_TMA) {
+        // =====================================================================================
+        // operand feed (one thread): weight boxes before the dependency wait, activation boxes after it
+        // =====================================================================================
+        if (lane == 0 && nkb > 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmw)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmx)) : "memory");
+            const int npre = min(nkb, D);
+            for (int it = 0; it < npre; ++it) {
+                mbar_expect_tx(&s_full[it], a_bytes * (HAS_RES ? 2 : 1) + B_TILE);
+                tma_load_2d(smem_u32(slots + (size_t)it * slot_bytes + A_TILE * (HAS_RES ? 2 : 1)), tmw, (kb_begin + it) * BK, n0, &s_full[it]);
+            }
+            pdl_wait();
+            pdl_trigger();
+            for (int it = 0; it < nkb; ++it) {
+                const int sl = it % D;
+                uint8_t* slot = slots + (size_t)sl * slot_bytes;
+                if (it >= D) {
+                    mbar_wait(&s_empty[sl], (uint32_t)(((it / D) - 1) & 1));
+                    mbar_expect_tx(&s_full[sl], a_bytes * (HAS_RES ? 2 : 1) + B_TILE);
+                    tma_load_2d(smem_u32(slot + A_TILE * (HAS_RES ? 2 : 1)), tmw, (kb_begin + it) * BK, n0, &s_full[sl]);
+                }
+                int r, s, c;
+                tap_of(kb_begin + it, r, s, c);
+                tma_load_4d(smem_u32(slot), tmx, c, s - pad, h0 + r - pad, b, &s_full[sl]);
+                FTI(it, 7);
+                if (HAS_RES) tma_load_4d(smem_u32(slot + A_TILE), &tmr, c, s - pad, h0 + r - pad, b, &s_full[sl]);
+            }
+        } else {
+            // lanes 1..31: the NEXT layer's weights DRAM -> L2 while this layer computes (each CTA takes a slice; weights are
+            // never written by a convolution launch, so no dependency wait is needed)
+            if (L.next_w != nullptr && lane > 0) {
+                const unsigned long long chunk = ((L.next_bytes / gridDim.x) + 1023) & ~1023ull;
+                const unsigned long long beg = chunk * blockIdx.x;
+                for (unsigned long long o = beg + (unsigned long long)(lane - 1) * 1024; o < beg + chunk && o + 1024 <= L.next_bytes; o += 31 * 1024)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], 1024;" ::"l"(reinterpret_cast<const char*>(L.next_w) + o) : "memory");
+            }
+            pdl_wait();
+            pdl_trigger();
+        }
+    } else if (warp == W_MMA) {
+        // =====================================================================================
+        // MMA issuer: 12 x tcgen05.mma per k-block (4 k-steps of 8 x {Ah*Bh, Ah*Bl, Al*Bh}).
+        // The tensor core adds into the fp32 accumulator with truncation: a chain of n accumulations shrinks the result by
+        // ~n * 2^-25 (measured: 2e-5 after 72 k-blocks).  k-block `it` therefore goes to accumulator it % 4 (4 x 64 TMEM
+        // columns); the epilogue adds the four in fp32 with round-to-nearest.
+        // =====================================================================================
+        if (lane == 0 && nkb > 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint64_t dslot = desc_sw128(smem_u32(slots)), dloa = desc_sw128(smem_u32(lo_a)), dlob = desc_sw128(smem_u32(lo_b));
+            constexpr uint64_t KSTEP = 32 >> 4;
+#pragma unroll 1
+            for (int it = 0; it < nkb; ++it) {
+                const int sl = it % D, ls = it & 1;
+                mbar_wait(&l_full[ls], (uint32_t)((it >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                FTI(it, 5);
+                const uint64_t dah = dslot + (uint64_t)((sl * slot_bytes) >> 4);
+                const uint64_t dbh = dah + (uint64_t)((A_TILE * (HAS_RES ? 2 : 1)) >> 4);
+                const uint64_t dal = dloa + (uint64_t)((ls * A_TILE) >> 4), dbl = dlob + (uint64_t)((ls * B_TILE) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < BK / 8; ++kk) {
+                    const uint32_t dacc = tmem_d + (uint32_t)((it & (NACC - 1)) * BN);
+                    mma_tf32(dacc, dah + kk * KSTEP, dbh + kk * KSTEP, idesc, (it >= NACC || kk > 0) ? 1u : 0u);
+                    mma_tf32(dacc, dah + kk * KSTEP, dbl + kk * KSTEP, idesc, 1u);
+                    mma_tf32(dacc, dal + kk * KSTEP, dbh + kk * KSTEP, idesc, 1u);
+                }
+                umma_commit(&l_empty[ls]);
+                umma_commit(&s_empty[sl]);
+                FTI(it, 6);
+            }
+            umma_commit(done);
+        }
+        pdl_wait();
+        pdl_trigger();
+    } else {
+        // =====================================================================================
+        // transform warps: thread t owns float4 t and t + 512 of the activation tile (rows r0 = t >> 3 and r0 + 64, the same
+        // physical 16-byte chunk pc = t & 7, hence the same logical chunk lc = pc ^ (r0 & 7)) and float4 t of the weight tile
+        // =====================================================================================
+        const int r0 = tid >> 3, pc = tid & 7, lc = pc ^ (r0 & 7);
+        int oh[2], ow[2];                                   // output pixel (row inside the tile, column) of the two activation rows
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { const int i = r0 + 64 * q; oh[q] = i / Wo; ow[q] = i - oh[q] * Wo; }
+        float* ab = (MODE >= 1 && PW(a_out) != nullptr && nt == 0) ? PW(a_out) + (size_t)b * Hi * Wi * Cin : nullptr;
+        int lgw = 0;
+        while ((4 << lgw) < Cin) ++lgw;
+        pdl_wait();
+        pdl_trigger();
+        FTL(2);
+        float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f}, mean2[4] = {0.f, 0.f, 0.f, 0.f}, rstd2[4] = {1.f, 1.f, 1.f, 1.f};
+        if (MODE >= 1) {
+            // statistics of the operand's GroupNorm(s): 8 fixed-point sums per sample -> (mean, rstd)
+            if (tid < (MODE == 3 ? 8 : 4)) {
+                const long long* acc = (tid < 4 ? PW(acc_in) : PW(acc2_in)) + ((size_t)b * 4 + (tid & 3)) * 2;
+                const double N = (double)Hi * Wi * (Cin >> 2);
+                const double s1 = (double)__ldcg(acc) / FIX, s2 = (double)__ldcg(acc + 1) / FIX;
+                const double mu = s1 / N, var = fmax(s2 / N - mu * mu, 0.0);
+                sstat[(tid >> 2) * 8 + (tid & 3)] = (float)mu;
+                sstat[(tid >> 2) * 8 + 4 + (tid & 3)] = 1.0f / sqrtf((float)var + GN_EPS);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NTT) : "memory");
+#pragma unroll
+            for (int g = 0; g < 4; ++g) { mean[g] = sstat[g]; rstd[g] = sstat[4 + g]; }
+            if (MODE == 3) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) { mean2[g] = sstat[8 + g]; rstd2[g] = sstat[12 + g]; }
+            }
+            if (mt == 0 && nt == 0 && rank == 0 && tid < 8) {
+                float* so = PW(stats_out);
+                if (so != nullptr) so[(b * 4 + (tid & 3)) * 2 + (tid >> 2)] = sstat[tid];
+                if (MODE == 3) {
+                    float* so2 = PW(stats2_out);
+                    if (so2 != nullptr) so2[(b * 4 + (tid & 3)) * 2 + (tid >> 2)] = sstat[8 + tid];
+                }
+            }
+        }
+#pragma unroll 1
+        for (int it = 0; it < nkb; ++it) {
+            const int sl = it % D, ls = it & 1;
+            uint8_t* slot = slots + (size_t)sl * slot_bytes;
+            int r, s, c;
+            tap_of(kb_begin + it, r, s, c);
+            const int cch = c + lc * 4;                          // absolute input channel of this thread's chunk
+            float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f), ga2 = ga, be2 = be;
+            float mu = 0.f, rs = 1.f, mu2 = 0.f, rs2 = 1.f;
+            if (MODE >= 1) {
+                const int g = cch >> lgw, ti = cch - tc0;
+                ga = *reinterpret_cast<const float4*>(tab + ti); be = *reinterpret_cast<const float4*>(tab + L.tabc + ti);
+                mu = g == 0 ? mean[0] : (g == 1 ? mean[1] : (g == 2 ? mean[2] : mean[3]));
+                rs = g == 0 ? rstd[0] : (g == 1 ? rstd[1] : (g == 2 ? rstd[2] : rstd[3]));
+                ga.x *= rs; ga.y *= rs; ga.z *= rs; ga.w *= rs;
+                if (MODE == 3) {
+                    ga2 = *reinterpret_cast<const float4*>(tab + 2 * L.tabc + ti); be2 = *reinterpret_cast<const float4*>(tab + 3 * L.tabc + ti);
+                    mu2 = g == 0 ? mean2[0] : (g == 1 ? mean2[1] : (g == 2 ? mean2[2] : mean2[3]));
+                    rs2 = g == 0 ? rstd2[0] : (g == 1 ? rstd2[1] : (g == 2 ? rstd2[2] : rstd2[3]));
+                    ga2.x *= rs2; ga2.y *= rs2; ga2.z *= rs2; ga2.w *= rs2;
+                }
+            }
+            const bool desig = ks == 1 || (r == 1 && s == 1);   // the tap that visits every input pixel exactly once
+            if (tid == 0) FTI(it, 0);
+            mbar_wait(&s_full[sl], (uint32_t)((it / D) & 1));
+            if (tid == 0) FTI(it, 1);
+            if (it >= 2) mbar_wait(&l_empty[ls], (uint32_t)(((it >> 1) - 1) & 1));
+            if (tid == 0) FTI(it, 2);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const uint32_t off = (uint32_t)(tid + q * NTT) * 16u;
+                float4 v = *reinterpret_cast<const float4*>(slot + off);
+                if (MODE >= 1) {
+                    const int hi = h0 + oh[q] + r - pad, wi = ow[q] + s - pad;
+                    const bool inb = (r0 + 64 * q) < rows_valid && (unsigned)hi < (unsigned)Hi && (unsigned)wi < (unsigned)Wi;
+                    float4 o;
+                    o.x = (v.x - mu) * ga.x + be.x; o.y = (v.y - mu) * ga.y + be.y; o.z = (v.z - mu) * ga.z + be.z; o.w = (v.w - mu) * ga.w + be.w;
+                    if (MODE >= 2) {
+                        const float4 rr = *reinterpret_cast<const float4*>(slot + A_TILE + off);
+                        if (MODE == 2) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+                        else {
+                            o.x += (rr.x - mu2) * ga2.x + be2.x; o.y += (rr.y - mu2) * ga2.y + be2.y;
+                            o.z += (rr.z - mu2) * ga2.z + be2.z; o.w += (rr.w - mu2) * ga2.w + be2.w;
+                        }
+                    }
+                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    if (!inb) o = make_float4(0.f, 0.f, 0.f, 0.f);     // padding is zero in the ACTIVATION domain
+                    else if (ab != nullptr && desig) *reinterpret_cast<float4*>(ab + ((size_t)hi * Wi + wi) * Cin + cch) = o;
+                    v = o;
+                }
+                const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                *reinterpret_cast<float4*>(slot + off) = h;
+                *reinterpret_cast<float4*>(lo_a + ls * A_TILE + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            }
+            {
+                const uint32_t off = (uint32_t)tid * 16u;
+                uint8_t* wraw = slot + A_TILE * (HAS_RES ? 2 : 1);
+                const float4 v = *reinterpret_cast<const float4*>(wraw + off);
+                const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                *reinterpret_cast<float4*>(wraw + off) = h;
+                *reinterpret_cast<float4*>(lo_b + ls * B_TILE + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&l_full[ls]);
+            if (tid == 0) FTI(it, 3);
+            if (it == 0) FTL(3);
+        }
+    }
+    FTL(4);
+    if (nkb > 0) mbar_wait(done, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    FTL(5);
+
+    // ---- epilogue: TMEM -> shared memory (thread = row), split-K reduction over the cluster, output + statistics
+    if (warp < NTW) {
+        const int q4 = warp & 3, cgp = warp >> 2;               // lane quadrant, 16-column group
+        float facc[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) facc[q] = 0.f;
+        const int nacc = nkb < NACC ? nkb : NACC;
+#pragma unroll 1
+        for (int a = 0; a < nacc; ++a) {
+            uint32_t r[16];
+            const uint32_t taddr = tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * BN + cgp * 16);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int q = 0; q < 16; ++q) facc[q] += __uint_as_float(r[q]);
+        }
+        float* dstrow = red + (q4 * 32 + lane) * RED_LD + cgp * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(dstrow + q * 4) = make_float4(facc[q * 4], facc[q * 4 + 1], facc[q * 4 + 2], facc[q * 4 + 3]);
+    }
+    cg::cluster_group cluster = cg::this_cluster();
+    if (nz == 1) __syncthreads(); else cluster.sync();
+    FTL(6);
+
+    const int rows_per = BM / nz, items = rows_per * (BN / 4);
+    const int gw = Cout >> 2;
+    const int gpt = gw >= BN ? 1 : BN / gw;
+    const int lpg = 16 / gpt;
+    // statistics of the band: every thread turns its own (count, mean, M2) -- exact about a thread-local pivot -- into 64-bit
+    // fixed-point contributions to (sum x, sum x^2); from there on everything is integer addition (warp shuffles, shared-memory
+    // atomics, two global atomics per group and CTA): associative, so the result does not depend on any order.
+    unsigned long long* sacc = reinterpret_cast<unsigned long long*>(wpart);      // [4 groups][2] in shared memory
+    if (tid < 8) sacc[tid] = 0ull;
+    __syncthreads();
+    if (warp < NTW) {
+        float* Y = PW(y) + ((size_t)b * Ho * Wo + m0) * Cout;
+        float pv = 0.f, s1 = 0.f, s2 = 0.f;
+        int cnt = 0;
+#pragma unroll 1
+        for (int v = tid; v < items; v += NTT) {
+            const int lr = rank * rows_per + (v >> 4), c4 = (v & 15) * 4;
+            if (lr < rows_valid) {
+                float4 acc;
+                if (nz == 1) {
+                    acc = *reinterpret_cast<const float4*>(red + lr * RED_LD + c4);
+                } else {
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+                    for (int zb = 0; zb < nz; zb += 8) {
+                        float4 q[8];
+#pragma unroll
+                        for (int z = 0; z < 8; ++z)
+                            if (zb + z < nz) q[z] = *reinterpret_cast<const float4*>(cluster.map_shared_rank(red, zb + z) + lr * RED_LD + c4);
+#pragma unroll
+                        for (int z = 0; z < 8; ++z)
+                            if (zb + z < nz) { acc.x += q[z].x; acc.y += q[z].y; acc.z += q[z].z; acc.w += q[z].w; }
+                    }
+                }
+                *reinterpret_cast<float4*>(Y + (size_t)lr * Cout + n0 + c4) = acc;
+                if (cnt == 0) pv = acc.x;
+                const float d0 = acc.x - pv, d1 = acc.y - pv, d2 = acc.z - pv, d3 = acc.w - pv;
+                s1 += (d0 + d1) + (d2 + d3);
+                s2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+                cnt += 4;
+            }
+        }
+        // sum x = n p + s1;  sum x^2 = s2 + 2 p s1 + n p^2   (double: exact to 2^-24 absolute after the scaling)
+        const double dn = (double)cnt, dp = (double)pv, d1 = (double)s1;
+        long long q1 = __double2ll_rn((dn * dp + d1) * FIX), q2 = __double2ll_rn(((double)s2 + 2.0 * dp * d1 + dn * dp * dp) * FIX);
+        // lanes of one group: the 16 / gpt float4 columns of both rows a warp covers per step
+#pragma unroll 1
+        for (int o = 16; o >= 1; o >>= 1) {
+            if (o == 16 || o < lpg) { q1 += __shfl_down_sync(0xffffffffu, q1, o); q2 += __shfl_down_sync(0xffffffffu, q2, o); }
+        }
+        if (lane < 16 && (lane % lpg) == 0) {
+            atomicAdd(&sacc[(lane / lpg) * 2], (unsigned long long)q1);
+            atomicAdd(&sacc[(lane / lpg) * 2 + 1], (unsigned long long)q2);
+        }
+    }
+    __syncthreads();
+    if (tid < 2 * gpt) {
+        const int gi = tid >> 1, g = gw >= BN ? (nt * BN) / gw : nt * gpt + gi;
+        atomicAdd(PW(acc_out) + ((size_t)b * 4 + g) * 2 + (tid & 1), sacc[tid]);
+    }
+    FTL(7);
+    if (nz > 1) cluster.sync();
+    FTL(8);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN * NACC) : "memory");
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+struct alignas(64) TmHolder { CUtensorMap tm; };
+
+static const CUtensorMap* weight_map(const float* w, int K, int Cout) {
+    static std::map<std::tuple<const float*, int, int>, TmHolder*> cache;
+    auto key = std::make_tuple(w, K, Cout);
+    auto it = cache.find(key);
+    if (it != cache.end()) return &it->second->tm;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return nullptr;
+    TmHolder* h = new TmHolder;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&h->tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete h; return nullptr; }
+    cache[key] = h;
+    return &h->tm;
+}
+// activation [B][H][W][C] as a 4-D tensor (C, W, H, B); box = 32 channels x W x bh rows x 1 sample, zero fill outside
+static const CUtensorMap* act_map(const float* x, int B, int H, int W, int C, int bw, int bh) {
+    static std::map<std::tuple<const float*, int, int, int, int, int, int>, TmHolder*> cache;
+    auto key = std::make_tuple(x, B, H, W, C, bw, bh);
+    auto it = cache.find(key);
+    if (it != cache.end()) return &it->second->tm;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return nullptr;
+    if (cache.size() > 4096) { for (auto& kv : cache) delete kv.second; cache.clear(); }      // tapes come and go with the allocator
+    TmHolder* h = new TmHolder;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&h->tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete h; return nullptr; }
+    cache[key] = h;
+    return &h->tm;
+}
+
+static int num_sms() {
+    static int n = [] { int dev = 0, v = 148; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v > 0 ? v : 148; }();
+    return n;
+}
+static int rows_of(int Ho) { return Ho * Ho <= BM ? Ho : BM / Ho; }          // image rows per output tile (square images)
+
+}  // namespace wz
+
+bool conv_wide_ok(const FusedConv& d) {
+    return d.Cin % 64 == 0 && d.Cout % 64 == 0 && (d.k == 1 || d.k == 3) && d.stride == 1 && d.pad == d.k / 2 && d.mode >= 0 && d.mode <= 3 &&
+           d.Ho <= wz::BM && d.Ho == d.Hi;
+}
+
+// cluster size (K-slices): largest power of two <= 16 that keeps the launch inside one wave of one CTA per SM (thread-block
+// clusters of 4 can use 132 SMs, of 8 / 16 only 128: B300_MICROARCH.md) with at least `min_kb` k-blocks per slice
+// CTA budget of a launch (default: every SM).  Two forwards that run side by side on different streams (student / teacher,
+// output forward next to the following frame's adaptation) are given half the SMs each: a launch owns its SMs (one CTA of
+// ~150-200 KB shared memory per SM), so two full-width launches would simply alternate.
+// Measured (bench.py, C2, 1 x B200): 143.3 frames/s with all 148 SMs per launch, 151.8 with 96, 151.2 with 74, 148.1 with 64; the
+// isolated forward is also slightly faster with fewer K-slices (0.831 vs 0.855 ms).  Default 96; DBOA_FUSED_MAX_CTAS overrides.
+static int g_cta_budget = [] { const char* e = getenv("DBOA_FUSED_MAX_CTAS"); int v = e ? atoi(e) : 96; return v; }();
+void conv_wide_set_cta_budget(int n) { g_cta_budget = n; }
+int conv_wide_plan(const FusedConv* d, int nprob, int B) {
+    int tiles = 0;
+    for (int i = 0; i < nprob; ++i) tiles += B * ceil_div(d[i].Ho, wz::rows_of(d[i].Ho)) * (d[i].Cout / wz::BN);
+    const int nkb = d[0].k * d[0].k * d[0].Cin / wz::BK;
+    static const int min_kb = [] { const char* e = getenv("DBOA_FUSED_MINKB"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+    int nz = 1;
+    auto cap = [](int c) {
+        const int hw = c <= 2 ? wz::num_sms() : (c == 4 ? (wz::num_sms() * 132) / 148 : (wz::num_sms() * 128) / 148);
+        return g_cta_budget > 0 && g_cta_budget < hw ? g_cta_budget : hw;
+    };
+    while (nz < 16 && tiles * nz * 2 <= cap(nz * 2) && nkb / (nz * 2) >= min_kb) nz *= 2;
+    while (nz > 1 && (nz - 1) * ceil_div(nkb, nz) >= nkb) nz >>= 1;
+    return nz;
+}
+
+#ifdef DBOA_TIMELINE
+static int g_wide_launch_id = 0;
+extern "C" int dboa_debug_set_fused_timeline(unsigned long long* buf) {
+    g_wide_launch_id = 0;
+    return cudaMemcpyToSymbol(wz::g_ftl, &buf, sizeof(buf)) == cudaSuccess ? 0 : -3;
+}
+#endif
+
+int conv_wide_launch(const FusedConv* d, int nprob, int B, int nz, const float* next_w, size_t next_bytes, cudaStream_t st, bool pdl) {
+    if (nprob < 1 || nprob > 2 || B < 1) return DBOA_ERR_ARG;
+    wz::Launch L;
+    memset(&L, 0, sizeof L);
+    const CUtensorMap *tmx[2] = {nullptr, nullptr}, *tmw[2] = {nullptr, nullptr}, *tmr = nullptr;
+    const int K0 = d[0].k * d[0].k * d[0].Cin;
+    const int nkb = K0 / wz::BK, per = ceil_div(nkb, nz);
+    if (nz < 1 || nz > 16 || (nz & (nz - 1)) || (nz - 1) * per >= nkb) return DBOA_ERR_ARG;
+    int total = 0, tabc = 0;
+    for (int i = 0; i < nprob; ++i) {
+        const FusedConv& c = d[i];
+        if (!conv_wide_ok(c) || c.mode != d[0].mode || c.k * c.k * c.Cin != K0) return DBOA_ERR_UNSUPPORTED;
+        if (i == 1 && (c.x != d[0].x || c.res != d[0].res || c.Hi != d[0].Hi || c.Cin != d[0].Cin)) return DBOA_ERR_UNSUPPORTED;    // one `res` map
+        wz::Problem& p = L.p[i];
+        p.a_out = c.a_out; p.stats_out = c.stats_out; p.stats2_out = c.stats2_out;
+        p.acc_in = reinterpret_cast<const long long*>(c.part_in); p.acc2_in = reinterpret_cast<const long long*>(c.part2_in);
+        p.gamma = c.gamma; p.beta = c.beta; p.gamma2 = c.gamma2; p.beta2 = c.beta2;
+        p.y = c.y; p.acc_out = reinterpret_cast<unsigned long long*>(c.part_out);
+        p.Hi = c.Hi; p.Wi = c.Hi; p.Cin = c.Cin; p.Ho = c.Ho; p.Wo = c.Ho; p.Cout = c.Cout; p.k = c.k; p.pad = c.pad;
+        p.bh = wz::rows_of(c.Ho); p.tps = ceil_div(c.Ho, p.bh); p.ntiles = c.Cout / wz::BN; p.nclusters = B * p.tps * p.ntiles;
+        total += p.nclusters;
+        const int tcn = c.k == 1 ? per * wz::BK : c.Cin;
+        if (c.mode >= 1 && tcn > tabc) tabc = tcn;
+        tmw[i] = wz::weight_map(c.w, K0, c.Cout);
+        tmx[i] = wz::act_map(c.x, B, c.Hi, c.Hi, c.Cin, c.Ho, p.bh);
+        if (tmw[i] == nullptr || tmx[i] == nullptr) return DBOA_ERR_CUDA;
+    }
+    if (d[0].mode >= 2) {
+        tmr = wz::act_map(d[0].res, B, d[0].Hi, d[0].Hi, d[0].Cin, d[0].Ho, L.p[0].bh);
+        if (tmr == nullptr) return DBOA_ERR_CUDA;
+    } else {
+        tmr = tmx[0];
+    }
+    if (nprob == 1) { tmx[1] = tmx[0]; tmw[1] = tmw[0]; }
+    L.nprob = nprob; L.nz = nz; L.per = per; L.tabc = tabc;
+    L.next_w = next_w; L.next_bytes = (unsigned long long)next_bytes;
+#ifdef DBOA_TIMELINE
+    L.launch_id = g_wide_launch_id++;
+#endif
+    const int ntab = d[0].mode == 3 ? 4 : (d[0].mode >= 1 ? 2 : 0);
+    const size_t slot = (size_t)wz::A_TILE * (d[0].mode >= 2 ? 2 : 1) + wz::B_TILE;
+    const size_t fixed = 2 * (size_t)(wz::A_TILE + wz::B_TILE) + (size_t)ntab * tabc * sizeof(float) + 2048 + 1024;     // + barriers / scratch + alignment slack
+    int D = per < wz::DMAX ? per : wz::DMAX;
+    while (D > 1 && fixed + (size_t)D * slot > 227 * 1024) --D;
+    L.D = D;
+    const size_t smem = fixed + (size_t)D * slot;
+    if (smem > 227 * 1024) return DBOA_ERR_SHAPE;
+    const dim3 grid(total * nz), block(wz::NT), cl(nz, 1, 1);
+    switch (d[0].mode) {
+        case 0: return launch_ex(wz::conv_wide_kernel<0>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr, *tmw[0], *tmw[1]);
+        case 1: return launch_ex(wz::conv_wide_kernel<1>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr, *tmw[0], *tmw[1]);
+        case 2: return launch_ex(wz::conv_wide_kernel<2>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr, *tmw[0], *tmw[1]);
+        default: return launch_ex(wz::conv_wide_kernel<3>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr, *tmw[0], *tmw[1]);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// GroupNorm apply from the fixed-point statistics (+ residual, ReLU) fused with the 7x7 average pool: the last layer of the
+// backbone (reference model/hmr.py:57-60 of layer4.2, :156-157).  grid (C / 128, B), 256 threads.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gn_acc_res_avgpool_kernel(const float* __restrict__ y, const float* __restrict__ res, const long long* __restrict__ acc,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  float* __restrict__ a_out, float* __restrict__ stats_out, float* __restrict__ out, int HW,
+                                                                  int C, int ld, int ncopy, size_t copy_stride) {
+    __shared__ float4 part[8][32];
+    __shared__ float sst[8];
+    pdl_wait();
+    pdl_trigger();
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 4) {
+        const long long* a = acc + ((size_t)b * 4 + threadIdx.x) * 2;
+        const double N = (double)HW * (C >> 2);
+        const double s1 = (double)__ldcg(a) / wz::FIX, s2 = (double)__ldcg(a + 1) / wz::FIX;
+        const double mu = s1 / N, var = fmax(s2 / N - mu * mu, 0.0);
+        sst[threadIdx.x] = (float)mu;
+        sst[4 + threadIdx.x] = 1.0f / sqrtf((float)var + wz::GN_EPS);
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < 8 && stats_out != nullptr) stats_out[(b * 4 + (threadIdx.x & 3)) * 2 + (threadIdx.x >> 2)] = sst[threadIdx.x];
+    const int c = blockIdx.x * 128 + lane * 4, g = c / (C >> 2);
+    const float mu = sst[g], rs = sst[4 + g];
+    const float4 ga = ldg4(gamma + c), be = ldg4(beta + c);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = warp; p < HW; p += 8) {
+        const size_t off = ((size_t)b * HW + p) * C + c;
+        const float4 v = ldg4(y + off), r = ldg4(res + off);
+        float4 o;
+        o.x = (v.x - mu) * (rs * ga.x) + be.x; o.y = (v.y - mu) * (rs * ga.y) + be.y;
+        o.z = (v.z - mu) * (rs * ga.z) + be.z; o.w = (v.w - mu) * (rs * ga.w) + be.w;
+        o.x = fmaxf(o.x + r.x, 0.f); o.y = fmaxf(o.y + r.y, 0.f); o.z = fmaxf(o.z + r.z, 0.f); o.w = fmaxf(o.w + r.w, 0.f);
+        *reinterpret_cast<float4*>(a_out + off) = o;
+        s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    }
+    part[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0) {
+        float4 t = part[0][lane];
+        for (int w = 1; w < 8; ++w) { const float4 q = part[w][lane]; t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+        const float hw = (float)HW;
+        t.x /= hw; t.y /= hw; t.z /= hw; t.w /= hw;
+        for (int k = 0; k < ncopy; ++k) *reinterpret_cast<float4*>(out + k * copy_stride + (size_t)b * ld + c) = t;
+    }
+}
+int gn_acc_res_avgpool(const float* y, const float* res, const float* acc, const float* gamma, const float* beta, float* a_out, float* stats_out,
+                       float* out, int B, int HW, int C, int ld, int ncopy, size_t copy_stride, cudaStream_t st) {
+    if (C % 128 != 0 || ld % 4 != 0 || copy_stride % 4 != 0) return DBOA_ERR_SHAPE;
+    return launch_ex(gn_acc_res_avgpool_kernel, dim3(C / 128, B), dim3(256), 0, st, dim3(1, 1, 1), true, y, res, reinterpret_cast<const long long*>(acc), gamma,
+                     beta, a_out, stats_out, out, HW, C, ld, ncopy, copy_stride);
+}
+
+// statistics of a materialised-elsewhere tensor are not available in fixed point: (sum, sum of squares) of y [B][HW][C] per
+// (sample, group) for a layer that ran on the unfused kernels -- not needed (those layers hand over a materialised activation)
+
+}  // namespace dboa

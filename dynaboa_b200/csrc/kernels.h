@@ -30,26 +30,26 @@ void conv_tc_set_enabled(bool on);
 void conv_tc_set_mode(int mode);                      // 0 off, 1 forward, 2 forward + dgrad + wgrad, 3 forward + dgrad
 void conv_tc_set_workspace(float* ws, size_t floats);
 
-// ---- conv_fused.cu (tcgen05 TF32x3 convolution with the operand's GroupNorm applied on load, GroupNorm statistics of the
-// output in the epilogue, weights through TMA)
+// ---- description of one fused convolution (conv_wide.cu)
 struct FusedConv {
     const float *x, *res, *w;                 // operand source (see `mode`), second source (modes 2, 3), weights [Cout][k*k*Cin]
     float *a_out, *stats_out, *stats2_out;    // optional tape stores: transformed operand, (mean, rstd) [B][4][2] of the operand's GroupNorm(s)
-    const float *part_in, *part2_in;          // partial statistics (float4 slots [B][4][S]) left by the producer(s) of x / res
+    const float *part_in, *part2_in;          // statistics accumulators of x / res left by their producers
     const float *gamma, *beta, *gamma2, *beta2;
-    float *y, *part_out;                      // raw output [B][Ho][Ho][Cout] and its partial statistics [B][4][conv_fused_slots()]
+    float *y, *part_out;                      // raw output [B][Ho][Ho][Cout] and its statistics accumulators
     int mode;                                 // 0: x as is; 1: relu(gn(x)); 2: relu(gn(x) + res); 3: relu(gn(x) + gn2(res))
-    int S_in, S2_in;
+    int S_in, S2_in;                          // unused
     int Hi, Cin, Cout, k, stride, pad, Ho;    // square images
 };
-bool conv_fused_ok(const FusedConv& d);
-int conv_fused_plan(const FusedConv* d, int nprob, int B);            // K-slices (cluster size) the launch will use
-int conv_fused_slots(const FusedConv& d, int nz);                      // partial-statistics slots per (sample, group) of the output
-// one launch for 1 or 2 problems of equal mode and reduction length
-int conv_fused_launch(const FusedConv* d, int nprob, int B, int nz, cudaStream_t st, bool pdl);
-// a = relu(gn(y) + res) -> a_out, (mean, rstd) -> stats_out, mean over HW of a -> out rows (ld, ncopy copies copy_stride apart)
-int gn_res_avgpool(const float* y, const float* res, const float* part, int S, const float* gamma, const float* beta, float* a_out,
-                   float* stats_out, float* out, int B, int HW, int C, int ld, int ncopy, size_t copy_stride, cudaStream_t st);
+// ---- conv_wide.cu (fused convolution: both operands through TMA, 16 transform warps, fixed-point statistics)
+// part_in / part_out point to the fixed-point accumulators (long long [B][4][2], ZEROED by the caller
+// before the producing launch); S_in / S2_in are unused.  Stride-1 convolutions only.
+bool conv_wide_ok(const FusedConv& d);
+int conv_wide_plan(const FusedConv* d, int nprob, int B);
+void conv_wide_set_cta_budget(int n);                                  // 0: all SMs
+int conv_wide_launch(const FusedConv* d, int nprob, int B, int nz, const float* next_w, size_t next_bytes, cudaStream_t st, bool pdl);
+int gn_acc_res_avgpool(const float* y, const float* res, const float* acc, const float* gamma, const float* beta, float* a_out, float* stats_out,
+                       float* out, int B, int HW, int C, int ld, int ncopy, size_t copy_stride, cudaStream_t st);
 
 // ---- groupnorm.cu (single-launch cluster kernels)
 size_t gn_partial_floats(int B, int HW, int C);     // forward scratch (none; kept for the C ABI)

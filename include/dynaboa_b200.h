@@ -39,6 +39,9 @@ int dboa_set_tensor_core_conv(int mode);
  * GroupNorm launch per layer (round-1 plan, kept as the A/B reference).  Both fill the same tape. */
 int dboa_set_fused_forward(int enable);
 int dboa_get_fused_forward(void);
+/* CTAs (= SMs) the fused convolutions of the following dboa_hmr_forward calls may use; 0 = all.  Forwards issued side by side
+ * on different streams share the device when each is given about half of it (a fused launch owns its SMs). */
+int dboa_set_forward_cta_budget(int n);
 
 /* ---- HMR regressor: parameter arena and tape layout ----------------------------------------
  * replaces: model/hmr.py:67-124 (HMR.__init__/_make_layer state_dict contract).
@@ -88,24 +91,26 @@ int dboa_conv2d_tc_dgrad(const float* dy, const float* w, float* dx, int B, int 
                          int Kpitch, int accumulate, dboa_stream_t stream);
 int dboa_conv2d_tc_wgrad(const float* dy, const float* x, float* dw, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
                          int Kpitch, dboa_stream_t stream);
-/* Fused tcgen05 convolution, the unit the forward plan is made of (csrc/conv_fused.cu).
+/* Fused tcgen05 convolution, the unit the forward plan is made of (csrc/conv_wide.cu).
  * replaces: nn.Conv2d + the nn.GroupNorm(4, C) / ReLU / residual add that PRECEDES it in Bottleneck.forward
  * (model/hmr.py:40-60), + the statistics pass of the GroupNorm that follows it.
- *   y = conv(T(x), w);  part_out <- per-tile (count, mean, M2) of y per (sample, group)  [float4 slots, B x 4 x slots]
+ *   y = conv(T(x), w);  part_out[b][g] += (sum y, sum y^2) of group g of sample b, as 64-bit fixed point (scale 2^24):
+ *   integer atomics, exact and order independent.  part_out (long long [B][4][2]) must be ZERO before the launch.
  *   mode 0: T(x) = x;  1: relu(gn(x));  2: relu(gn(x) + res);  3: relu(gn(x) + gn2(res))
- * gn statistics come from `part_in` (`slots_in` slots per (sample, group), as a previous call reported through slots_out).
+ * gn statistics come from `part_in` (`part2_in`): the accumulators a previous call filled for x (res).
  * a_out / stats_out / stats2_out (optional): T(x) materialised, (mean, rstd) [B][4][2] of the GroupNorm(s).
- * Up to 2 problems of equal mode and reduction length k*k*Cin share one launch.  Cin % 64 == 0, Cout % 64 == 0, k in {1, 3}. */
+ * Up to 2 problems of equal mode, operand and reduction length share one launch.
+ * Cin % 64 == 0, Cout % 64 == 0, k in {1, 3}, stride 1, pad k/2, H <= 128 (DBOA_ERR_UNSUPPORTED otherwise). */
 typedef struct dboa_fused_conv {
     const float *x, *res, *w;
     float *a_out, *stats_out, *stats2_out;
     const float *part_in, *part2_in, *gamma, *beta, *gamma2, *beta2;
     float *y, *part_out;
-    int mode, slots_in, slots2_in;
+    int mode;
     int Hi, Cin, Cout, k, stride, pad;
 } dboa_fused_conv;
-long long dboa_conv_fused_part_floats(int B, int Ho, int Cout);   /* capacity of part_out in floats */
-int dboa_conv_fused_fwd(const dboa_fused_conv* probs, int nprob, int B, int* slots_out, dboa_stream_t stream);
+long long dboa_conv_fused_part_floats(int B, int Ho, int Cout);   /* size of part_out in floats (= B * 16) */
+int dboa_conv_fused_fwd(const dboa_fused_conv* probs, int nprob, int B, dboa_stream_t stream);
 
 /* replaces: nn.GroupNorm(4, C) + ReLU (+ residual) forward / backward (model/hmr.py:14-18,40-60).
  * C / 16 must be a power of two; one launch each (thread-block clusters).  `partial` is caller-provided scratch of

@@ -1,6 +1,7 @@
-"""Fused tcgen05 convolution (csrc/conv_fused.cu): GroupNorm of the operand applied on load, GroupNorm statistics of the
-output from the epilogue, weights through TMA.  Checked against torch (fp64 convolution, F.group_norm) on the device,
-one problem and two problems per launch, every transform mode, and end to end against the unfused plan."""
+"""Fused tcgen05 convolution (csrc/conv_wide.cu): both operands through TMA, GroupNorm of the operand applied on load,
+GroupNorm statistics of the output as fixed-point sums from the epilogue.  Checked against torch (fp64 convolution,
+F.group_norm) on the device, one problem and two problems per launch, every transform mode, and end to end against the
+unfused plan."""
 import ctypes as C
 
 import pytest
@@ -27,14 +28,12 @@ def wmat(w):
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
 
 
-def merged_stats(part, B, slots):
-    """(count, mean, M2) slots [B][4][slots] -> mean, biased variance per (b, g) in fp64 (Chan merge on the host)."""
-    p = part.view(-1, 4)[:B * 4 * slots].view(B, 4, slots, 4).double().cpu()
-    n, m, M2 = p[..., 0], p[..., 1], p[..., 2]
-    N = n.sum(-1)
-    mean = (n * m).sum(-1) / N
-    var = (M2 + n * (m - mean[..., None]) ** 2).sum(-1) / N
-    return N, mean, var
+def merged_stats(part, B, n_per_group):
+    """fixed-point (sum, sum of squares) accumulators, long long [B][4][2], scale 2^24 -> mean, biased variance (fp64)."""
+    acc = part.view(torch.int64)[:B * 8].view(B, 4, 2).double().cpu() / 2.0 ** 24
+    mean = acc[..., 0] / n_per_group
+    var = acc[..., 1] / n_per_group - mean ** 2
+    return mean, var
 
 
 def group_stats(y_nchw):
@@ -46,8 +45,8 @@ def group_stats(y_nchw):
 class Prob:
     """One problem of a fused launch: keeps every tensor alive and builds the C struct."""
 
-    def __init__(self, L, B, Hi, Cin, Cout, k, stride, pad, mode, x, w, res=None, part_in=None, slots_in=0, gamma=None, beta=None,
-                 part2_in=None, slots2_in=0, gamma2=None, beta2=None, want_a=True):
+    def __init__(self, L, B, Hi, Cin, Cout, k, stride, pad, mode, x, w, res=None, part_in=None, gamma=None, beta=None,
+                 part2_in=None, gamma2=None, beta2=None, want_a=True):
         self.L, self.B, self.mode = L, B, mode
         self.Ho = (Hi + 2 * pad - k) // stride + 1
         dev = 'cuda'
@@ -63,37 +62,33 @@ class Prob:
                         ('part_in', part_in), ('part2_in', part2_in), ('gamma', gamma), ('beta', beta), ('gamma2', gamma2), ('beta2', beta2),
                         ('y', self.y), ('part_out', self.part_out)):
             setattr(s, name, None if t is None else t.data_ptr())
-        s.mode, s.slots_in, s.slots2_in = mode, slots_in, slots2_in
+        s.mode = mode
         s.Hi, s.Cin, s.Cout, s.k, s.stride, s.pad = Hi, Cin, Cout, k, stride, pad
         self.struct = s
-        self.slots = None
 
 
 def launch(L, probs):
     B = probs[0].B
     arr = (L.FusedConvStruct * len(probs))(*[p.struct for p in probs])
-    slots = (C.c_int * 2)()
-    L.call('dboa_conv_fused_fwd', arr, len(probs), B, slots, L.stream())
+    L.call('dboa_conv_fused_fwd', arr, len(probs), B, L.stream())
     torch.cuda.synchronize()
-    for i, p in enumerate(probs):
-        p.slots = slots[i]
 
 
 def check_output(p, a_nchw, w_nchw, stride, pad, tag):
     ref = F.conv2d(a_nchw.double(), w_nchw.double(), stride=stride, padding=pad)
     assert torch.isfinite(p.y).all(), tag
-    assert rel_err(p.y.permute(0, 3, 1, 2), ref) < 5e-6, tag
-    N, mean, var = merged_stats(p.part_out, p.B, p.slots)
+    # TF32x3 with fp32 accumulation in the tensor core: ~1e-6 for short reductions, up to ~2e-5 for K = 4608 in one chain
+    assert rel_err(p.y.permute(0, 3, 1, 2), ref) < 3e-5, tag
+    mean, var = merged_stats(p.part_out, p.B, ref[0].numel() / 4)
     rm, rv = group_stats(ref)
-    assert torch.equal(N, torch.full_like(N, ref[0].numel() / 4)), tag
     assert (mean - rm).abs().max() <= 1e-5 * rv.sqrt().max() + 1e-6, tag
-    assert ((var - rv).abs() / rv).max() < 2e-5, tag
+    assert ((var - rv).abs() / rv).max() < 3e-5, tag
 
 
-CASES = [  # B, H, Cin, Cout, k, stride, pad
-    (1, 56, 64, 64, 1, 1, 0), (1, 56, 64, 256, 1, 1, 0), (1, 56, 64, 64, 3, 1, 1), (2, 28, 128, 128, 3, 2, 1), (1, 28, 512, 128, 1, 1, 0),
-    (1, 14, 256, 256, 3, 1, 1), (3, 14, 1024, 256, 1, 1, 0), (1, 14, 512, 512, 3, 2, 1), (1, 7, 512, 2048, 1, 1, 0), (2, 7, 2048, 512, 1, 1, 0),
-    (1, 7, 512, 512, 3, 1, 1), (9, 7, 512, 512, 3, 1, 1), (1, 28, 512, 1024, 1, 2, 0)]
+CASES = [  # B, H, Cin, Cout, k, stride, pad   (stride 1 only: the stride-2 layers stay on the unfused kernels)
+    (1, 56, 64, 64, 1, 1, 0), (1, 56, 64, 256, 1, 1, 0), (1, 56, 64, 64, 3, 1, 1), (2, 28, 128, 128, 3, 1, 1), (1, 28, 512, 128, 1, 1, 0),
+    (1, 14, 256, 256, 3, 1, 1), (3, 14, 1024, 256, 1, 1, 0), (1, 7, 512, 2048, 1, 1, 0), (2, 7, 2048, 512, 1, 1, 0),
+    (1, 7, 512, 512, 3, 1, 1), (9, 7, 512, 512, 3, 1, 1), (2, 28, 128, 512, 1, 1, 0)]
 
 
 @pytest.mark.parametrize('case', CASES)
@@ -109,8 +104,8 @@ def test_plain_operand_and_statistics(L, case):
 
 
 CHAINS = [  # B, H, C0 (input of the producer), C1 (its output = operand channels), C2, k, stride of the consumer
-    (1, 56, 64, 64, 64, 3, 1), (2, 56, 64, 128, 128, 3, 2), (1, 28, 128, 128, 512, 1, 1), (2, 14, 256, 256, 256, 3, 1), (1, 14, 256, 1024, 256, 1, 1),
-    (1, 14, 128, 512, 512, 3, 2), (3, 7, 512, 512, 2048, 1, 1), (1, 7, 512, 2048, 512, 1, 1)]
+    (1, 56, 64, 64, 64, 3, 1), (2, 56, 64, 128, 128, 1, 1), (1, 28, 128, 128, 512, 1, 1), (2, 14, 256, 256, 256, 3, 1), (1, 14, 256, 1024, 256, 1, 1),
+    (1, 28, 128, 128, 128, 3, 1), (3, 7, 512, 512, 2048, 1, 1), (1, 7, 512, 2048, 512, 1, 1), (2, 7, 256, 512, 512, 3, 1)]
 
 
 @pytest.mark.parametrize('case', CHAINS)
@@ -126,7 +121,7 @@ def test_groupnorm_on_load(L, case):
     w1 = (torch.randn(C2, C1, k, k, generator=g) / (k * k * C1) ** 0.5).cuda()
     p0 = Prob(L, B, H, C0, C1, 1, 1, 0, 0, nhwc(x), wmat(w0))
     launch(L, [p0])
-    p1 = Prob(L, B, H, C1, C2, k, s, k // 2, 1, p0.y, wmat(w1), part_in=p0.part_out, slots_in=p0.slots, gamma=gamma, beta=beta)
+    p1 = Prob(L, B, H, C1, C2, k, s, k // 2, 1, p0.y, wmat(w1), part_in=p0.part_out, gamma=gamma, beta=beta)
     launch(L, [p1])
     y0 = p0.y.permute(0, 3, 1, 2)
     a_ref = F.relu(F.group_norm(y0.double(), 4, gamma.double(), beta.double(), eps=1e-5))
@@ -138,7 +133,7 @@ def test_groupnorm_on_load(L, case):
     check_output(p1, p1.a_out.permute(0, 3, 1, 2), w1, s, k // 2, case)
 
 
-@pytest.mark.parametrize('B,H,C,planes,stride', [(1, 56, 256, 128, 2), (2, 14, 1024, 512, 2), (1, 28, 512, 128, 1), (1, 7, 2048, 512, 1)])
+@pytest.mark.parametrize('B,H,C,planes,stride', [(1, 56, 256, 64, 1), (2, 14, 1024, 256, 1), (1, 28, 512, 128, 1), (1, 7, 2048, 512, 1)])
 @pytest.mark.parametrize('mode', [2, 3])
 def test_block_output_on_load_two_problems(L, B, H, C, planes, stride, mode):
     """conv1 (+ the down-sampling 1x1 conv, second problem of the launch) of a bottleneck: the operand is the previous block's
@@ -151,8 +146,9 @@ def test_block_output_on_load_two_problems(L, B, H, C, planes, stride, mode):
     wd = (torch.randn(C, Cq, 1, 1, generator=g) / Cq ** 0.5).cuda()
     ga3, be3 = (1 + 0.3 * torch.randn(C, generator=g)).cuda(), (0.2 * torch.randn(C, generator=g)).cuda()
     gad, bed = (1 + 0.3 * torch.randn(C, generator=g)).cuda(), (0.2 * torch.randn(C, generator=g)).cuda()
-    p3 = Prob(L, B, H, Cq, C, 1, 1, 0, 0, nhwc(xin), wmat(w3))
-    pdn = Prob(L, B, H, Cq, C, 1, 1, 0, 0, nhwc(xin), wmat(wd))
+    xin_d = nhwc(xin)                                               # both problems of a launch read the SAME operand tensor
+    p3 = Prob(L, B, H, Cq, C, 1, 1, 0, 0, xin_d, wmat(w3))
+    pdn = Prob(L, B, H, Cq, C, 1, 1, 0, 0, xin_d, wmat(wd))
     launch(L, [p3, pdn])                                            # two problems, mode 0
     y3, yd = p3.y.permute(0, 3, 1, 2).double(), pdn.y.permute(0, 3, 1, 2).double()
     if mode == 2:
@@ -161,10 +157,10 @@ def test_block_output_on_load_two_problems(L, B, H, C, planes, stride, mode):
         extra = dict(res=res)
     else:
         block_out = F.relu(F.group_norm(y3, 4, ga3.double(), be3.double(), eps=1e-5) + F.group_norm(yd, 4, gad.double(), bed.double(), eps=1e-5))
-        extra = dict(res=pdn.y, part2_in=pdn.part_out, slots2_in=pdn.slots, gamma2=gad, beta2=bed)
+        extra = dict(res=pdn.y, part2_in=pdn.part_out, gamma2=gad, beta2=bed)
     w1 = (torch.randn(planes, C, 1, 1, generator=g) / C ** 0.5).cuda()
     wds = (torch.randn(planes * 4, C, 1, 1, generator=g) / C ** 0.5).cuda()
-    common = dict(part_in=p3.part_out, slots_in=p3.slots, gamma=ga3, beta=be3, **extra)
+    common = dict(part_in=p3.part_out, gamma=ga3, beta=be3, **extra)
     c1 = Prob(L, B, H, C, planes, 1, 1, 0, mode, p3.y, wmat(w1), **common)
     ds = Prob(L, B, H, C, planes * 4, 1, stride, 0, mode, p3.y, wmat(wds), want_a=False, **common)
     launch(L, [c1, ds])
@@ -199,7 +195,7 @@ def test_fused_forward_fills_the_same_tape_as_the_unfused_plan(L):
                 lib.dboa_set_fused_forward(1)
         (r0, s0, c0, p0, t0, n_un), (r1, s1, c1, p1, t1, n_fu) = outs[0], outs[1]
         print(f'B={B}: launches unfused {n_un} fused {n_fu}')
-        assert n_fu <= n_un - 50
+        assert n_fu <= n_un - 40
         assert rel_err(r1, r0) < 1e-4 and rel_err(s1, s0) < 1e-4 and rel_err(c1, c0) < 1e-4
         f0, f1 = hmr_mod._feature_views(t0, B), hmr_mod._feature_views(t1, B)
         for i in range(15):
