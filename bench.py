@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the DynaBOA per-frame hot path: adapted frames/sec on the synthetic 3DPW-shape stream.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c5]
 
 One "step" = one adapted frame at BASELINE.json configs[1] (C2: 1 inner step, batch 1; S-adapt scope of
 SURVEY.md §8d: adaptation + one output forward/SMPL).  Prints ONE JSON line (see DESIGN.md "Measurement").
@@ -28,6 +28,10 @@ METRIC = 'adapted frames/sec (224x224, 1 inner step)'
 WORKLOADS = {
     'c2': dict(inner_step=1, retrieval=0, lower_level_mixtrain=0, upper_level_mixtrain=0, dynamic_boa=0, sample_num=1),
     'c3': dict(inner_step=3, retrieval=1, lower_level_mixtrain=1, upper_level_mixtrain=1, dynamic_boa=0, sample_num=8),
+    # BASELINE.json configs[4]: C3 + the dynamic re-adaptation loop at the reference's threshold (dynaboa_benchmark.py:48-49); the
+    # trip count is data dependent; under torchrun the (a.b, |a|^2, |b|^2) sums are all-reduced so that every rank takes the same one
+    'c5': dict(inner_step=3, retrieval=1, lower_level_mixtrain=1, upper_level_mixtrain=1, dynamic_boa=1, sample_num=8,
+               cos_sim_threshold=3.1e-4, optim_steps=7),
 }
 N_EXEMPLARS = 256        # synthetic exemplar bank of the retrieval workloads: 10 clusters of ~25 items >= sample_num
 W_MB = 107.91            # fp32 parameters
@@ -220,12 +224,14 @@ def run_ours(args, rank, world, local):
     # more, so that NCCL's channels and both ranks' allocators are in steady state before the W warm-up steps
     PRELUDE = 7 if world == 1 else 15
     n_frames = PRELUDE + args.steps + args.warmup
-    opts = default_options(expdir=work, expname='bench', model_file=config.BASE_MODEL, synthetic_frames=n_frames, rank=rank,
-                           **WORKLOADS[args.workload])
+    flags = dict(WORKLOADS[args.workload])
+    if args.cos_threshold is not None:
+        flags['cos_sim_threshold'] = args.cos_threshold
+    opts = default_options(expdir=work, expname='bench', model_file=config.BASE_MODEL, synthetic_frames=n_frames, rank=rank, **flags)
     ad = Adaptor(opts)
     ad.fused_eval = 'none'
     if world > 1:
-        ad.optimizer.pre_step_hook = ddist.make_grad_sync(world)
+        ddist.attach(ad, world)        # bucketed all-reduce under the upper-level backward, 1/world folded into Adam
     stream = synthetic.SyntheticStream(length=n_frames, batch_size=1, rank=rank)
     keys = ('image', 'smpl_j2d')
     host = [{k: stream[t][k].pin_memory() for k in keys} for t in range(n_frames)]
@@ -332,7 +338,7 @@ def run_ours(args, rank, world, local):
         fwd_ms = tot / reps
         fwd_launches = (lib.dboa_launch_count() - l0) // reps
         achieved = FWD_MB(1) / 1e3 / (fwd_ms / 1e3)
-        roof = {'bound': 'hbm', 'kernel': f'dboa_hmr_forward b=1 ({fwd_launches} launches: 53 conv + 53 GroupNorm + head)',
+        roof = {'bound': 'hbm', 'kernel': f'dboa_hmr_forward b=1 ({fwd_launches} launches: fused plan -- stride-1 convs apply the GroupNorm of their operand on load)',
                 'achieved': achieved, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': forward_traffic_mb(), 'traffic_unit': 'MB per forward (dram__bytes_read.sum + dram__bytes_write.sum, ncu capture '
                 'profiles/r01b_forward_traffic.json)', 'algorithmic_MB_per_launch': FWD_MB(1), 'ms_per_launch': fwd_ms,
@@ -346,11 +352,15 @@ def run_ours(args, rank, world, local):
                 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
                 'data': 'synthetic',
                 'config': {'workload': f'{args.workload}: 3DPW-shape synthetic stream, batch 1 per GPU, S-adapt scope '
-                                       '(adaptation + one output forward/SMPL)', 'flags': WORKLOADS[args.workload],
+                                       '(adaptation + one output forward/SMPL)', 'flags': flags,
                            'output': 'serial' if args.serial_output else 'output forward + SMPL of frame t on a side stream, overlapped with '
                            'the adaptation of frame t+1 (same weights; the optimiser step waits for the read); --serial-output disables',
-                           'parallelism': f'dp{world}: frames sharded over ranks, 1 all-reduce of the 107.9 MB outer gradient per step'
+                           'parallelism': f'dp{world}: frames sharded over ranks, the 107.9 MB outer gradient all-reduced in 3 buckets '
+                           'under the upper-level backward (NCCL on a communication stream), 1/world folded into Adam'
                            if world > 1 else 'single GPU',
+                           'dynamic_steps': (list(ad.optim_step_record[-args.steps:]) if WORKLOADS[args.workload]['dynamic_boa'] else None),
+                           'one_minus_cos12_first_test': ([round(1.0 - v[0][12]['cos'], 7) for _, v in sorted(ad.feat_sims.items())][-args.steps:]
+                                                          if WORKLOADS[args.workload]['dynamic_boa'] else None),
                            'l2': 'per-step working set (theta, fast weights, Adam m/v, teacher, gradient arena: 6 x 108 MB + '
                                  'activations) exceeds the 126 MB L2; the isolated forward timing flushes L2 with a 256 MB memset'},
                 'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -367,6 +377,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--cpu-frames', type=int, default=8)
+    ap.add_argument('--cos-threshold', type=float, default=None,
+                    help='override cos_sim_threshold of a dynamic_boa workload (the reference default 3.1e-4 never fires on the synthetic stream)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--serial-output', action='store_true',
                     help='run the output forward on the adaptation stream (no overlap with the next frame)')

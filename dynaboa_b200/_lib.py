@@ -82,6 +82,11 @@ SIGNATURES = {
     'dboa_sgd_update': (I, [P, P, P, F, L, P]),
     'dboa_adam_ema': (I, [P, P, P, P, P, L, F, F, F, F, I, F, P]),
     'dboa_ema_update': (I, [P, P, L, F, P]),
+    'dboa_adam_ema_scaled': (I, [P, P, P, P, P, L, F, F, F, F, I, F, F, P]),
+    'dboa_fill_zero': (I, [P, L, P]),
+    'dboa_copy_async': (I, [P, P, L, P]),
+    'dboa_hmr_backward_buckets': (I, [P, P, P]),
+    'dboa_hmr_bucket_offset': (L, [I]),
     'dboa_cosine_pairs': (I, [C.POINTER(P), C.POINTER(P), C.POINTER(L), I, P, L, P, F, P]),
     'dboa_cosine_partial_floats': (L, [C.POINTER(L), I]),
     'dboa_cosine_terms': (I, [C.POINTER(P), C.POINTER(P), C.POINTER(L), I, P, L, P, P]),

@@ -15,6 +15,8 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
                 cudaStream_t st);
 int hmr_backward(const float* P, const float* T, int B, int masked, const float* d_rotmat, const float* d_shape, const float* d_cam,
                  float* G, float* scratch, cudaStream_t st);
+void hmr_arm_bucket_events(cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2);
+long long hmr_bucket_offset(int k);
 void hmr_set_fused_forward(bool on);
 bool hmr_fused_forward();
 int hmr_num_params();
@@ -250,8 +252,27 @@ int dboa_sgd_update(const float* p, const float* g, float* out, float lr, long l
 int dboa_adam_ema(float* p, const float* g, float* m, float* v, float* teacher, long long n, float lr, float beta1, float beta2, float eps,
                   int step, float alpha, dboa_stream_t stream) {
     if (!p || !g || !m || !v || n < 0) return DBOA_ERR_ARG;
-    return adam_ema(p, g, m, v, teacher, (size_t)n, lr, beta1, beta2, eps, step, alpha, ST(stream));
+    return adam_ema(p, g, m, v, teacher, (size_t)n, lr, beta1, beta2, eps, step, alpha, 1.0f, ST(stream));
 }
+int dboa_adam_ema_scaled(float* p, const float* g, float* m, float* v, float* teacher, long long n, float lr, float beta1, float beta2, float eps,
+                         int step, float alpha, float gscale, dboa_stream_t stream) {
+    if (!p || !g || !m || !v || n < 0) return DBOA_ERR_ARG;
+    return adam_ema(p, g, m, v, teacher, (size_t)n, lr, beta1, beta2, eps, step, alpha, gscale, ST(stream));
+}
+int dboa_fill_zero(void* dst, long long bytes, dboa_stream_t stream) {
+    if (!dst || bytes < 0) return DBOA_ERR_ARG;
+    return cudaMemsetAsync(dst, 0, (size_t)bytes, ST(stream)) == cudaSuccess ? DBOA_OK : DBOA_ERR_CUDA;
+}
+int dboa_copy_async(void* dst, const void* src, long long bytes, dboa_stream_t stream) {
+    if (!dst || !src || bytes < 0) return DBOA_ERR_ARG;
+    return cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, ST(stream)) == cudaSuccess ? DBOA_OK : DBOA_ERR_CUDA;
+}
+int dboa_hmr_backward_buckets(void* ev0, void* ev1, void* ev2) {
+    if (!ev0 || !ev1 || !ev2) return DBOA_ERR_ARG;
+    hmr_arm_bucket_events(reinterpret_cast<cudaEvent_t>(ev0), reinterpret_cast<cudaEvent_t>(ev1), reinterpret_cast<cudaEvent_t>(ev2));
+    return DBOA_OK;
+}
+long long dboa_hmr_bucket_offset(int k) { return hmr_bucket_offset(k); }
 int dboa_ema_update(float* teacher, const float* p, long long n, float alpha, dboa_stream_t stream) {
     if (!teacher || !p || n < 0) return DBOA_ERR_ARG;
     return ema_update(teacher, p, (size_t)n, alpha, ST(stream));

@@ -597,9 +597,12 @@ int conv_wide_plan(const FusedConv* d, int nprob, int B) {
     const int nkb = d[0].k * d[0].k * d[0].Cin / wz::BK;
     static const int min_kb = [] { const char* e = getenv("DBOA_FUSED_MINKB"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
     int nz = 1;
-    auto cap = [](int c) {
+    // the budget limits how far a launch with FEW tiles is split; a launch whose tiles alone exceed it (large batches) may still
+    // split up to the hardware wave, which halves its accumulation chains
+    auto cap = [tiles](int c) {
         const int hw = c <= 2 ? wz::num_sms() : (c == 4 ? (wz::num_sms() * 132) / 148 : (wz::num_sms() * 128) / 148);
-        return g_cta_budget > 0 && g_cta_budget < hw ? g_cta_budget : hw;
+        const int soft = g_cta_budget > 2 * tiles ? g_cta_budget : 2 * tiles;
+        return g_cta_budget > 0 && soft < hw ? soft : hw;
     };
     while (nz < 16 && tiles * nz * 2 <= cap(nz * 2) && nkb / (nz * 2) >= min_kb) nz *= 2;
     while (nz > 1 && (nz - 1) * ceil_div(nkb, nz) >= nkb) nz >>= 1;

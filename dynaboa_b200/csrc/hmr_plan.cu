@@ -220,6 +220,27 @@ struct BwdAsync {
     }
 };
 static BwdAsync g_async;
+
+// Gradient buckets for the data-parallel all-reduce ("bucketed in reverse layer order and overlapped with
+// backward").  The backward produces gradients head -> layer4 -> ... -> stem; the arena is laid out stem, layer1..4, head.
+// Bucket 0 = [layer4 .. end), 1 = [layer3, layer4), 2 = [0, layer3).  When a caller hands over three events, event k is
+// recorded once every kernel that writes bucket k (main chain, weight-gradient side streams, GroupNorm finish) has been
+// enqueued and ordered before it; the caller's communication stream waits on it and all-reduces that span while the rest of
+// the backward is still running.
+struct BucketReq { cudaEvent_t ev[3]; bool armed; };
+static BucketReq g_bucket_req = {{nullptr, nullptr, nullptr}, false};
+static cudaStream_t g_join_stream = nullptr;
+static cudaEvent_t g_join_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+void hmr_arm_bucket_events(cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2) { g_bucket_req.ev[0] = e0; g_bucket_req.ev[1] = e1; g_bucket_req.ev[2] = e2; g_bucket_req.armed = true; }
+long long hmr_bucket_offset(int k) {        // first float of bucket k's span; bucket k = [offset(k), offset(k - 1)) with offset(-1) = arena size
+    const Net& n = net();
+    if (k <= -1) return n.arena_floats;
+    if (k >= 2) return 0;
+    const char* first = k == 0 ? "layer4.0.conv1" : "layer3.0.conv1";
+    for (const ConvLayer& c : n.convs)
+        if (c.wname == first) return c.w_off;
+    return 0;
+}
 // DBOA_ASYNC_WGRAD=0 in the environment keeps everything on the caller's stream (A/B measurements, debugging)
 static bool g_async_enabled = [] { const char* e = getenv("DBOA_ASYNC_WGRAD"); return !(e && e[0] == '0'); }();
 void hmr_set_async_wgrad(bool on) { g_async_enabled = on; }
@@ -518,6 +539,13 @@ int hmr_backward(const float* P, const float* T, int B, int masked_in, const flo
     const Tape& t = tape_for(B);
     Scratch sc(scratch, B);
     const bool masked = masked_in != 0;     // the forward ran with dropout keep-masks (saved in the tape)
+    BucketReq breq = g_bucket_req;
+    g_bucket_req.armed = false;
+    if (breq.armed) {
+        if (g_join_stream == nullptr && cudaStreamCreateWithFlags(&g_join_stream, cudaStreamNonBlocking) != cudaSuccess) return DBOA_ERR_CUDA;
+        for (int i = 0; i < 4; ++i)
+            if (g_join_ev[i] == nullptr && cudaEventCreateWithFlags(&g_join_ev[i], cudaEventDisableTiming) != cudaSuccess) return DBOA_ERR_CUDA;
+    }
 
     // ---- head
     const float* p3 = T + t.params + 3ULL * B * DEC_LD;
@@ -583,9 +611,31 @@ int hmr_backward(const float* P, const float* T, int B, int masked_in, const flo
         A.pending[k] = true;
         return s_;
     };
+    // gradients of convs [first_conv, ...) are complete (B > 1: their GroupNorm affine rows get summed here, not at the very end)
+    int finished_from = (int)n.convs.size();
+    auto bucket_done = [&](int k, int first_conv) {
+        if (B > 1 && first_conv < finished_from) {
+            const GnItems& gi = gn_items();
+            if (gi.dev == nullptr) return DBOA_ERR_CUDA;
+            DBOA_TRY(gn_param_finish(gi.dev + first_conv, finished_from - first_conv, sc.gnp, G, B, st));
+            finished_from = first_conv;
+        }
+        if (!breq.armed) return DBOA_OK;
+        cudaEventRecord(g_join_ev[0], st);
+        cudaStreamWaitEvent(g_join_stream, g_join_ev[0], 0);
+        if (async)
+            for (int i = 0; i < BwdAsync::NSIDE; ++i) {
+                cudaEventRecord(g_join_ev[1 + i], A.side[i]);
+                cudaStreamWaitEvent(g_join_stream, g_join_ev[1 + i], 0);
+            }
+        cudaEventRecord(breq.ev[k], g_join_stream);
+        return DBOA_OK;
+    };
     for (int bi = (int)n.blocks.size() - 1; bi >= 0; --bi) {
         const Block& b = n.blocks[bi];
         const ConvLayer &c1 = n.convs[b.c1], &c2 = n.convs[b.c2], &c3 = n.convs[b.c3];
+        if (bi == 12) DBOA_TRY(bucket_done(0, n.blocks[13].c1));          // layer4 (blocks 13..15) and the head are done
+        if (bi == 6) DBOA_TRY(bucket_done(1, n.blocks[7].c1));            // layer3 (blocks 7..12)
         const float* xin = bi == 0 ? T + t.p0 : T + t.conv[n.blocks[bi - 1].c3].a;
         const float* a3 = T + t.conv[b.c3].a;
         // temps: 0 = dy3, 1 = dy_downsample, 2 = da2, 3 = dy2, 4 = da1, 5 = dy1
@@ -612,11 +662,7 @@ int hmr_backward(const float* P, const float* T, int B, int masked_in, const flo
     DBOA_TRY(maxpool3x3s2_bwd(dOut, reinterpret_cast<const unsigned char*>(T + t.p0_idx), dIn, B, 112, 112, 64, st));
     DBOA_TRY(gnb(0, dIn, T + t.conv[0].a, claim(0)));
     int rc = conv_wgrad(tmp[0], T + t.x0, G + n.convs[0].w_off, dims_of(n.convs[0], B), sc.ws, (size_t)kConvWs, st);
-    if (rc == DBOA_OK && B > 1) {                          // affine-parameter gradients of all 53 GroupNorms, summed over the samples
-        const GnItems& gi = gn_items();
-        if (gi.dev == nullptr) return DBOA_ERR_CUDA;
-        rc = gn_param_finish(gi.dev, (int)n.convs.size(), sc.gnp, G, B, st);
-    }
+    if (rc == DBOA_OK) rc = bucket_done(2, 0);               // stem, layer1, layer2 (and, for B > 1, their GroupNorm affine rows)
     if (async) {                                   // join: nothing of this call is left running when the caller's stream continues
         for (int i = 0; i < BwdAsync::NSIDE; ++i) {
             cudaEventRecord(A.ev_join[i], A.side[i]);

@@ -47,10 +47,12 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                        float* __restrict__ v, float* __restrict__ teacher, size_t n4, float w1, float b2,
                                                        float one_m_b2, float bc2_sqrt, float eps, float neg_step, float alpha,
-                                                       float one_m_alpha) {
+                                                       float one_m_alpha, float gscale) {
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
         float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<const float4*>(g)[i];
         float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        // data-parallel mean of the all-reduced (summed) gradient: g / R folded into this sweep (1.0f is exact: single-GPU results unchanged)
+        gg.x = __fmul_rn(gg.x, gscale); gg.y = __fmul_rn(gg.y, gscale); gg.z = __fmul_rn(gg.z, gscale); gg.w = __fmul_rn(gg.w, gscale);
         adam_one(pp.x, gg.x, mm.x, vv.x, w1, b2, one_m_b2, bc2_sqrt, eps, neg_step);
         adam_one(pp.y, gg.y, mm.y, vv.y, w1, b2, one_m_b2, bc2_sqrt, eps, neg_step);
         adam_one(pp.z, gg.z, mm.z, vv.z, w1, b2, one_m_b2, bc2_sqrt, eps, neg_step);
@@ -67,14 +69,14 @@ __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, co
     }
 }
 int adam_ema(float* p, const float* g, float* m, float* v, float* teacher, size_t n, float lr, float beta1, float beta2, float eps,
-             int step, float alpha, cudaStream_t st) {
+             int step, float alpha, float gscale, cudaStream_t st) {
     if (n % 4 || step < 1) return DBOA_ERR_ARG;
     // torch.optim.Adam (single-tensor path) computes these in Python doubles, then casts the scalars
     double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
     float neg_step = (float)(-((double)lr / bc1)), bc2_sqrt = (float)sqrt(bc2);
     adam_ema_kernel<<<sweep_grid(n / 4), 256, 0, st>>>(p, g, m, v, teacher, n / 4, (float)(1.0 - (double)beta1), beta2,
                                                        (float)(1.0 - (double)beta2), bc2_sqrt, eps, neg_step, alpha,
-                                                       (float)(1.0 - (double)alpha));
+                                                       (float)(1.0 - (double)alpha), gscale);
     return check_launch();
 }
 

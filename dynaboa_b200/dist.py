@@ -34,13 +34,64 @@ def shard_range(n_items, rank, world):
 
 
 def make_grad_sync(world, group=None):
-    """Hook for ``FusedAdam.pre_step_hook``: all-reduce(sum) of the flat gradient arena, then 1/world."""
+    """Hook for ``FusedAdam.pre_step_hook``: all-reduce(sum) of the flat gradient arena, then 1/world (one blocking
+    collective after the backward: the path the autograd driver uses; ``attach`` installs the overlapped variant)."""
     if world <= 1:
         return None
 
     def sync(flat_grad):
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
         flat_grad.mul_(1.0 / world)
+    return sync
+
+
+class BucketedGradSync:
+    """Overlaps the all-reduce of the outer gradient with the backward that produces it.
+
+    ``dboa_hmr_backward`` completes the gradient arena head -> layer4 -> layer3 -> ... -> stem; armed through
+    ``dboa_hmr_backward_buckets`` it records one event per bucket (layer4 + head: 74 MB, layer3: 28 MB, the rest: 6 MB) as
+    soon as every kernel writing that span is ordered.  ``after_backward`` makes a communication stream wait for each event
+    and all-reduce (sum) that span of the flat arena, so only the last, smallest bucket is exposed after the backward; the
+    mean (1 / world) is folded into the Adam sweep (``FusedAdam.gscale``), which waits for the communication stream."""
+
+    def __init__(self, world, device, group=None):
+        from . import _lib
+        self.world, self.group = world, group
+        self.comm = torch.cuda.Stream(device=device)
+        self.events = [torch.cuda.Event() for _ in range(3)]
+        for ev in self.events:
+            ev.record()                                    # forces creation of the cudaEvent_t handed to the library
+        lib = _lib.load()
+        self.bounds = [(lib.dboa_hmr_bucket_offset(k), lib.dboa_hmr_bucket_offset(k - 1)) for k in range(3)]
+
+    def arm(self):
+        from . import _lib
+        import ctypes as C
+        _lib.call('dboa_hmr_backward_buckets', *[C.c_void_p(ev.cuda_event) for ev in self.events])
+
+    def after_backward(self, flat_grad):
+        for ev, (lo, hi) in zip(self.events, self.bounds):
+            self.comm.wait_event(ev)
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+        flat_grad.record_stream(self.comm)
+
+
+def attach(adaptor, world, group=None):
+    """Turn ``adaptor`` into one rank of a data-parallel run: the fused path (``Adaptor.adapt``) all-reduces the outer
+    gradient bucket by bucket under the upper-level backward, the autograd path (``Adaptor.adaptation``) with one collective
+    before the optimiser step; both leave the 1 / world to the Adam sweep, and ``cal_feature_diff`` all-reduces its sums."""
+    if world <= 1:
+        return None
+    opt = adaptor.optimizer
+    opt.gscale = 1.0 / world
+    adaptor.dp_group = group
+    sync = BucketedGradSync(world, adaptor.device, group)
+    opt.grad_sync = sync
+
+    def hook(flat_grad):                                   # autograd path / any step the bucketed path did not cover
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    opt.pre_step_hook = hook
     return sync
 
 

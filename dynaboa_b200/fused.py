@@ -98,20 +98,33 @@ def _loss_head(ad, p, w, kp=None, t_p2d=None, t_j3d=None, t_beta=None, t_R=None,
     return terms, dp2d, dj3d, dR, dbeta
 
 
-def backward_graph(ad, arena, p, dp2d, dj3d, dR, dbeta, grad_arena):
-    """d(loss)/d(p2d, joints, R, beta) -> accumulate d(loss)/d(weights) into ``grad_arena``."""
+def _zero(t):
+    """Stream-ordered memset (copy engine / driver memset node): no ATen fill kernel in the step."""
+    _lib.call('dboa_fill_zero', ptr(t), t.numel() * t.element_size(), stream())
+
+
+def backward_graph(ad, arena, p, dp2d, dj3d, dR, dbeta, grad_arena, sync=None):
+    """d(loss)/d(p2d, joints, R, beta) -> accumulate d(loss)/d(weights) into ``grad_arena``.  ``sync``: the data-parallel
+    ``BucketedGradSync`` when this is the LAST graph accumulated into the outer gradient: its buckets are all-reduced on the
+    communication stream while the rest of this backward runs."""
     B, dev = p.B, p.rot.device
     dcam = torch.empty(B, 3, dtype=torch.float32, device=dev)
     _lib.call('dboa_project_bwd', ptr(p.cam), ptr(p.joints), ptr(dp2d), ptr(dj3d), ptr(dcam), B, 49, 1, 0, stream())
     scratch = torch.empty(_lib.load().dboa_smpl_scratch_floats(B), dtype=torch.float32, device=dev)
     _lib.call('dboa_smpl_backward', ad.smpl_neutral._struct_ref(), ptr(p.rot), B, ptr(p.smpl_tape), ptr(dj3d), ptr(scratch), ptr(dR),
               ptr(dbeta), 1, stream())
+    if sync is not None:
+        sync.arm()
     hmr_mod.raw_backward(arena, p.tape, B, p.masked, dR, dbeta, dcam, grad_arena)
+    if sync is not None:
+        sync.after_backward(grad_arena)
+        ad.optimizer.reduced = True
 
 
-def level_backward(ad, arena, buffers, image, kp, lower, grad_arena, main=None):
+def level_backward(ad, arena, buffers, image, kp, lower, grad_arena, main=None, sync=None):
     """One level of the bilevel problem (reference base_adaptor.py:222-317) on weights ``arena``: evaluates the
-    level's loss and accumulates its gradient into ``grad_arena``.  ``main`` is an already computed forward of
+    level's loss and accumulates its gradient into ``grad_arena`` (``sync``: data-parallel bucketed all-reduce to attach to
+    the last graph of the level).  ``main`` is an already computed forward of
     ``image`` with these weights (re-used when given).  When the motion loss is live and no forward is supplied,
     the current and the history frame go through ONE batched forward / backward (same weights, independent
     samples).  Returns (loss as a device scalar, the forward whose first rows belong to ``image``)."""
@@ -138,7 +151,13 @@ def level_backward(ad, arena, buffers, image, kp, lower, grad_arena, main=None):
     if motion:
         hist_image, hist_kp = ad.get_hist()
         if main is None:
-            main = forward_graph(ad, arena, buffers, torch.cat([image, hist_image], 0))      # rows [nb:] = history frame
+            pair = getattr(ad, '_pair', None)                   # persistent (2 nb, 3, 224, 224) staging: rows [nb:] = history frame
+            if pair is None or pair.shape[0] != 2 * nb or pair.device != image.device:
+                pair = ad._pair = torch.empty(2 * nb, 3, 224, 224, dtype=torch.float32, device=image.device)
+            half = image.numel() * 4
+            _lib.call('dboa_copy_async', ptr(pair), ptr(image), half, stream())
+            _lib.call('dboa_copy_async', C.c_void_p(pair.data_ptr() + half), ptr(hist_image.contiguous()), half, stream())
+            main = forward_graph(ad, arena, buffers, pair)
         else:
             hist = forward_graph(ad, arena, buffers, hist_image)
     elif main is None:
@@ -159,8 +178,16 @@ def level_backward(ad, arena, buffers, image, kp, lower, grad_arena, main=None):
         targets = dict(t_p2d=t.p2d, t_j3d=t.joints, t_beta=t.shape, t_R=t.rot)
     _mark(ad, f'{tag}: forward(s) issued')
     batched = main.B > nb
-    grads = (torch.zeros_like(main.p2d), torch.zeros_like(main.joints), torch.zeros_like(main.rot), torch.zeros_like(main.shape)) \
-        if batched else None
+    grads = None
+    if batched:                                                 # gradients of the 2 nb rows in ONE zeroed buffer (rows [nb:] only get the motion term)
+        Bm = main.B
+        sizes = (Bm * 49 * 2, Bm * 49 * 3, Bm * 24 * 9, Bm * 10)
+        flat = getattr(ad, '_bgrad_flat', None)
+        if flat is None or flat.numel() != sum(sizes) or flat.device != image.device:
+            flat = ad._bgrad_flat = torch.empty(sum(sizes), dtype=torch.float32, device=image.device)
+        _zero(flat)
+        e = [0, sizes[0], sizes[0] + sizes[1], sizes[0] + sizes[1] + sizes[2]]
+        grads = (flat[e[0]:e[1]].view(Bm, 49, 2), flat[e[1]:e[2]].view(Bm, 49, 3), flat[e[2]:e[3]].view(Bm, 24, 3, 3), flat[e[3]:].view(Bm, 10))
     terms, dp2d, dj3d, dR, dbeta = _loss_head(ad, main, w, kp=kp if use_frame else None, grads=grads, nb=nb, **targets)
     total = terms[8]
     if use_frame:
@@ -178,7 +205,8 @@ def level_backward(ad, arena, buffers, image, kp, lower, grad_arena, main=None):
         total = total + mterm[0] * o.motionloss_weight
         ad.fit_losses['ul/motion_loss'] = mterm[0]
     _mark(ad, f'{tag}: loss head')
-    backward_graph(ad, arena, main, dp2d, dj3d, dR, dbeta, grad_arena)
+    mix = bool(o.retrieval and (o.lower_level_mixtrain if lower else o.upper_level_mixtrain))
+    backward_graph(ad, arena, main, dp2d, dj3d, dR, dbeta, grad_arena, sync=None if mix else sync)
     _mark(ad, f'{tag}: backward')
     if o.retrieval:
         ex = ad.retrieval(hmr_mod._feature_views(main.tape, main.B)[5][:nb])
@@ -190,7 +218,7 @@ def level_backward(ad, arena, buffers, image, kp, lower, grad_arena, main=None):
             lw = o.labelloss_weight
             eterms, a, b, c, d = _loss_head(ad, e, [5 * lw, 0, 0, 0, 0, 0.001 * lw, 1 * lw, 5 * lw], kp=ex['keypoints'], t_beta=ex['betas'],
                                             t_R=gt_R, gt_s3d=ex['pose_3d'])
-            backward_graph(ad, arena, e, a, b, c, d, grad_arena)
+            backward_graph(ad, arena, e, a, b, c, d, grad_arena, sync=sync)
             total = total + eterms[8]
             ad.fit_losses[f'{tag}/labled_loss'] = eterms[8]
     return total, main
@@ -215,9 +243,11 @@ def fused_adapt(ad, batch):
         _mark(ad, 'start')
         probe = forward_graph(ad, theta, buffers, image)            # init_features (reference :132-133)
         _mark(ad, 'probe forward')
+        import torch.distributed as tdist
+        sync = opt.grad_sync if (opt.grad_sync is not None and tdist.is_initialized() and tdist.get_world_size() > 1) else None
         if not o.use_boa:
-            G.zero_()
-            ad.last_upper_loss, _ = level_backward(ad, theta, buffers, image, kp, True, G, main=probe)
+            _zero(G)
+            ad.last_upper_loss, _ = level_backward(ad, theta, buffers, image, kp, True, G, main=probe, sync=sync)
             opt.step()
             return ad.inference(batch, ad.model) if evaluate != 'none' else None
         fast, cur = theta, probe
@@ -225,7 +255,7 @@ def fused_adapt(ad, batch):
             ad._fast_bufs = [torch.empty_like(theta), torch.empty_like(theta)]
             ad._inner_grad = torch.empty_like(theta)
         for i in range(o.inner_step):
-            ad._inner_grad.zero_()
+            _zero(ad._inner_grad)
             level_backward(ad, fast, buffers, image, kp, True, ad._inner_grad, main=cur if i == 0 else None)
             _mark(ad, 'lower level (loss + backward)')
             nxt = ad._fast_bufs[i % 2]
@@ -234,8 +264,8 @@ def fused_adapt(ad, batch):
             _mark(ad, 'inner SGD step')
             if evaluate == 'all':
                 ad.inference(batch, _ArenaModel(model, fast))
-        G.zero_()
-        ad.last_upper_loss, _ = level_backward(ad, fast, buffers, image, kp, False, G)
+        _zero(G)
+        ad.last_upper_loss, _ = level_backward(ad, fast, buffers, image, kp, False, G, sync=sync)
         _mark(ad, 'upper level (forward + loss + backward)')
         opt.step(teacher=teacher, alpha=o.alpha)                    # Adam + EMA teacher, one sweep
         _mark(ad, 'Adam + EMA')
@@ -251,8 +281,8 @@ def fused_adapt(ad, batch):
                 steps += 1
                 if steps > o.optim_steps:
                     break
-                G.zero_()
-                level_backward(ad, theta, buffers, image, kp, False, G, main=after)   # 'after' was computed with the current theta
+                _zero(G)
+                level_backward(ad, theta, buffers, image, kp, False, G, main=after, sync=sync)   # 'after' was computed with the current theta
                 opt.step(teacher=teacher, alpha=o.alpha)
                 before, after = after, forward_graph(ad, theta, buffers, image)
                 sims = feature_cosines(ad, before.tape, after.tape, probe.B)

@@ -29,7 +29,10 @@ class FusedAdam(torch.optim.Optimizer):
         self.m = torch.zeros_like(self.model.arena)
         self.v = torch.zeros_like(self.model.arena)
         self.step_count = 0
-        self.pre_step_hook = None                              # e.g. the data-parallel gradient all-reduce
+        self.pre_step_hook = None                              # e.g. the data-parallel gradient all-reduce (dist.attach)
+        self.grad_sync = None                                  # dist.BucketedGradSync: all-reduce overlapped with the backward
+        self.reduced = False                                   # the gradient of the coming step has already been all-reduced
+        self.gscale = 1.0                                      # g * gscale inside the sweep (1 / world under data parallelism)
         self.wait_before_write = []                            # events of side-stream readers of the weights (Adaptor.predict_async)
 
     def _gather_grads(self):
@@ -54,14 +57,18 @@ class FusedAdam(torch.optim.Optimizer):
         return g
 
     def zero_grad(self, set_to_none=False):
-        self.model.grad_arena().zero_()
+        g = self.model.grad_arena()
+        _lib.call('dboa_fill_zero', ptr(g), g.numel() * 4, stream())
 
     @torch.no_grad()
     def step(self, closure=None, teacher=None, alpha=0.0):
         if closure is not None:
             raise NotImplementedError('closures are not used on the DynaBOA path')
         g = self._gather_grads()
-        if self.pre_step_hook is not None:
+        if self.reduced:                                       # bucketed all-reduce in flight on the communication stream
+            torch.cuda.current_stream().wait_stream(self.grad_sync.comm)
+            self.reduced = False
+        elif self.pre_step_hook is not None:
             self.pre_step_hook(g)
         if self.wait_before_write:                             # a side stream may still be reading the weights this step overwrites
             cur = torch.cuda.current_stream()
@@ -71,9 +78,9 @@ class FusedAdam(torch.optim.Optimizer):
         grp = self.param_groups[0]
         self.step_count += 1
         t = None if teacher is None else teacher.arena
-        _lib.call('dboa_adam_ema', ptr(self.model.arena), ptr(g), ptr(self.m), ptr(self.v), ptr(t), self.model.arena.numel(),
+        _lib.call('dboa_adam_ema_scaled', ptr(self.model.arena), ptr(g), ptr(self.m), ptr(self.v), ptr(t), self.model.arena.numel(),
                   float(grp['lr']), float(grp['betas'][0]), float(grp['betas'][1]), float(grp['eps']), self.step_count, float(alpha),
-                  stream())
+                  float(self.gscale), stream())
 
 
 def ema_update(teacher, model, alpha):

@@ -67,6 +67,14 @@ int dboa_hmr_backward(const float* arena, const float* tape, int B, int masked /
                       const float* d_rotmat, const float* d_shape, const float* d_cam, float* grad_arena, float* scratch,
                       dboa_stream_t stream);
 
+/* Gradient buckets of the NEXT dboa_hmr_backward call, for overlapping the data-parallel all-reduce with the backward
+ * (SURVEY.md section 8e).  Bucket k spans the floats [dboa_hmr_bucket_offset(k), dboa_hmr_bucket_offset(k - 1)) of the gradient
+ * arena (offset(-1) = arena size): 0 = layer4 + regressor head, 1 = layer3, 2 = stem + layer1 + layer2 -- the order in which the
+ * backward completes them.  ev0..2 are cudaEvent_t handles; event k is recorded when every kernel writing bucket k is ordered
+ * before it.  Arm only for the LAST backward call that accumulates into the arena. */
+int dboa_hmr_backward_buckets(void* ev0, void* ev1, void* ev2);
+long long dboa_hmr_bucket_offset(int k);
+
 /* ---- single operators (unit-parity surface; same kernels the plan above launches) ----------- */
 /* replaces: nn.Conv2d forward / backward (model/hmr.py:29-34,72,113); NHWC activations, weights [Cout][Kpitch] */
 int dboa_conv2d_fwd(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
@@ -184,6 +192,12 @@ int dboa_sgd_update(const float* p, const float* g, float* out, float lr, long l
 int dboa_adam_ema(float* p, const float* g, float* m, float* v, float* teacher /* or NULL */, long long n, float lr, float beta1,
                   float beta2, float eps, int step, float alpha, dboa_stream_t stream);     /* base_adaptor.py:126,193-201 */
 int dboa_ema_update(float* teacher, const float* p, long long n, float alpha, dboa_stream_t stream);
+/* Adam(+EMA) on g * gscale: the data-parallel mean of an all-reduced (summed) gradient without a separate sweep */
+int dboa_adam_ema_scaled(float* p, const float* g, float* m, float* v, float* teacher /* or NULL */, long long n, float lr, float beta1,
+                         float beta2, float eps, int step, float alpha, float gscale, dboa_stream_t stream);
+/* stream-ordered fill / device-to-device copy on the copy engine (gradient arenas, frame staging: no ATen kernels in a step) */
+int dboa_fill_zero(void* dst, long long bytes, dboa_stream_t stream);
+int dboa_copy_async(void* dst, const void* src, long long bytes, dboa_stream_t stream);
 /* cal_feature_diff :211-219: cosine similarity of npairs (<=16) flattened tensor pairs; host arrays of device pointers */
 int dboa_cosine_pairs(const float* const* a, const float* const* b, const long long* n, int npairs, float* partial,
                       long long partial_floats, float* out, float eps, dboa_stream_t stream);

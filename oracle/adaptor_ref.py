@@ -82,6 +82,10 @@ class OracleAdaptor:
         self.fit_losses = {}
         self.kp2dlosses_lower, self.kp2dlosses_upper = [], {}
         self.mask_fn = None          # callable(B) -> [(m1, m2)] * 3 scaled keep-masks for the teacher
+        # data-parallel emulation (oracle/dp_ref.py): called between loss.backward() and optimizer.step() / with the per-feature
+        # (a.b, |a|^2, |b|^2) sums of the dynamic test; None = single stream (the reference's semantics)
+        self.grad_hook = None
+        self.cos_hook = None
         self.mask_gen = torch.Generator().manual_seed(options.seed)
 
     # ------------------------------------------------------------------ model pieces
@@ -234,7 +238,13 @@ class OracleAdaptor:
                 self.teacher[k].mul_(a).add_(p.data, alpha=1 - a)
 
     def feature_diff(self, fa, fb):
-        sims = [F.cosine_similarity(a.flatten(), b.flatten(), dim=0, eps=1e-12) for a, b in zip(fa, fb)]
+        if self.cos_hook is not None:
+            terms = torch.stack([torch.stack([(a.flatten().double() * b.flatten().double()).sum(), (a.flatten().double() ** 2).sum(),
+                                              (b.flatten().double() ** 2).sum()]) for a, b in zip(fa, fb)])
+            terms = self.cos_hook(terms)                                             # summed over the ranks
+            sims = list((terms[:, 0] / (terms[:, 1].sqrt().clamp_min(1e-12) * terms[:, 2].sqrt().clamp_min(1e-12))).float())
+        else:
+            sims = [F.cosine_similarity(a.flatten(), b.flatten(), dim=0, eps=1e-12) for a, b in zip(fa, fb)]
         self.fit_losses['feat_sim/cos_sim'] = sum(sims) / (len(sims) - 1)          # :218 divides by last index
         return [s.item() for s in sims]
 
@@ -242,6 +252,8 @@ class OracleAdaptor:
     def outer_step(self, loss):
         self.optimizer.zero_grad()
         loss.backward()
+        if self.grad_hook is not None:
+            self.grad_hook(self)
         self.optimizer.step()
         if self.o.use_meanteacher:
             self.update_teacher()
@@ -272,6 +284,8 @@ class OracleAdaptor:
         rec['upper_loss'] = uloss.item()
         self.optimizer.zero_grad()
         uloss.backward()
+        if self.grad_hook is not None:
+            self.grad_hook(self)
         rec['grad_sample'] = {k: self.theta[k].grad.detach().clone() for k in
                               ('conv1.weight', 'layer2.0.bn1.weight', 'layer4.2.conv3.weight', 'fc1.bias',
                                'decpose.weight')}

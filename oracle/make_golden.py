@@ -410,6 +410,37 @@ def golden_adapt(workdir, tag, n_frames, **over):
     print(f'adapt {tag} ok')
 
 
+def golden_dp(R=2, n_frames=3):
+    """Data-parallel trajectory (oracle/dp_ref.py: R replicas in lock step, rank-mean outer gradient, rank-summed cosine
+    terms): 1 inner step, deterministic teacher, dynamic loop armed with a low threshold so that it fires.  The reference has no
+    distributed mode; this fixture pins the B200 implementation's NCCL path to the CPU emulation of SURVEY.md section 8e."""
+    from oracle import dp_ref
+    opts = adaptor_ref.default_options(inner_step=1, retrieval=0, lower_level_mixtrain=0, upper_level_mixtrain=0, dynamic_boa=1,
+                                       cos_sim_threshold=1e-7, optim_steps=2, teacher_dropout=0)
+    streams = [synthetic.SyntheticStream(length=n_frames, batch_size=1, rank=r) for r in range(R)]
+
+    def make(rank):
+        return adaptor_ref.OracleAdaptor(
+            opts, synthetic.make_basemodel(), {g: synthetic.make_smpl_model(g) for g in ('neutral', 'male', 'female')},
+            synthetic.make_extra_regressors(), dict(np.load(os.path.join(REPO, 'dynaboa_b200/assets/gmm_08.npz'))),
+            joint_map=C.JOINT_MAP_49, vertex_ids=C.SMPL_EXTRA_VERTEX_IDS, h36m_to_j14=C.H36M_TO_J14)
+    records, oracles = dp_ref.run(make, streams, n_frames)
+    names = list(oracles[0].theta.keys())
+    for k in names:                                        # replicas must stay identical
+        assert torch.equal(oracles[0].theta[k], oracles[1].theta[k]), k
+    out = dict(options=np.array(repr(sorted(vars(opts).items()))), param_names=np.array(names),
+               dyn_steps=np.array([[rec['dynamic_steps'] for rec in records[r]] for r in range(R)]),
+               upper_loss=np.array([[rec['upper_loss'] for rec in records[r]] for r in range(R)]),
+               theta_samples=_theta_samples([(k, oracles[0].theta[k]) for k in names]))
+    for r in range(R):
+        pred = oracles[r].predict(streams[r][n_frames - 1]['image'])
+        for key in ('rotmat', 'betas', 'cam', 'joints'):
+            out[f'{key}_r{r}'] = pred[key].numpy()
+    assert (out['dyn_steps'][0] == out['dyn_steps'][1]).all()
+    np.savez_compressed(os.path.join(OUT, 'adapt_dp2.npz'), **out)
+    print('adapt dp2 ok: dynamic steps', out['dyn_steps'].tolist(), 'upper', out['upper_loss'].tolist())
+
+
 def golden_eval():
     """Evaluation metrics: the reference's own Procrustes (utils/pose_utils.py) inside the arithmetic of
     dynaboa_benchmark.py:217-240, on seeded meshes (small vertex count keeps the fixture small).  Sample 2 is a mirrored
@@ -454,7 +485,9 @@ def main():
         synthetic.write_asset_dir(os.path.join(workdir, 'data'))
         os.makedirs(os.path.join(workdir, 'data/spin_data'), exist_ok=True)
         os.symlink(os.path.join(REF, 'data/gmm_08.pkl'), os.path.join(workdir, 'data/spin_data/gmm_08.pkl'))
-        which = sys.argv[1:] or ['geometry', 'prior', 'hmr', 'smpl', 'eval', 'c2', 'c3', 'c5']
+        which = sys.argv[1:] or ['geometry', 'prior', 'hmr', 'smpl', 'eval', 'c2', 'c3', 'c5', 'dp2']
+        if 'dp2' in which:
+            golden_dp()
         if 'geometry' in which:
             golden_geometry()
         if 'prior' in which:
