@@ -22,6 +22,9 @@ def init_from_env(backend=None):
         if backend is None:
             backend = 'nccl' if torch.cuda.is_available() else 'gloo'
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        # the bucketed all-reduce runs UNDER the backward: 16 channels were the best trade between link bandwidth and the SMs NCCL
+        # takes from the backward kernels on 2 x B200 (290 frames/s; 2: 241, 4: 288/260, 8: 276/291; profiles/r02_summary.md)
+        os.environ.setdefault('NCCL_MAX_NCHANNELS', '16')
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, world, local
 
@@ -86,7 +89,9 @@ def attach(adaptor, world, group=None):
     opt = adaptor.optimizer
     opt.gscale = 1.0 / world
     adaptor.dp_group = group
-    sync = BucketedGradSync(world, adaptor.device, group)
+    sync = None
+    if os.environ.get('DBOA_DP_BUCKETS', '1') != '0':          # 0: one all-reduce after the backward (A/B reference of the overlap)
+        sync = BucketedGradSync(world, adaptor.device, group)
     opt.grad_sync = sync
 
     def hook(flat_grad):                                   # autograd path / any step the bucketed path did not cover
