@@ -91,6 +91,8 @@ SIGNATURES = {
     'dboa_cosine_partial_floats': (L, [C.POINTER(L), I]),
     'dboa_cosine_terms': (I, [C.POINTER(P), C.POINTER(P), C.POINTER(L), I, P, L, P, P]),
     'dboa_retrieval_nearest': (I, [P, P, I, I, P, P, P]),
+    'dboa_crop_resize_normalize': (I, [P, I, I, I, I, I, I, P, P, I, P, P, I, I, P, P, P, P, P]),
+    'dboa_keypoint_transform': (I, [P, I, C.c_double, C.c_double, C.c_double, C.c_double, I, P, P]),
     'dboa_eval_scratch_floats': (L, [I, I]),
     'dboa_eval_metrics': (I, [P, P, P, P, I, I, P, I, P, P, I, P]),
 }

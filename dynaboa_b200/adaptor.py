@@ -176,3 +176,46 @@ class Adaptor(BaseAdaptor):
     def adapt(self, batch):
         from .fused import fused_adapt
         return fused_adapt(self, batch)
+
+
+class InternetAdaptor(Adaptor):
+    """Client of the same path without ground truth (reference dynaboa_internet.py ``Adaptor`` :68-168): the adaptation is
+    ``Adaptor.adaptation`` minus the per-step evaluation, ``inference`` only decodes the mesh and caches ``Pred_<step>.pt``."""
+
+    def reset_records(self):
+        self.feat_sims, self.optim_step_record = {}, []
+        self.mpjpe_statistics, self.pampjpe_statistics = [], []
+        self.mpjpe_all_lower = [[] for _ in range(self.options.inner_step)]
+        self.pampjpe_all_lower = [[] for _ in range(self.options.inner_step)]
+        self.history, self.kp2dlosses_lower, self.kp2dlosses_upper = {}, [], {}
+
+    def excute(self, max_frames=None, fused=False):
+        self.reset_records()
+        outs = []
+        for step, batch in enumerate(self.dataloader):
+            if max_frames is not None and step >= max_frames:
+                break
+            self.global_step, self.fit_losses = step, {}
+            batch = {k: v.to(self.device) if isinstance(v, torch.Tensor) else v for k, v in batch.items()}
+            self.model.eval()
+            if fused:
+                self.fused_eval = 'none'
+                self.adapt(batch)
+            else:
+                self.adaptation(batch)
+            outs.append(self.inference(batch, self.model))
+        return outs
+
+    def inference(self, batch, model, need_feature=False):
+        """reference dynaboa_internet.py:142-168: no metrics (there is no ground truth), cached predictions only."""
+        model.eval()
+        with torch.no_grad():
+            out = model(batch['image'], need_feature)
+            pred_rotmat, pred_shape, pred_cam = out[0], out[1], out[2]
+            pred_vertices = self.decode_smpl_params(pred_rotmat, pred_shape)['vts']
+        cam_t = torch.stack([pred_cam[:, 1], pred_cam[:, 2], 2 * 5000. / (constants.IMG_RES * pred_cam[:, 0] + 1e-9)], dim=-1)
+        res = {'verts': pred_vertices, 'cam': cam_t, 'rotmat': pred_rotmat, 'beta': pred_shape}
+        if getattr(self.options, 'cache_results', 1):
+            torch.save({k: v.cpu().numpy() for k, v in res.items()}, osp.join(self.exppath, 'result', f'Pred_{self.global_step}.pt'))
+        zero = np.zeros(pred_rotmat.shape[0], np.float32)
+        return (zero, zero, 0.0, out[3]) if need_feature else (zero, zero, 0.0)

@@ -302,6 +302,17 @@ int dboa_retrieval_nearest(const float* feat, const float* centers, int K, int D
     return retrieval_nearest(feat, centers, K, D, best, dists, ST(stream));
 }
 
+int dboa_crop_resize_normalize(const void* img, int is_u8, int H, int W, int ul_x, int ul_y, int Hc, const float* wx, const int* sx, int Tx,
+                               const float* wy, const int* sy, int Ty, int res, const float* mean3, const float* std3, float* tmp, float* out,
+                               dboa_stream_t stream) {
+    if (!img || !wx || !sx || !wy || !sy || !mean3 || !std3 || !tmp || !out) return DBOA_ERR_ARG;
+    return crop_resize_normalize(img, is_u8, H, W, ul_x, ul_y, Hc, wx, sx, Tx, wy, sy, Ty, res, mean3, std3, tmp, out, ST(stream));
+}
+int dboa_keypoint_transform(const float* kp, int n, double t00, double t02, double t11, double t12, int res, float* out, dboa_stream_t stream) {
+    if (!kp || !out || n < 0) return DBOA_ERR_ARG;
+    return keypoint_transform(kp, n, t00, t02, t11, t12, res, out, ST(stream));
+}
+
 long long dboa_eval_scratch_floats(int B, int NJ) { return (long long)eval_scratch_floats(B, NJ); }
 int dboa_eval_metrics(const float* pred_verts, const float* gt_verts_joints, const float* gt_verts_pve, const float* J_regressor, int NJ,
                       int NV, const int* joint_map, int n_map, float* scratch, float* out, int B, dboa_stream_t stream) {

@@ -87,6 +87,12 @@ int rot6d_bwd_launch(const float* pose6d, const float* drot, float* dpose, int n
 int ew_mul(const float* a, const float* b, float* out, size_t n, cudaStream_t st);
 int ew_add_rows(float* dst, int ld_dst, const float* a, int lda, const float* b, int ldb, int B, int n, cudaStream_t st);
 
+// ---- dataprocess.cu (crop + anti-aliased resize + normalise, keypoint transform)
+int crop_resize_normalize(const void* img, int is_u8, int H, int W, int ul_x, int ul_y, int Hc, const float* wx, const int* sx, int Tx,
+                          const float* wy, const int* sy, int Ty, int res, const float mean[3], const float stdv[3], float* tmp, float* out,
+                          cudaStream_t st);
+int keypoint_transform(const float* kp, int n, double t00, double t02, double t11, double t12, int res, float* out, cudaStream_t st);
+
 // ---- eval.cu (evaluation metrics on the device)
 size_t eval_scratch_floats(int B, int NJ);
 int eval_metrics(const float* pred_verts, const float* gt_verts_joints, const float* gt_verts_pve, const float* Jreg, int NJ, int NV,

@@ -441,6 +441,43 @@ def golden_dp(R=2, n_frames=3):
     print('adapt dp2 ok: dynamic steps', out['dyn_steps'].tolist(), 'upper', out['upper_loss'].tolist())
 
 
+def golden_dataprocess():
+    """Input side: the reference's OWN crop / transform code (utils/dataprocess.py, imported unmodified with
+    skimage.transform.resize -- not installed here -- stubbed by its scipy restatement) on a seeded image; asserts the oracle
+    restatement reproduces it and stores inputs + outputs."""
+    import types
+    from oracle import dataprocess_ref as R
+    sk, skt = types.ModuleType('skimage'), types.ModuleType('skimage.transform')
+    skt.resize = lambda img, res: R.resize(img, res)
+    sk.transform = skt
+    sys.modules.setdefault('skimage', sk); sys.modules.setdefault('skimage.transform', skt)
+    if 'constants' not in sys.modules:            # the reference module does `import constants` (its own constants.py)
+        sys.modules['constants'] = _load_by_path('constants', os.path.join(REF, 'constants.py'))
+    ref = _load_by_path('ref_dataprocess', os.path.join(REF, 'utils', 'dataprocess.py'))
+    rng = np.random.default_rng(7)
+    img = rng.uniform(0, 255, size=(120, 160, 3)).astype(np.float32)
+    boxes = [([80.0, 60.0], 0.5), ([20.0, 100.0], 0.8), ([150.5, 10.25], 0.35), ([81.0, 59.0], 1.3), ([60.0, 60.0], 0.2)]
+    kp = np.concatenate([rng.uniform(-10, 170, size=(49, 2)), (rng.random((49, 1)) > 0.3).astype(np.float64)], 1)
+    crops, kps = [], []
+    for center, scale in boxes:
+        a = ref.crop(img.copy(), center, scale, [224, 224])
+        b = R.crop(img.copy(), center, scale, [224, 224])
+        assert np.array_equal(a, b), (center, scale)
+        rgb = np.transpose(a.astype('float32'), (2, 0, 1)) / 255.0
+        rgb = (rgb - R.IMG_NORM_MEAN[:, None, None].astype('float32')) / R.IMG_NORM_STD[:, None, None].astype('float32')
+        assert np.array_equal(rgb.astype('float32'), R.rgb_processing(img, center, scale))
+        ka = kp.copy()
+        for i in range(ka.shape[0]):
+            ka[i, 0:2] = ref.transform(ka[i, 0:2] + 1, center, scale, [224, 224])
+        ka[:, :-1] = 2. * ka[:, :-1] / 224 - 1.
+        assert np.array_equal(ka.astype('float32'), R.j2d_processing(kp, center, scale))
+        crops.append(R.rgb_processing(img, center, scale)[:, ::4, ::4])
+        kps.append(ka.astype('float32'))
+    np.savez_compressed(os.path.join(OUT, 'dataprocess.npz'), img=img, kp=kp, centers=np.array([b[0] for b in boxes]),
+                        scales=np.array([b[1] for b in boxes]), crops_sub=np.stack(crops), kps=np.stack(kps))
+    print('dataprocess.npz ok')
+
+
 def golden_eval():
     """Evaluation metrics: the reference's own Procrustes (utils/pose_utils.py) inside the arithmetic of
     dynaboa_benchmark.py:217-240, on seeded meshes (small vertex count keeps the fixture small).  Sample 2 is a mirrored
@@ -485,9 +522,11 @@ def main():
         synthetic.write_asset_dir(os.path.join(workdir, 'data'))
         os.makedirs(os.path.join(workdir, 'data/spin_data'), exist_ok=True)
         os.symlink(os.path.join(REF, 'data/gmm_08.pkl'), os.path.join(workdir, 'data/spin_data/gmm_08.pkl'))
-        which = sys.argv[1:] or ['geometry', 'prior', 'hmr', 'smpl', 'eval', 'c2', 'c3', 'c5', 'dp2']
+        which = sys.argv[1:] or ['geometry', 'prior', 'hmr', 'smpl', 'eval', 'c2', 'c3', 'c5', 'dp2', 'dataprocess']
         if 'dp2' in which:
             golden_dp()
+        if 'dataprocess' in which:
+            golden_dataprocess()
         if 'geometry' in which:
             golden_geometry()
         if 'prior' in which:
