@@ -134,6 +134,11 @@ int dboa_conv2d_tc_wgrad(const float* dy, const float* x, float* dw, int B, int 
     if (!dy || !x || !dw) return DBOA_ERR_ARG;
     return conv_tc_wgrad(dy, x, dw, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), ST(stream), cabi_pdl());
 }
+int dboa_conv2d_wgrad_tma(const float* dy, const float* x, float* dw, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
+                          int Kpitch, dboa_stream_t stream) {
+    if (!dy || !x || !dw) return DBOA_ERR_ARG;
+    return conv_wgrad_wide(dy, x, dw, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), ST(stream), false);
+}
 long long dboa_conv_fused_part_floats(int B, int Ho, int Cout) { (void)Ho; (void)Cout; return (long long)B * 16; }
 int dboa_conv_fused_fwd(const dboa_fused_conv* probs, int nprob, int B, dboa_stream_t stream) {
     if (!probs || nprob < 1 || nprob > 2 || B < 1) return DBOA_ERR_ARG;

@@ -550,9 +550,11 @@ static const CUtensorMap* weight_map(const float* w, int K, int Cout) {
     return &h->tm;
 }
 // activation [B][H][W][C] as a 4-D tensor (C, W, H, B); box = 32 channels x W x bh rows x 1 sample, zero fill outside
-static const CUtensorMap* act_map(const float* x, int B, int H, int W, int C, int bw, int bh) {
-    static std::map<std::tuple<const float*, int, int, int, int, int, int>, TmHolder*> cache;
-    auto key = std::make_tuple(x, B, H, W, C, bw, bh);
+// atom32: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (32-byte chunks swizzled with the row index mod 4): the only shared-memory layout
+// tcgen05 accepts for MN-major TF32 operands (UMMA layout type SWIZZLE_128B_BASE32B)
+static const CUtensorMap* act_map(const float* x, int B, int H, int W, int C, int bw, int bh, bool atom32 = false) {
+    static std::map<std::tuple<const float*, int, int, int, int, int, int, bool>, TmHolder*> cache;
+    auto key = std::make_tuple(x, B, H, W, C, bw, bh, atom32);
     auto it = cache.find(key);
     if (it != cache.end()) return &it->second->tm;
     EncodeTiledFn enc = encode_fn();
@@ -564,7 +566,8 @@ static const CUtensorMap* act_map(const float* x, int B, int H, int W, int C, in
     const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     if (enc(&h->tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete h; return nullptr; }
+            atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete h; return nullptr; }
     cache[key] = h;
     return &h->tm;
 }
@@ -576,6 +579,9 @@ static int num_sms() {
 static int rows_of(int Ho) { return Ho * Ho <= BM ? Ho : BM / Ho; }          // image rows per output tile (square images)
 
 }  // namespace wz
+
+// shared with conv_wgrad_wide.cu
+const void* tma_act_map(const float* x, int B, int H, int W, int C, int bw, int bh, bool atom32) { return wz::act_map(x, B, H, W, C, bw, bh, atom32); }
 
 bool conv_wide_ok(const FusedConv& d) {
     return d.Cin % 64 == 0 && d.Cout % 64 == 0 && (d.k == 1 || d.k == 3) && d.stride == 1 && d.pad == d.k / 2 && d.mode >= 0 && d.mode <= 3 &&

@@ -303,7 +303,13 @@ static int conv_backward_data(const ConvLayer& c, int B, const float* dy, const 
     }
     return conv_dgrad(dy, w, dx, dims_of(c, B), accumulate, ws, (size_t)kConvWs, st);
 }
+// DBOA_WGRAD_TMA=0 keeps every weight gradient on the CUDA-core kernel (A/B reference)
+static const bool g_wgrad_tma = [] { const char* e = getenv("DBOA_WGRAD_TMA"); return !(e && e[0] == '0'); }();
 static int conv_backward_weight(const ConvLayer& c, int B, const float* dy, const float* x, float* dw, float* ws, cudaStream_t st) {
+    if (g_wgrad_tma && conv_tc_enabled()) {                 // tcgen05, MN-major operands through TMA (stride 1, Cout >= 128)
+        int s = conv_wgrad_wide(dy, x, dw, dims_of(c, B), st, false);
+        if (s != DBOA_ERR_UNSUPPORTED) return s;
+    }
     if (conv_tc_wgrad_enabled()) {
         int s = conv_tc_wgrad(dy, x, dw, dims_of(c, B), st);
         if (s != DBOA_ERR_UNSUPPORTED) return s;

@@ -51,6 +51,10 @@ int conv_wide_launch(const FusedConv* d, int nprob, int B, int nz, const float* 
 int gn_acc_res_avgpool(const float* y, const float* res, const float* acc, const float* gamma, const float* beta, float* a_out, float* stats_out,
                        float* out, int B, int HW, int C, int ld, int ncopy, size_t copy_stride, cudaStream_t st);
 
+// ---- conv_wgrad_wide.cu (tcgen05 weight gradient, MN-major operands through TMA); dw is accumulated (+=)
+bool conv_wgrad_wide_ok(const ConvDims& d);
+int conv_wgrad_wide(const float* dy, const float* x, float* dw, const ConvDims& d, cudaStream_t st, bool pdl);
+
 // ---- groupnorm.cu (single-launch cluster kernels)
 size_t gn_partial_floats(int B, int HW, int C);     // forward scratch (none; kept for the C ABI)
 size_t gn_bwd_partial_floats(int B, int HW, int C); // backward scratch: per-sample dgamma / dbeta rows

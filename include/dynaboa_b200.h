@@ -99,6 +99,10 @@ int dboa_conv2d_tc_dgrad(const float* dy, const float* w, float* dx, int B, int 
                          int Kpitch, int accumulate, dboa_stream_t stream);
 int dboa_conv2d_tc_wgrad(const float* dy, const float* x, float* dw, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
                          int Kpitch, dboa_stream_t stream);
+/* weight gradient on tcgen05 with MN-major operands fed by TMA (csrc/conv_wgrad_wide.cu): dw += dy^T * im2col(x); stride 1,
+ * Cout % 128 == 0, Cin % 64 == 0, k in {1, 3}, pad k/2, square images of 56 / 28 / 14 / 7 (DBOA_ERR_UNSUPPORTED otherwise) */
+int dboa_conv2d_wgrad_tma(const float* dy, const float* x, float* dw, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,
+                          int Kpitch, dboa_stream_t stream);
 /* Fused tcgen05 convolution, the unit the forward plan is made of (csrc/conv_wide.cu).
  * replaces: nn.Conv2d + the nn.GroupNorm(4, C) / ReLU / residual add that PRECEDES it in Bottleneck.forward
  * (model/hmr.py:40-60), + the statistics pass of the GroupNorm that follows it.

@@ -208,3 +208,29 @@ def test_fused_forward_fills_the_same_tape_as_the_unfused_plan(L):
         hmr_mod.raw_backward(m.arena, t1, B, False, dr, dsh, dc, G1)
         torch.cuda.synchronize()
         assert ((G1 - G0).norm() / G0.norm()).item() < 2e-3, B
+
+
+WGRAD = [  # B, H, Cin, Cout, k
+    (1, 56, 64, 256, 1), (1, 28, 128, 128, 3), (2, 28, 512, 128, 1), (1, 14, 256, 256, 3), (3, 14, 1024, 256, 1), (1, 7, 512, 512, 3),
+    (2, 7, 512, 2048, 1), (9, 7, 2048, 512, 1), (1, 14, 256, 1024, 1)]
+
+
+@pytest.mark.parametrize('case', WGRAD)
+def test_weight_gradient_on_tensor_cores_mn_major(L, case):
+    """tcgen05 weight gradient with MN-major TMA operands (csrc/conv_wgrad_wide.cu) against the fp32 CUDA-core kernel and an fp64
+    reference; dw is accumulated."""
+    B, H, Cin, Cout, k = case
+    g = torch.Generator().manual_seed(sum(case) + 3)
+    x = torch.randn(B, H, H, Cin, generator=g).cuda()
+    dy = torch.randn(B, H, H, Cout, generator=g).cuda()
+    K = k * k * Cin
+    base = (torch.randn(Cout, K, generator=g) * 0.1).cuda()
+    dw_tma, dw32 = base.clone(), base.clone()
+    L.call('dboa_conv2d_wgrad_tma', L.ptr(dy), L.ptr(x), L.ptr(dw_tma), B, H, H, Cin, Cout, k, 1, k // 2, K, L.stream())
+    ws = torch.empty(8 << 20, device='cuda')
+    L.call('dboa_conv2d_wgrad', L.ptr(dy), L.ptr(x), L.ptr(dw32), B, H, H, Cin, Cout, k, 1, k // 2, K, L.ptr(ws), ws.numel(), L.stream())
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2).double(), (Cout, Cin, k, k), dy.permute(0, 3, 1, 2).double(), padding=k // 2)
+    ref = ref.permute(0, 2, 3, 1).reshape(Cout, K)
+    assert rel_err(dw_tma - base, ref) < 2e-5, case
+    assert rel_err(dw_tma - base, dw32 - base) < 2e-5, case
