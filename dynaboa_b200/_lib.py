@@ -32,6 +32,12 @@ class FusedConvStruct(C.Structure):
                 + [(n, I) for n in ('mode', 'Hi', 'Cin', 'Cout', 'k', 'stride', 'pad')])
 
 
+class DgradFusedStruct(C.Structure):
+    _fields_ = ([(n, P) for n in ('dz', 'y_c', 'w', 'stats_c', 'sums_c', 'gamma_c', 'dy_out', 'addend', 'out', 'mask')]
+                + [('prep_y', P * 2), ('prep_stats', P * 2), ('prep_gamma', P * 2), ('prep_sums', P * 2), ('prep_dgb', P * 2), ('nprep', I),
+                   ('accumulate', I)])
+
+
 # name -> (restype, argtypes); mirrors include/dynaboa_b200.h one to one
 SIGNATURES = {
     'dboa_version': (C.c_char_p, []),
@@ -40,7 +46,9 @@ SIGNATURES = {
     'dboa_set_tensor_core_conv': (I, [I]),
     'dboa_set_fused_forward': (I, [I]),
     'dboa_get_fused_forward': (I, []),
+    'dboa_set_fused_backward': (I, [I]),
     'dboa_set_forward_cta_budget': (I, [I]),
+    'dboa_dgrad_fused': (I, [C.POINTER(DgradFusedStruct), I, I, I, I, I, P]),
     'dboa_conv_fused_part_floats': (L, [I, I, I]),
     'dboa_conv_fused_fwd': (I, [C.POINTER(FusedConvStruct), I, I, P]),
     'dboa_hmr_num_params': (I, []),

@@ -18,6 +18,7 @@ int hmr_backward(const float* P, const float* T, int B, int masked, const float*
 void hmr_arm_bucket_events(cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2);
 long long hmr_bucket_offset(int k);
 void hmr_set_fused_forward(bool on);
+void hmr_set_fused_backward(bool on);
 bool hmr_fused_forward();
 int hmr_num_params();
 long long hmr_arena_floats();
@@ -72,6 +73,7 @@ int dboa_set_tensor_core_conv(int enable) { conv_tc_set_mode(enable); return DBO
 
 int dboa_set_fused_forward(int enable) { hmr_set_fused_forward(enable != 0); return DBOA_OK; }
 int dboa_get_fused_forward(void) { return hmr_fused_forward() ? 1 : 0; }
+int dboa_set_fused_backward(int enable) { hmr_set_fused_backward(enable != 0); return DBOA_OK; }
 int dboa_set_forward_cta_budget(int n) { conv_wide_set_cta_budget(n < 0 ? 0 : n); return DBOA_OK; }
 
 int dboa_hmr_num_params(void) { return hmr_num_params(); }
@@ -138,6 +140,19 @@ int dboa_conv2d_wgrad_tma(const float* dy, const float* x, float* dw, int B, int
                           int Kpitch, dboa_stream_t stream) {
     if (!dy || !x || !dw) return DBOA_ERR_ARG;
     return conv_wgrad_wide(dy, x, dw, make_dims(B, Hi, Wi, Cin, Cout, k, stride, pad, Kpitch), ST(stream), false);
+}
+int dboa_dgrad_fused(const dboa_dgrad_args* f, int B, int H, int Cin, int Cout, int k, dboa_stream_t stream) {
+    if (!f || !f->dz || !f->y_c || !f->w || !f->stats_c || !f->sums_c || !f->gamma_c || !f->out) return DBOA_ERR_ARG;
+    DgradFused d;
+    memset(&d, 0, sizeof d);
+    d.dz = f->dz; d.y_c = f->y_c; d.w = f->w; d.stats_c = f->stats_c; d.sums_c = f->sums_c; d.gamma_c = f->gamma_c; d.dy_out = f->dy_out;
+    d.addend = f->addend; d.out = f->out; d.mask = f->mask; d.nprep = f->nprep; d.accumulate = f->accumulate;
+    for (int j = 0; j < 2; ++j) {
+        d.prep[j].y = f->prep_y[j]; d.prep[j].stats = f->prep_stats[j]; d.prep[j].gamma = f->prep_gamma[j];
+        d.prep[j].sums = f->prep_sums[j]; d.prep[j].dgb = f->prep_dgb[j];
+        if (f->mask && j < f->nprep && (!d.prep[j].y || !d.prep[j].stats || !d.prep[j].gamma || !d.prep[j].sums || !d.prep[j].dgb)) return DBOA_ERR_ARG;
+    }
+    return dgrad_wide(d, make_dims(B, H, H, Cin, Cout, k, 1, k / 2, k * k * Cin), ST(stream), cabi_pdl());
 }
 long long dboa_conv_fused_part_floats(int B, int Ho, int Cout) { (void)Ho; (void)Cout; return (long long)B * 16; }
 int dboa_conv_fused_fwd(const dboa_fused_conv* probs, int nprob, int B, dboa_stream_t stream) {

@@ -280,8 +280,11 @@ int conv_wgrad_wide(const float* dy, const float* x, float* dw, const ConvDims& 
     L.kps = ceil_div(d.Ho, bh); L.nkb_total = d.B * L.kps;
     L.ntn = d.Cin / wg::BN; L.taps = d.kh * d.kw;
     const int tiles = (d.Cout / wg::BM) * L.ntn * L.taps;
+    // weight gradients run on side streams NEXT to the data-gradient chain: a launch owns its SMs (one CTA of 170 KB each), so its
+    // K-slices are limited to a CTA budget that leaves room for the chain (DBOA_WGRAD_MAX_CTAS)
+    static const int budget = [] { const char* e = getenv("DBOA_WGRAD_MAX_CTAS"); int v = e ? atoi(e) : 128; return v < 1 ? 1 : v; }();
     int nz = 1;
-    while (nz < 16 && tiles * nz * 2 <= 128 && L.nkb_total / (nz * 2) >= 1) nz *= 2;
+    while (nz < 16 && tiles * nz * 2 <= budget && L.nkb_total / (nz * 2) >= 1) nz *= 2;
     while (nz > 1 && (nz - 1) * ceil_div(L.nkb_total, nz) >= L.nkb_total) nz >>= 1;
     L.nz = nz; L.per = ceil_div(L.nkb_total, nz);
     const CUtensorMap* tmdy = static_cast<const CUtensorMap*>(tma_act_map(dy, d.B, d.Ho, d.Wo, d.Cout, W, bh, true));

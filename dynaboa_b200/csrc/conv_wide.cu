@@ -549,6 +549,25 @@ static const CUtensorMap* weight_map(const float* w, int K, int Cout) {
     cache[key] = h;
     return &h->tm;
 }
+// weight matrix [Cout][K] read TRANSPOSED (data gradient: B[n = ci][k = co]): boxes of 32 input channels (contiguous) x 32 output
+// channels with the 32-byte-atom swizzle = the MN-major TF32 operand layout of tcgen05
+static const CUtensorMap* weight_map_mn(const float* w, int K, int Cout) {
+    static std::map<std::tuple<const float*, int, int>, TmHolder*> cache;
+    auto key = std::make_tuple(w, K, Cout);
+    auto it = cache.find(key);
+    if (it != cache.end()) return &it->second->tm;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return nullptr;
+    TmHolder* h = new TmHolder;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&h->tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete h; return nullptr; }
+    cache[key] = h;
+    return &h->tm;
+}
 // activation [B][H][W][C] as a 4-D tensor (C, W, H, B); box = 32 channels x W x bh rows x 1 sample, zero fill outside
 // atom32: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (32-byte chunks swizzled with the row index mod 4): the only shared-memory layout
 // tcgen05 accepts for MN-major TF32 operands (UMMA layout type SWIZZLE_128B_BASE32B)
@@ -580,7 +599,8 @@ static int rows_of(int Ho) { return Ho * Ho <= BM ? Ho : BM / Ho; }          // 
 
 }  // namespace wz
 
-// shared with conv_wgrad_wide.cu
+// shared with conv_wgrad_wide.cu / dgrad_wide.cu
+const void* tma_weight_map_mn(const float* w, int K, int Cout) { return wz::weight_map_mn(w, K, Cout); }
 const void* tma_act_map(const float* x, int B, int H, int W, int C, int bw, int bh, bool atom32) { return wz::act_map(x, B, H, W, C, bw, bh, atom32); }
 
 bool conv_wide_ok(const FusedConv& d) {

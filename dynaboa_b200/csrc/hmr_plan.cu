@@ -167,6 +167,8 @@ static const long long kConvWs = 8LL << 20;    // split-K workspace (floats)
 
 struct Scratch {
     float *ws, *g0, *g1, *t1, *t2, *t3, *t4, *t5, *t6, *gnp, *dP, *dy_dec, *d_h2, *d_h1, *dxc, *dxf, *tmp1024, *lin_ws;
+    float *bsums, *bdgb;            // fused backward: fixed-point GroupNorm-backward sums [conv][B][4][2] and (d gamma, d beta) [channel][2] (long long)
+    long long bacc_floats, gnp_floats;
     long long total;
     long long lin_ws_floats;
     Scratch(float* base, int B) {
@@ -178,6 +180,12 @@ struct Scratch {
         long long gsum = 0;                               // per-sample dgamma / dbeta rows of EVERY GroupNorm (reduced once, at the end)
         for (const ConvLayer& c : net().convs) gsum += (long long)gn_bwd_partial_floats(B, c.hout * c.hout, c.cout);
         gnp = take(gsum);
+        gnp_floats = gsum;
+        long long csum = 0;
+        for (const ConvLayer& c : net().convs) csum += c.cout;
+        bsums = take((long long)net().convs.size() * B * 16);
+        bdgb = take(csum * 4);
+        bacc_floats = (long long)((bdgb + csum * 4) - bsums);
         dP = take((long long)B * DEC_LD);
         dy_dec = take(3LL * B * DEC_LD);
         d_h2 = take(3LL * B * HID); d_h1 = take(3LL * B * HID);
@@ -249,6 +257,13 @@ static const int g_wgrad_streams = [] { const char* e = getenv("DBOA_WGRAD_STREA
 
 static ConvDims dims_of(const ConvLayer& c, int B);
 
+// DBOA_FUSED_BWD=1 (or dboa_set_fused_backward(1)) selects the fused data-gradient chain (dgrad_wide.cu).  It is parity-green and
+// saves 96 launches per frame, but measured SLOWER end to end (C2, 1 x B200: 151.5 frames/s at best against 155.3): every fused
+// launch owns its SMs (576 threads, ~150 KB of shared memory per CTA), so the weight-gradient side streams no longer overlap
+// the chain, and the ~10 us fixed cost of a launch is not lower than GroupNorm-backward + data-gradient of round 1
+// (profiles/r02_summary.md).  Default: the round-1 chain with the tcgen05 / TMA weight gradient.
+static bool g_fused_bwd = [] { const char* e = getenv("DBOA_FUSED_BWD"); return e && e[0] == '1'; }();
+void hmr_set_fused_backward(bool on) { g_fused_bwd = on; }
 // DBOA_FUSED_FWD=0 in the environment (or dboa_set_fused_forward(0)) selects the round-1 forward: one convolution launch and
 // one GroupNorm launch per layer (kept as the A/B reference of the fused path; both fill the same tape)
 static bool g_fused_fwd = [] { const char* e = getenv("DBOA_FUSED_FWD"); return !(e && e[0] == '0'); }();
@@ -637,6 +652,94 @@ int hmr_backward(const float* P, const float* T, int B, int masked_in, const flo
         cudaEventRecord(breq.ev[k], g_join_stream);
         return DBOA_OK;
     };
+    const bool fused = g_fused_bwd && conv_tc_bwd_enabled();
+    if (fused) {
+        // ---- fused chain (dgrad_wide.cu): per stride-1 layer ONE launch does GroupNorm backward (on load), the data gradient, the
+        // shortcut add, the ReLU mask of the producing layer and the sums of ITS GroupNorm backward; the stride-2 layers (conv2
+        // and shortcut of layer2.0 / 3.0 / 4.0) keep the unfused kernels, stitched in with gn_bwd_prep.
+        auto sums_of = [&](int ci) { return sc.bsums + (long long)ci * B * 16; };
+        auto dgb_of = [&](int ci) { return sc.bdgb + 4 * gn_items().cum[ci]; };
+        auto prep_of = [&](int ci) {
+            const ConvLayer& c = n.convs[ci];
+            DgradPrep p;
+            p.y = T + t.conv[ci].y; p.stats = T + t.conv[ci].stats; p.gamma = P + c.g_off; p.sums = sums_of(ci); p.dgb = dgb_of(ci);
+            return p;
+        };
+        auto K = [&](int ci, const float* dzin, float* dy_out, const float* addend, float* out, const float* mask, int np, int p0, int p1) {
+            const ConvLayer& c = n.convs[ci];
+            DgradFused f;
+            memset(&f, 0, sizeof f);
+            f.dz = dzin; f.y_c = T + t.conv[ci].y; f.w = P + c.w_off; f.stats_c = T + t.conv[ci].stats; f.sums_c = sums_of(ci); f.gamma_c = P + c.g_off;
+            f.dy_out = dy_out; f.addend = addend; f.out = out; f.mask = mask; f.nprep = mask ? np : 0;
+            if (mask && np >= 1) f.prep[0] = prep_of(p0);
+            if (mask && np >= 2) f.prep[1] = prep_of(p1);
+            return dgrad_wide(f, dims_of(c, B), st, true);
+        };
+        cudaMemsetAsync(sc.bsums, 0, (size_t)sc.bacc_floats * sizeof(float), st);
+        if (B > 1) cudaMemsetAsync(sc.gnp, 0, (size_t)sc.gnp_floats * sizeof(float), st);       // rows of the layers that stay fused are never written
+        {   // seam: dA of the last block's output -> masked gradient + sums of its bn3
+            const Block& lb = n.blocks.back();
+            DBOA_TRY(gn_bwd_prep(dOut, T + t.conv[lb.c3].a, dOut, prep_of(lb.c3), B, 49, 2048, st));
+        }
+        auto finish_fixed = [&](int first_conv, int end_conv) {
+            const GnItems& gi = gn_items();
+            if (gi.dev == nullptr) return DBOA_ERR_CUDA;
+            return gn_dgb_finish(gi.dev + first_conv, end_conv - first_conv, sc.bdgb, G, st);
+        };
+        int fixed_from = (int)n.convs.size();
+        for (int bi = (int)n.blocks.size() - 1; bi >= 0; --bi) {
+            const Block& b = n.blocks[bi];
+            const ConvLayer &c1 = n.convs[b.c1], &c2 = n.convs[b.c2], &c3 = n.convs[b.c3];
+            if (bi == 12 || bi == 6) {
+                const int first = bi == 12 ? n.blocks[13].c1 : n.blocks[7].c1;
+                DBOA_TRY(finish_fixed(first, fixed_from));
+                fixed_from = first;
+                DBOA_TRY(bucket_done(bi == 12 ? 0 : 1, first));
+            }
+            const float* xin = bi == 0 ? T + t.p0 : T + t.conv[n.blocks[bi - 1].c3].a;
+            const float* a3 = T + t.conv[b.c3].a;
+            float* dzo = dOut;                                  // masked gradient w.r.t. this block's pre-ReLU output (sums of bn3 [and the fused shortcut's norm] filled)
+            const bool sblock = c2.stride != 1;
+            if (!sblock) {
+                DBOA_TRY(K(b.c3, dzo, claim(0), nullptr, tmp[2], T + t.conv[b.c2].a, 1, b.c2, -1));
+                DBOA_TRY(wgrad(c3, 0, T + t.conv[b.c2].a));
+                DBOA_TRY(K(b.c2, tmp[2], claim(3), nullptr, tmp[4], T + t.conv[b.c1].a, 1, b.c1, -1));
+                DBOA_TRY(wgrad(c2, 3, T + t.conv[b.c1].a));
+                const float* addend = dzo;                      // identity shortcut: d(out) flows straight to the block input
+                if (b.cd >= 0) {                                // stride-1 shortcut convolution (layer1.0): its data gradient is the addend
+                    DBOA_TRY(K(b.cd, dzo, claim(1), nullptr, dIn, nullptr, 0, -1, -1));
+                    DBOA_TRY(wgrad(n.convs[b.cd], 1, xin));
+                    addend = dIn;
+                }
+                if (bi > 0) {
+                    const Block& pb = n.blocks[bi - 1];
+                    const bool two = pb.cd >= 0 && n.convs[pb.cd].stride == 1;
+                    DBOA_TRY(K(b.c1, tmp[4], claim(5), addend, dIn, T + t.conv[pb.c3].a, two ? 2 : 1, pb.c3, pb.cd));
+                } else {
+                    DBOA_TRY(K(b.c1, tmp[4], claim(5), addend, dIn, nullptr, 0, -1, -1));
+                }
+                DBOA_TRY(wgrad(c1, 5, xin));
+            } else {
+                DBOA_TRY(K(b.c3, dzo, claim(0), nullptr, claim(2), nullptr, 0, -1, -1));     // plain dA2: conv2's GroupNorm backward stays unfused
+                DBOA_TRY(wgrad(c3, 0, T + t.conv[b.c2].a));
+                const ConvLayer& cd = n.convs[b.cd];
+                DBOA_TRY(gnb(b.cd, dzo, a3, claim(1)));
+                DBOA_TRY(wgrad(cd, 1, xin));
+                DBOA_TRY(conv_backward_data(cd, B, tmp[1], P + cd.w_off, dIn, 0, sc.ws, st));
+                DBOA_TRY(gnb(b.c2, tmp[2], T + t.conv[b.c2].a, claim(3)));
+                DBOA_TRY(wgrad(c2, 3, T + t.conv[b.c1].a));
+                DBOA_TRY(conv_backward_data(c2, B, tmp[3], P + c2.w_off, claim(4), 0, sc.ws, st));
+                DBOA_TRY(gnb(b.c1, tmp[4], T + t.conv[b.c1].a, claim(5)));
+                DBOA_TRY(wgrad(c1, 5, xin));
+                DBOA_TRY(conv_backward_data(c1, B, tmp[5], P + c1.w_off, dIn, 1, sc.ws, st));
+                const Block& pb = n.blocks[bi - 1];             // seam: the previous block (last of its layer) has an identity shortcut
+                const ConvLayer& p3 = n.convs[pb.c3];
+                DBOA_TRY(gn_bwd_prep(dIn, T + t.conv[pb.c3].a, dIn, prep_of(pb.c3), B, p3.hout * p3.hout, p3.cout, st));
+            }
+            float* sw = dOut; dOut = dIn; dIn = sw;
+        }
+        DBOA_TRY(finish_fixed(0, fixed_from));
+    } else {
     for (int bi = (int)n.blocks.size() - 1; bi >= 0; --bi) {
         const Block& b = n.blocks[bi];
         const ConvLayer &c1 = n.convs[b.c1], &c2 = n.convs[b.c2], &c3 = n.convs[b.c3];
@@ -663,6 +766,7 @@ int hmr_backward(const float* P, const float* T, int B, int masked_in, const flo
         DBOA_TRY(wgrad(c1, 5, xin));
         DBOA_TRY(conv_backward_data(c1, B, tmp[5], P + c1.w_off, dIn, 1, sc.ws, st));
         float* sw = dOut; dOut = dIn; dIn = sw;
+    }
     }
     // ---- stem: maxpool, GroupNorm+ReLU, conv (weight gradient only; the image needs none)
     DBOA_TRY(maxpool3x3s2_bwd(dOut, reinterpret_cast<const unsigned char*>(T + t.p0_idx), dIn, B, 112, 112, 64, st));

@@ -55,6 +55,31 @@ int gn_acc_res_avgpool(const float* y, const float* res, const float* acc, const
 bool conv_wgrad_wide_ok(const ConvDims& d);
 int conv_wgrad_wide(const float* dy, const float* x, float* dw, const ConvDims& d, cudaStream_t st, bool pdl);
 
+// ---- dgrad_wide.cu (fused data gradient: GroupNorm backward of the operand on load, ReLU mask + the next GroupNorm backward's
+// sums in the epilogue; see the file header).  All sums are 64-bit fixed point (long long, scale 2^28), zeroed by the caller.
+struct DgradPrep {
+    const float* y;            // raw output of the layer whose GroupNorm backward is prepared [B][H][W][C]
+    const float* stats;        // its (mean, rstd) [B][4][2]
+    const float* gamma;
+    float* sums;               // long long [B][4][2]: sum q, sum q x^   (q = dz gamma)
+    float* dgb;                // long long [C][2]: d gamma, d beta
+};
+struct DgradFused {
+    const float *dz, *y_c, *w;                     // masked gradient w.r.t. GroupNorm_c's output, raw output of conv c, weights of conv c
+    const float *stats_c, *sums_c, *gamma_c;       // GroupNorm_c: (mean, rstd), backward sums (long long), gamma
+    float* dy_out;                                 // dy_c materialised for the weight gradient, or NULL
+    const float* addend;                           // added to dX before the mask (shortcut gradient), or NULL
+    float* out;                                    // mask == NULL: dX (accumulate: +=); else dz of the producing layer
+    const float* mask;                             // post-activation output of the producing layer, or NULL
+    DgradPrep prep[2];
+    int nprep, accumulate;
+};
+bool dgrad_wide_ok(const ConvDims& d);
+int dgrad_wide(const DgradFused& f, const ConvDims& d, cudaStream_t st, bool pdl);
+int gn_bwd_prep(const float* dA, const float* mask, float* out, const DgradPrep& p, int B, int HW, int C, cudaStream_t st);
+struct GnFinishItem;
+int gn_dgb_finish(const GnFinishItem* items_dev, int n_items, const float* dgb, float* G, cudaStream_t st);
+
 // ---- groupnorm.cu (single-launch cluster kernels)
 size_t gn_partial_floats(int B, int HW, int C);     // forward scratch (none; kept for the C ABI)
 size_t gn_bwd_partial_floats(int B, int HW, int C); // backward scratch: per-sample dgamma / dbeta rows

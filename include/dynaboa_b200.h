@@ -39,6 +39,9 @@ int dboa_set_tensor_core_conv(int mode);
  * GroupNorm launch per layer (round-1 plan, kept as the A/B reference).  Both fill the same tape. */
 int dboa_set_fused_forward(int enable);
 int dboa_get_fused_forward(void);
+/* the same switch for dboa_hmr_backward: 1 = fused data-gradient chain (csrc/dgrad_wide.cu: parity-green, fewer launches, but
+ * measured slower end to end), 0 (default) = GroupNorm-backward and data-gradient launches per layer */
+int dboa_set_fused_backward(int enable);
 /* CTAs (= SMs) the fused convolutions of the following dboa_hmr_forward calls may use; 0 = all.  Forwards issued side by side
  * on different streams share the device when each is given about half of it (a fused launch owns its SMs). */
 int dboa_set_forward_cta_budget(int n);
@@ -123,6 +126,26 @@ typedef struct dboa_fused_conv {
 } dboa_fused_conv;
 long long dboa_conv_fused_part_floats(int B, int Ho, int Cout);   /* size of part_out in floats (= B * 16) */
 int dboa_conv_fused_fwd(const dboa_fused_conv* probs, int nprob, int B, dboa_stream_t stream);
+
+/* Fused data gradient, the unit the backward plan is made of (csrc/dgrad_wide.cu).
+ * replaces: the autograd backward of nn.GroupNorm (layer c) -> nn.Conv2d data gradient (layer c) -> residual add -> ReLU mask of
+ * the producing layer p, + the reduction pass of GroupNorm_p's backward (model/hmr.py:40-60 under loss.backward()).
+ *   dy  = rstd (dz gamma - m1 - x^ m2)                with (m1, m2) = sums_c / N, x^ = (y_c - mean) rstd     [dy_out: optional store]
+ *   dX  = conv_c^T(dy) + addend                       stride 1, k in {1, 3}, Cin % 64 == 0, Cout % 64 == 0
+ *   mask == NULL: out (+)= dX;   else out = dz_p = dX * (mask > 0) and, for each of the nprep GroupNorms of layer p,
+ *   prep_sums[j][b][g] += (sum q, sum q x^), prep_dgb[j][c] += (d gamma, d beta) as 64-bit fixed point (scale 2^28; long long
+ *   buffers the caller zeroes; integer atomics: exact and order independent). */
+typedef struct dboa_dgrad_args {
+    const float *dz, *y_c, *w, *stats_c, *sums_c, *gamma_c;
+    float* dy_out;
+    const float* addend;
+    float* out;
+    const float* mask;
+    const float *prep_y[2], *prep_stats[2], *prep_gamma[2];
+    float *prep_sums[2], *prep_dgb[2];
+    int nprep, accumulate;
+} dboa_dgrad_args;
+int dboa_dgrad_fused(const dboa_dgrad_args* f, int B, int H, int Cin, int Cout, int k, dboa_stream_t stream);
 
 /* replaces: nn.GroupNorm(4, C) + ReLU (+ residual) forward / backward (model/hmr.py:14-18,40-60).
  * C / 16 must be a power of two; one launch each (thread-block clusters).  `partial` is caller-provided scratch of

@@ -234,3 +234,121 @@ def test_weight_gradient_on_tensor_cores_mn_major(L, case):
     ref = ref.permute(0, 2, 3, 1).reshape(Cout, K)
     assert rel_err(dw_tma - base, ref) < 2e-5, case
     assert rel_err(dw_tma - base, dw32 - base) < 2e-5, case
+
+
+DGRAD = [  # B, H, Cin, Cout, k, nprep, addend
+    (1, 56, 64, 64, 3, 1, False), (1, 56, 256, 64, 1, 1, True), (2, 28, 128, 128, 3, 1, False), (1, 28, 128, 512, 1, 0, False),
+    (1, 14, 256, 256, 3, 1, False), (3, 14, 1024, 256, 1, 2, True), (1, 7, 512, 512, 3, 1, False), (2, 7, 2048, 512, 1, 1, True),
+    (1, 7, 512, 2048, 1, 1, False), (9, 7, 512, 512, 3, 1, False)]
+FIX = 2.0 ** 28
+
+
+def _group_sums(q, xh, B):
+    """(sum q, sum q x^) per (sample, group) of an NHWC tensor pair, fp64."""
+    Cc = q.shape[-1]
+    qg = q.double().reshape(B, -1, 4, Cc // 4).permute(0, 2, 1, 3).reshape(B, 4, -1)
+    xg = xh.double().reshape(B, -1, 4, Cc // 4).permute(0, 2, 1, 3).reshape(B, 4, -1)
+    return torch.stack([qg.sum(-1), (qg * xg).sum(-1)], -1)
+
+
+def _stats(y, B):
+    Cc = y.shape[-1]
+    g = y.double().reshape(B, -1, 4, Cc // 4).permute(0, 2, 1, 3).reshape(B, 4, -1)
+    mean, var = g.mean(-1), g.var(-1, unbiased=False)
+    return torch.stack([mean, 1.0 / (var + 1e-5).sqrt()], -1)              # (B, 4, 2)
+
+
+def _expand(st, Cc):                                                         # (B,4) -> (B,1,1,C)
+    return st.repeat_interleave(Cc // 4, dim=1)[:, None, None, :]
+
+
+@pytest.mark.parametrize('case', DGRAD)
+def test_fused_data_gradient(L, case):
+    """csrc/dgrad_wide.cu against an fp64 torch restatement: GroupNorm_c backward on load, transposed convolution (MN-major weight
+    operand), shortcut addend, ReLU mask, and the fixed-point sums of the producing layer's GroupNorm backward(s)."""
+    B, H, Cin, Cout, k, nprep, with_add = case
+    g = torch.Generator().manual_seed(sum(case[:5]) + 17)
+    rn = lambda *s: torch.randn(*s, generator=g).cuda()
+    dz, y_c = rn(B, H, H, Cout) * 0.1, rn(B, H, H, Cout) + 0.2
+    gamma_c = 1 + 0.3 * rn(Cout)
+    w = rn(Cout, Cin, k, k) / (k * k * Cin) ** 0.5
+    st_c = _stats(y_c, B)
+    xh_c = (y_c.double() - _expand(st_c[..., 0], Cout)) * _expand(st_c[..., 1], Cout)
+    q_c = dz.double() * gamma_c.double()
+    sums_c = _group_sums(q_c, xh_c, B)
+    N = H * H * Cout // 4
+    dy = _expand(st_c[..., 1], Cout) * (q_c - _expand(sums_c[..., 0] / N, Cout) - xh_c * _expand(sums_c[..., 1] / N, Cout))
+    dX = torch.nn.grad.conv2d_input((B, Cin, H, H), w.double(), dy.permute(0, 3, 1, 2), padding=k // 2).permute(0, 2, 3, 1)
+    addend = rn(B, H, H, Cin) * 0.05 if with_add else None
+    if addend is not None:
+        dX = dX + addend.double()
+    f = L.DgradFusedStruct()
+    sums_c_fix = (sums_c * FIX).round().long().cuda().contiguous()
+    st_c32 = st_c.float().cuda().contiguous()
+    dy_out = torch.full((B, H, H, Cout), float('nan'), device='cuda')
+    out = torch.full((B, H, H, Cin), float('nan'), device='cuda')
+    keep = [dz, y_c, gamma_c, sums_c_fix, st_c32, dy_out, out, addend]
+    wm = wmat(w)
+    for name, t in (('dz', dz), ('y_c', y_c), ('w', wm), ('stats_c', st_c32), ('sums_c', sums_c_fix), ('gamma_c', gamma_c), ('dy_out', dy_out),
+                    ('addend', addend), ('out', out)):
+        setattr(f, name, None if t is None else t.data_ptr())
+    preps = []
+    if nprep > 0:
+        a_p = rn(B, H, H, Cin)
+        f.mask = a_p.data_ptr()
+        for j in range(nprep):
+            y_p, gamma_p = rn(B, H, H, Cin) - 0.1, 1 + 0.3 * rn(Cin)
+            st_p = _stats(y_p, B).float().cuda().contiguous()
+            sums_p = torch.zeros(B, 4, 2, dtype=torch.int64, device='cuda')
+            dgb_p = torch.zeros(Cin, 2, dtype=torch.int64, device='cuda')
+            f.prep_y[j], f.prep_stats[j], f.prep_gamma[j] = y_p.data_ptr(), st_p.data_ptr(), gamma_p.data_ptr()
+            f.prep_sums[j], f.prep_dgb[j] = sums_p.data_ptr(), dgb_p.data_ptr()
+            preps.append((y_p, gamma_p, st_p, sums_p, dgb_p))
+        keep.append(a_p)
+    f.nprep, f.accumulate = nprep, 0
+    L.call('dboa_dgrad_fused', C.byref(f), B, H, Cin, Cout, k, L.stream())
+    torch.cuda.synchronize()
+    assert rel_err(dy_out, dy) < 2e-5, case
+    if nprep == 0:
+        assert rel_err(out, dX) < 3e-5, case
+        return
+    dz_p = dX * (a_p > 0)
+    assert rel_err(out, dz_p) < 3e-5, case
+    for y_p, gamma_p, st_p, sums_p, dgb_p in preps:
+        xh = (y_p.double() - _expand(st_p[..., 0].double(), Cin)) * _expand(st_p[..., 1].double(), Cin)
+        ref_sums = _group_sums(dz_p * gamma_p.double(), xh, B)
+        got = sums_p.double() / FIX
+        assert (got - ref_sums).abs().max() <= 3e-5 * ref_sums.abs().max() + 1e-6, case
+        ref_dg, ref_db = (dz_p * xh).sum((0, 1, 2)), dz_p.sum((0, 1, 2))
+        got_g = dgb_p.double() / FIX
+        assert (got_g[:, 0] - ref_dg).abs().max() <= 3e-5 * ref_dg.abs().max() + 1e-6, case
+        assert (got_g[:, 1] - ref_db).abs().max() <= 3e-5 * ref_db.abs().max() + 1e-6, case
+
+
+def test_fused_backward_chain_matches_the_unfused_chain(L):
+    """dboa_hmr_backward through the fused data-gradient chain (dgrad_wide.cu + gn_bwd_prep seams) against the default chain, same
+    tape, B = 1, 2 and 9: the complete gradient arena."""
+    from dynaboa_b200 import hmr as hmr_mod, synthetic
+    from oracle import hmr_ref
+    m = hmr_mod.hmr(synthetic.make_mean_params()).cuda()
+    m.load_state_dict(hmr_ref.strip_prefix(synthetic.make_basemodel()['model']), strict=True)
+    m.eval()
+    lib = L.load()
+    for B in (1, 2, 9):
+        x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(40 + B)).cuda()
+        rot, shp, cam, _, tape = hmr_mod.raw_forward(m.arena, m._buffers, x)
+        dr, dsh, dc = torch.randn_like(rot), torch.randn_like(shp), torch.randn_like(cam)
+        G = []
+        for fused in (0, 1):
+            lib.dboa_set_fused_backward(fused)
+            try:
+                g = torch.zeros_like(m.arena)
+                hmr_mod.raw_backward(m.arena, tape, B, False, dr, dsh, dc, g)
+                torch.cuda.synchronize()
+                G.append(g)
+            finally:
+                lib.dboa_set_fused_backward(0)
+        assert ((G[1] - G[0]).norm() / G[0].norm()).item() < 1e-4, B
+        lay = hmr_mod.layout()
+        for name, a, b in zip(lay.names, lay.views(G[0]), lay.views(G[1])):
+            assert ((a - b).norm() <= 2e-3 * a.norm() + 1e-12), (B, name)
