@@ -17,7 +17,8 @@
 //   * TF32x3: one elementwise shared-memory pass turns the landed raw tiles into (hi in place, lo in a second tile) -- the same
 //     pass as conv_wide.cu, layout agnostic;
 //   * split-K over thread-block clusters (pixels), deterministic DSMEM reduction, then dW += tile (single writer per element).
-// Layers with Cout < 128 (stem, layer1's 64-channel outputs) and the stride-2 layers stay on conv.cu.
+// Stride 2: the X tensor map samples every second pixel (TMA element strides).  Layers with Cout < 128 (stem, layer1's
+// 64-channel outputs) stay on conv.cu.
 #include <cooperative_groups.h>
 #include <cuda.h>
 #include <stdint.h>
@@ -30,7 +31,7 @@
 namespace cg = cooperative_groups;
 
 namespace dboa {
-const void* tma_act_map(const float* x, int B, int H, int W, int C, int bw, int bh, bool atom32);      // conv_wide.cu
+const void* tma_act_map(const float* x, int B, int H, int W, int C, int bw, int bh, bool atom32, int stride);      // conv_wide.cu
 
 namespace wg {
 
@@ -42,7 +43,7 @@ constexpr int RED_LD = BN + 4;
 
 struct Launch {
     float* dw;
-    int Cin, Cout, k, pad, H, W, bh, kps, nkb_total;     // kps: k-blocks per sample; nkb_total = B * kps
+    int Cin, Cout, k, pad, stride, H, W, bh, kps, nkb_total;     // kps: k-blocks per sample; nkb_total = B * kps
     int ntn, taps, nz, per;
 };
 
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_wide_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 4; ++j) tma_load_4d(smem_u32(a + j * ATOM), &tmdy, m0 + 32 * j, 0, h0, b, &s_full[st]);
 #pragma unroll
-                for (int j = 0; j < 2; ++j) tma_load_4d(smem_u32(a + A_BYTES + j * ATOM), &tmx, n0 + 32 * j, s - L.pad, h0 + r - L.pad, b, &s_full[st]);
+                for (int j = 0; j < 2; ++j) tma_load_4d(smem_u32(a + A_BYTES + j * ATOM), &tmx, n0 + 32 * j, s - L.pad, h0 * L.stride + r - L.pad, b, &s_full[st]);
             }
         }
     } else if (warp == W_MMA) {
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_wide_kernel(const __grid_con
 
 bool conv_wgrad_wide_ok(const ConvDims& d) {
     const int W = d.Wo;
-    return d.stride == 1 && d.Ho == d.Hi && d.Wo == d.Wi && d.Ho == d.Wo && d.Cout % 128 == 0 && d.Cin % 64 == 0 && (d.kh == 1 || d.kh == 3) && d.kh == d.kw &&
+    return (d.stride == 1 || d.stride == 2) && d.Hi == d.Ho * d.stride && d.Wi == d.Wo * d.stride && d.Ho == d.Wo && d.Cout % 128 == 0 && d.Cin % 64 == 0 && (d.kh == 1 || d.kh == 3) && d.kh == d.kw &&
            d.pad == d.kh / 2 && d.Kpitch == d.kh * d.kw * d.Cin && (W == 56 || W == 28 || W == 14 || W == 7);
 }
 
@@ -276,7 +277,7 @@ int conv_wgrad_wide(const float* dy, const float* x, float* dw, const ConvDims& 
     wg::Launch L;
     memset(&L, 0, sizeof L);
     const int W = d.Wo, bh = W == 7 ? 8 : wg::KB / W;
-    L.dw = dw; L.Cin = d.Cin; L.Cout = d.Cout; L.k = d.kh; L.pad = d.pad; L.H = d.Ho; L.W = W; L.bh = bh;
+    L.dw = dw; L.Cin = d.Cin; L.Cout = d.Cout; L.k = d.kh; L.pad = d.pad; L.stride = d.stride; L.H = d.Ho; L.W = W; L.bh = bh;
     L.kps = ceil_div(d.Ho, bh); L.nkb_total = d.B * L.kps;
     L.ntn = d.Cin / wg::BN; L.taps = d.kh * d.kw;
     const int tiles = (d.Cout / wg::BM) * L.ntn * L.taps;
@@ -287,8 +288,8 @@ int conv_wgrad_wide(const float* dy, const float* x, float* dw, const ConvDims& 
     while (nz < 16 && tiles * nz * 2 <= budget && L.nkb_total / (nz * 2) >= 1) nz *= 2;
     while (nz > 1 && (nz - 1) * ceil_div(L.nkb_total, nz) >= L.nkb_total) nz >>= 1;
     L.nz = nz; L.per = ceil_div(L.nkb_total, nz);
-    const CUtensorMap* tmdy = static_cast<const CUtensorMap*>(tma_act_map(dy, d.B, d.Ho, d.Wo, d.Cout, W, bh, true));
-    const CUtensorMap* tmx = static_cast<const CUtensorMap*>(tma_act_map(x, d.B, d.Hi, d.Wi, d.Cin, W, bh, true));
+    const CUtensorMap* tmdy = static_cast<const CUtensorMap*>(tma_act_map(dy, d.B, d.Ho, d.Wo, d.Cout, W, bh, true, 1));
+    const CUtensorMap* tmx = static_cast<const CUtensorMap*>(tma_act_map(x, d.B, d.Hi, d.Wi, d.Cin, W, bh, true, d.stride));
     if (tmdy == nullptr || tmx == nullptr) return DBOA_ERR_CUDA;
     const size_t smem = 4 * (size_t)wg::STAGE + 1024 + 1024;
     return launch_ex(wg::conv_wgrad_wide_kernel, dim3(tiles * nz), dim3(wg::NT), smem, st, dim3(nz, 1, 1), pdl, L, *tmdy, *tmx);

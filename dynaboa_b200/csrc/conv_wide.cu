@@ -17,8 +17,7 @@
 //     scaled by 2^24: integer addition is associative, so the result is exact and order independent, hence deterministic);
 //     the consumer reads 8 integers instead of merging hundreds of partial triples;
 //   * output tiles are whole image rows (W x rows <= 128 pixels), so a tile is a rectangle the TMA box can address.
-// Stride-1 convolutions only (1x1, 3x3): the six stride-2 layers of the backbone run on conv_tc.cu + groupnorm.cu and hand
-// a materialised activation to the next fused layer (mode 0).
+// Stride 1 and 2 (1x1, 3x3): for stride 2 the tensor map itself samples every second pixel (TMA element strides).
 #include <cooperative_groups.h>
 #include <cuda.h>
 #include <stdint.h>
@@ -56,7 +55,7 @@ struct Problem {
     const float* gamma; const float* beta; const float* gamma2; const float* beta2;
     float* y;                    // output [B][Ho][Wo][Cout]
     unsigned long long* acc_out; // [B][4][2]
-    int Hi, Wi, Cin, Ho, Wo, Cout, k, pad;
+    int Hi, Wi, Cin, Ho, Wo, Cout, k, pad, stride;
     int bh, tps, ntiles, nclusters;
 };
 struct Launch {
@@ -154,8 +153,9 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 // tensor maps: tmx = operand x of problem 0 / 1, tmr = second operand (modes 2, 3), tmw = weights
 template <int MODE>
 __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant__ Launch L, const __grid_constant__ CUtensorMap tmx0,
-                                                          const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmr,
-                                                          const __grid_constant__ CUtensorMap tmw0, const __grid_constant__ CUtensorMap tmw1) {
+                                                          const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmr0,
+                                                          const __grid_constant__ CUtensorMap tmr1, const __grid_constant__ CUtensorMap tmw0,
+                                                          const __grid_constant__ CUtensorMap tmw1) {
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nz = L.nz, D = L.D;
@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
     const int tix = second ? cidx - L.p[0].nclusters : cidx;
     const CUtensorMap* tmx = second ? &tmx1 : &tmx0;
     const CUtensorMap* tmw = second ? &tmw1 : &tmw0;
-    const int Hi = PW(Hi), Wi = PW(Wi), Cin = PW(Cin), Ho = PW(Ho), Wo = PW(Wo), Cout = PW(Cout), ks = PW(k), pad = PW(pad);
+    const CUtensorMap* tmr = second ? &tmr1 : &tmr0;
+    const int Hi = PW(Hi), Wi = PW(Wi), Cin = PW(Cin), Ho = PW(Ho), Wo = PW(Wo), Cout = PW(Cout), ks = PW(k), pad = PW(pad), stride = PW(stride);
     const int bh = PW(bh), tps = PW(tps), ntiles = PW(ntiles);
     const int nt = tix % ntiles, bm = tix / ntiles, mt = bm % tps, b = bm / tps;
     const int h0 = mt * bh, n0 = nt * BN;
@@ -250,9 +251,10 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
                 }
                 int r, s, c;
                 tap_of(kb_begin + it, r, s, c);
-                tma_load_4d(smem_u32(slot), tmx, c, s - pad, h0 + r - pad, b, &s_full[sl]);
+                // box origin in INPUT coordinates; the tensor map samples every `stride`-th pixel (element strides)
+                tma_load_4d(smem_u32(slot), tmx, c, s - pad, h0 * stride + r - pad, b, &s_full[sl]);
                 FTI(it, 7);
-                if (HAS_RES) tma_load_4d(smem_u32(slot + A_TILE), &tmr, c, s - pad, h0 + r - pad, b, &s_full[sl]);
+                if (HAS_RES) tma_load_4d(smem_u32(slot + A_TILE), tmr, c, s - pad, h0 * stride + r - pad, b, &s_full[sl]);
             }
         } else {
             // lanes 1..31: the NEXT layer's weights DRAM -> L2 while this layer computes (each CTA takes a slice; weights are
@@ -365,7 +367,8 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
                     ga2.x *= rs2; ga2.y *= rs2; ga2.z *= rs2; ga2.w *= rs2;
                 }
             }
-            const bool desig = ks == 1 || (r == 1 && s == 1);   // the tap that visits every input pixel exactly once
+            // taps that together visit every input pixel exactly once (stride 2, 3x3: the four taps (1..2, 1..2))
+            const bool desig = ks == 1 ? stride == 1 : (stride == 1 ? (r == 1 && s == 1) : (r >= 1 && s >= 1));
             if (tid == 0) FTI(it, 0);
             mbar_wait(&s_full[sl], (uint32_t)((it / D) & 1));
             if (tid == 0) FTI(it, 1);
@@ -376,7 +379,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
                 const uint32_t off = (uint32_t)(tid + q * NTT) * 16u;
                 float4 v = *reinterpret_cast<const float4*>(slot + off);
                 if (MODE >= 1) {
-                    const int hi = h0 + oh[q] + r - pad, wi = ow[q] + s - pad;
+                    const int hi = (h0 + oh[q]) * stride + r - pad, wi = ow[q] * stride + s - pad;
                     const bool inb = (r0 + 64 * q) < rows_valid && (unsigned)hi < (unsigned)Hi && (unsigned)wi < (unsigned)Wi;
                     float4 o;
                     o.x = (v.x - mu) * ga.x + be.x; o.y = (v.y - mu) * ga.y + be.y; o.z = (v.z - mu) * ga.z + be.z; o.w = (v.w - mu) * ga.w + be.w;
@@ -571,9 +574,11 @@ static const CUtensorMap* weight_map_mn(const float* w, int K, int Cout) {
 // activation [B][H][W][C] as a 4-D tensor (C, W, H, B); box = 32 channels x W x bh rows x 1 sample, zero fill outside
 // atom32: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (32-byte chunks swizzled with the row index mod 4): the only shared-memory layout
 // tcgen05 accepts for MN-major TF32 operands (UMMA layout type SWIZZLE_128B_BASE32B)
-static const CUtensorMap* act_map(const float* x, int B, int H, int W, int C, int bw, int bh, bool atom32 = false) {
-    static std::map<std::tuple<const float*, int, int, int, int, int, int, bool>, TmHolder*> cache;
-    auto key = std::make_tuple(x, B, H, W, C, bw, bh, atom32);
+// stride: the box delivers bw x bh pixels sampled every `stride`-th pixel (boxDim = N * elementStride, as cuTensorMapEncodeTiled
+// specifies for element strides other than one)
+static const CUtensorMap* act_map(const float* x, int B, int H, int W, int C, int bw, int bh, bool atom32 = false, int stride = 1) {
+    static std::map<std::tuple<const float*, int, int, int, int, int, int, bool, int>, TmHolder*> cache;
+    auto key = std::make_tuple(x, B, H, W, C, bw, bh, atom32, stride);
     auto it = cache.find(key);
     if (it != cache.end()) return &it->second->tm;
     EncodeTiledFn enc = encode_fn();
@@ -582,8 +587,8 @@ static const CUtensorMap* act_map(const float* x, int B, int H, int W, int C, in
     TmHolder* h = new TmHolder;
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     if (enc(&h->tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete h; return nullptr; }
@@ -601,11 +606,11 @@ static int rows_of(int Ho) { return Ho * Ho <= BM ? Ho : BM / Ho; }          // 
 
 // shared with conv_wgrad_wide.cu / dgrad_wide.cu
 const void* tma_weight_map_mn(const float* w, int K, int Cout) { return wz::weight_map_mn(w, K, Cout); }
-const void* tma_act_map(const float* x, int B, int H, int W, int C, int bw, int bh, bool atom32) { return wz::act_map(x, B, H, W, C, bw, bh, atom32); }
+const void* tma_act_map(const float* x, int B, int H, int W, int C, int bw, int bh, bool atom32, int stride) { return wz::act_map(x, B, H, W, C, bw, bh, atom32, stride); }
 
 bool conv_wide_ok(const FusedConv& d) {
-    return d.Cin % 64 == 0 && d.Cout % 64 == 0 && (d.k == 1 || d.k == 3) && d.stride == 1 && d.pad == d.k / 2 && d.mode >= 0 && d.mode <= 3 &&
-           d.Ho <= wz::BM && d.Ho == d.Hi;
+    return d.Cin % 64 == 0 && d.Cout % 64 == 0 && (d.k == 1 || d.k == 3) && (d.stride == 1 || d.stride == 2) && d.pad == d.k / 2 && d.mode >= 0 &&
+           d.mode <= 3 && d.Ho <= wz::BM && d.Hi == d.Ho * d.stride && !(d.a_out != nullptr && d.k == 1 && d.stride == 2);
 }
 
 // cluster size (K-slices): largest power of two <= 16 that keeps the launch inside one wave of one CTA per SM (thread-block
@@ -647,7 +652,7 @@ int conv_wide_launch(const FusedConv* d, int nprob, int B, int nz, const float* 
     if (nprob < 1 || nprob > 2 || B < 1) return DBOA_ERR_ARG;
     wz::Launch L;
     memset(&L, 0, sizeof L);
-    const CUtensorMap *tmx[2] = {nullptr, nullptr}, *tmw[2] = {nullptr, nullptr}, *tmr = nullptr;
+    const CUtensorMap *tmx[2] = {nullptr, nullptr}, *tmw[2] = {nullptr, nullptr}, *tmr[2] = {nullptr, nullptr};
     const int K0 = d[0].k * d[0].k * d[0].Cin;
     const int nkb = K0 / wz::BK, per = ceil_div(nkb, nz);
     if (nz < 1 || nz > 16 || (nz & (nz - 1)) || (nz - 1) * per >= nkb) return DBOA_ERR_ARG;
@@ -661,22 +666,17 @@ int conv_wide_launch(const FusedConv* d, int nprob, int B, int nz, const float* 
         p.acc_in = reinterpret_cast<const long long*>(c.part_in); p.acc2_in = reinterpret_cast<const long long*>(c.part2_in);
         p.gamma = c.gamma; p.beta = c.beta; p.gamma2 = c.gamma2; p.beta2 = c.beta2;
         p.y = c.y; p.acc_out = reinterpret_cast<unsigned long long*>(c.part_out);
-        p.Hi = c.Hi; p.Wi = c.Hi; p.Cin = c.Cin; p.Ho = c.Ho; p.Wo = c.Ho; p.Cout = c.Cout; p.k = c.k; p.pad = c.pad;
+        p.Hi = c.Hi; p.Wi = c.Hi; p.Cin = c.Cin; p.Ho = c.Ho; p.Wo = c.Ho; p.Cout = c.Cout; p.k = c.k; p.pad = c.pad; p.stride = c.stride;
         p.bh = wz::rows_of(c.Ho); p.tps = ceil_div(c.Ho, p.bh); p.ntiles = c.Cout / wz::BN; p.nclusters = B * p.tps * p.ntiles;
         total += p.nclusters;
         const int tcn = c.k == 1 ? per * wz::BK : c.Cin;
         if (c.mode >= 1 && tcn > tabc) tabc = tcn;
         tmw[i] = wz::weight_map(c.w, K0, c.Cout);
-        tmx[i] = wz::act_map(c.x, B, c.Hi, c.Hi, c.Cin, c.Ho, p.bh);
-        if (tmw[i] == nullptr || tmx[i] == nullptr) return DBOA_ERR_CUDA;
+        tmx[i] = wz::act_map(c.x, B, c.Hi, c.Hi, c.Cin, c.Ho, p.bh, false, c.stride);
+        tmr[i] = c.mode >= 2 ? wz::act_map(c.res, B, c.Hi, c.Hi, c.Cin, c.Ho, p.bh, false, c.stride) : tmx[i];
+        if (tmw[i] == nullptr || tmx[i] == nullptr || tmr[i] == nullptr) return DBOA_ERR_CUDA;
     }
-    if (d[0].mode >= 2) {
-        tmr = wz::act_map(d[0].res, B, d[0].Hi, d[0].Hi, d[0].Cin, d[0].Ho, L.p[0].bh);
-        if (tmr == nullptr) return DBOA_ERR_CUDA;
-    } else {
-        tmr = tmx[0];
-    }
-    if (nprob == 1) { tmx[1] = tmx[0]; tmw[1] = tmw[0]; }
+    if (nprob == 1) { tmx[1] = tmx[0]; tmw[1] = tmw[0]; tmr[1] = tmr[0]; }
     L.nprob = nprob; L.nz = nz; L.per = per; L.tabc = tabc;
     L.next_w = next_w; L.next_bytes = (unsigned long long)next_bytes;
 #ifdef DBOA_TIMELINE
@@ -692,10 +692,10 @@ int conv_wide_launch(const FusedConv* d, int nprob, int B, int nz, const float* 
     if (smem > 227 * 1024) return DBOA_ERR_SHAPE;
     const dim3 grid(total * nz), block(wz::NT), cl(nz, 1, 1);
     switch (d[0].mode) {
-        case 0: return launch_ex(wz::conv_wide_kernel<0>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr, *tmw[0], *tmw[1]);
-        case 1: return launch_ex(wz::conv_wide_kernel<1>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr, *tmw[0], *tmw[1]);
-        case 2: return launch_ex(wz::conv_wide_kernel<2>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr, *tmw[0], *tmw[1]);
-        default: return launch_ex(wz::conv_wide_kernel<3>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr, *tmw[0], *tmw[1]);
+        case 0: return launch_ex(wz::conv_wide_kernel<0>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr[0], *tmr[1], *tmw[0], *tmw[1]);
+        case 1: return launch_ex(wz::conv_wide_kernel<1>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr[0], *tmr[1], *tmw[0], *tmw[1]);
+        case 2: return launch_ex(wz::conv_wide_kernel<2>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr[0], *tmr[1], *tmw[0], *tmw[1]);
+        default: return launch_ex(wz::conv_wide_kernel<3>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr[0], *tmr[1], *tmw[0], *tmw[1]);
     }
 }
 

@@ -30,7 +30,7 @@
 namespace cg = cooperative_groups;
 
 namespace dboa {
-const void* tma_act_map(const float* x, int B, int H, int W, int C, int bw, int bh, bool atom32);      // conv_wide.cu
+const void* tma_act_map(const float* x, int B, int H, int W, int C, int bw, int bh, bool atom32, int stride);      // conv_wide.cu
 const void* tma_weight_map_mn(const float* w, int K, int Cout);                                         // conv_wide.cu
 
 namespace dz {
@@ -548,8 +548,8 @@ int dgrad_wide(const DgradFused& f, const ConvDims& d, cudaStream_t st, bool pdl
     while (D > 1 && fixed + (size_t)D * dz::SLOT > 227 * 1024) --D;
     L.D = D;
     const size_t smem = fixed + (size_t)D * dz::SLOT;
-    const CUtensorMap* tmdz = static_cast<const CUtensorMap*>(tma_act_map(f.dz, d.B, d.Hi, d.Wi, d.Cout, d.Wi, L.bh, false));
-    const CUtensorMap* tmy = static_cast<const CUtensorMap*>(tma_act_map(f.y_c, d.B, d.Hi, d.Wi, d.Cout, d.Wi, L.bh, false));
+    const CUtensorMap* tmdz = static_cast<const CUtensorMap*>(tma_act_map(f.dz, d.B, d.Hi, d.Wi, d.Cout, d.Wi, L.bh, false, 1));
+    const CUtensorMap* tmy = static_cast<const CUtensorMap*>(tma_act_map(f.y_c, d.B, d.Hi, d.Wi, d.Cout, d.Wi, L.bh, false, 1));
     const CUtensorMap* tmw = static_cast<const CUtensorMap*>(tma_weight_map_mn(f.w, d.kh * d.kw * d.Cin, d.Cout));
     if (!tmdz || !tmy || !tmw) return DBOA_ERR_CUDA;
     return launch_ex(dz::dgrad_wide_kernel, dim3(tiles * nz), dim3(dz::NT), smem, st, dim3(nz, 1, 1), pdl, L, *tmdz, *tmy, *tmw);

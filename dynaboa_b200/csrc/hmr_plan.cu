@@ -427,10 +427,9 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
     DBOA_TRY(maxpool3x3s2_fwd(T + t.conv[0].a, T + t.p0, reinterpret_cast<unsigned char*>(T + t.p0_idx), B, 112, 112, 64, st));
     const float* x = T + t.p0;
     if (g_fused_fwd && conv_tc_enabled()) {
-        // ---- fused plan (conv_wide.cu): every stride-1 convolution applies the GroupNorm (+ residual, ReLU) of its operand on
-        // load and leaves the statistics of its output as fixed-point sums; 3 launches per bottleneck.  The six stride-2
-        // convolutions (conv2 and the shortcut of layer2.0 / 3.0 / 4.0) run on the unfused kernels and hand a materialised
-        // activation to the next fused layer.
+        // ---- fused plan (conv_wide.cu): every convolution applies the GroupNorm (+ residual, ReLU) of its operand on load and
+        // leaves the statistics of its output as fixed-point sums; 3 launches per bottleneck (conv1 and the shortcut
+        // convolution of a block share one launch).
         auto acc_of = [&](int ci) { return T + t.acc + (long long)ci * B * 16; };
         auto base_desc = [&](int ci) {
             const ConvLayer& c = n.convs[ci];
@@ -451,59 +450,36 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
             const ConvLayer* nx = next_ci >= 0 ? &n.convs[next_ci] : nullptr;
             return conv_wide_launch(d, np, B, nz, nx ? P + nx->w_off : nullptr, nx ? (size_t)nx->cout * nx->kpitch * sizeof(float) : 0, st, true);
         };
-        bool shortcut_in_t1 = false;                               // the previous block's down-sampled shortcut gn(yd) sits in sc.t1
         for (size_t bi = 0; bi < n.blocks.size(); ++bi) {
             const Block& b = n.blocks[bi];
-            const ConvLayer &c1 = n.convs[b.c1], &c2 = n.convs[b.c2];
-            const bool ds_fused = b.cd >= 0 && n.convs[b.cd].stride == 1, ds_old = b.cd >= 0 && !ds_fused;
-            // ---- conv1 (+ a stride-1 shortcut convolution in the same launch): operand = output of the previous block
+            // ---- conv1 (+ the shortcut convolution in the same launch: both read the previous block's output, formed on load)
             FusedConv d[2];
-            const int np = ds_fused ? 2 : 1;
+            const int np = b.cd >= 0 ? 2 : 1;
             const int ci[2] = {b.c1, b.cd};
-            const float* x_block = T + t.p0;                       // materialised input of this block (after the conv1 launch)
             for (int i = 0; i < np; ++i) {
                 FusedConv& f = d[i];
                 f = base_desc(ci[i]);
                 if (bi == 0) { f.mode = 0; f.x = T + t.p0; continue; }
                 const Block& pb = n.blocks[bi - 1];
                 gn_of(f, pb.c3);
-                x_block = T + t.conv[pb.c3].a;
-                if (shortcut_in_t1) {
-                    f.mode = 2; f.res = sc.t1;
-                } else if (pb.cd >= 0) {
+                if (pb.cd >= 0) {
                     const ConvLayer& pd = n.convs[pb.cd];
                     f.mode = 3; f.res = T + t.conv[pb.cd].y; f.part2_in = acc_of(pb.cd);
                     f.gamma2 = P + pd.g_off; f.beta2 = P + pd.b_off; f.stats2_out = T + t.conv[pb.cd].stats;
                 } else {
                     f.mode = 2; f.res = bi >= 2 ? T + t.conv[n.blocks[bi - 2].c3].a : T + t.p0;
                 }
-                if (i == 1) { f.a_out = nullptr; f.stats_out = nullptr; f.stats2_out = nullptr; }
+                if (i == 1) { f.a_out = nullptr; f.stats_out = nullptr; f.stats2_out = nullptr; }     // conv1 is the writer
             }
-            DBOA_TRY(run(d, np, ds_old ? b.cd : b.c2));
-            shortcut_in_t1 = false;
-            if (ds_old) {                                          // stride-2 shortcut on the unfused kernels: sc.t1 = gn(conv(x))
-                const ConvLayer& cd = n.convs[b.cd];
-                DBOA_TRY(conv_forward(cd, B, x_block, P + cd.w_off, T + t.conv[b.cd].y, sc.ws, st));
-                DBOA_TRY(gn_plain(b.cd, sc.t1, 0, nullptr));
-                shortcut_in_t1 = true;
-            }
-            // ---- conv2, conv3
-            if (c2.stride == 1) {
-                d[0] = base_desc(b.c2); gn_of(d[0], b.c1);
-                DBOA_TRY(run(d, 1, b.c3));
-                d[0] = base_desc(b.c3); gn_of(d[0], b.c2);
-            } else {
-                DBOA_TRY(gn_plain(b.c1, T + t.conv[b.c1].a, 1, nullptr));
-                DBOA_TRY(conv_forward(c2, B, T + t.conv[b.c1].a, P + c2.w_off, T + t.conv[b.c2].y, sc.ws, st));
-                DBOA_TRY(gn_plain(b.c2, T + t.conv[b.c2].a, 1, nullptr));
-                d[0] = base_desc(b.c3); d[0].mode = 0; d[0].x = T + t.conv[b.c2].a;
-            }
+            DBOA_TRY(run(d, np, b.c2));
+            d[0] = base_desc(b.c2); gn_of(d[0], b.c1);
+            DBOA_TRY(run(d, 1, b.c3));
+            d[0] = base_desc(b.c3); gn_of(d[0], b.c2);
             DBOA_TRY(run(d, 1, bi + 1 < n.blocks.size() ? n.blocks[bi + 1].c1 : -1));
-            (void)c1;
         }
         const Block& lb = n.blocks.back();
         const ConvLayer& l3 = n.convs[lb.c3];
-        if (lb.cd >= 0 || shortcut_in_t1) return DBOA_ERR_UNSUPPORTED;
+        if (lb.cd >= 0) return DBOA_ERR_UNSUPPORTED;
         DBOA_TRY(gn_acc_res_avgpool(T + t.conv[lb.c3].y, T + t.conv[n.blocks[n.blocks.size() - 2].c3].a, acc_of(lb.c3), P + l3.g_off, P + l3.b_off,
                                     T + t.conv[lb.c3].a, T + t.conv[lb.c3].stats, T + t.xc, B, 49, 2048, HEAD_LD, 3, (size_t)B * HEAD_LD, st));
     } else {

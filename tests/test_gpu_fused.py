@@ -85,10 +85,11 @@ def check_output(p, a_nchw, w_nchw, stride, pad, tag):
     assert ((var - rv).abs() / rv).max() < 3e-5, tag
 
 
-CASES = [  # B, H, Cin, Cout, k, stride, pad   (stride 1 only: the stride-2 layers stay on the unfused kernels)
+CASES = [  # B, H, Cin, Cout, k, stride, pad
     (1, 56, 64, 64, 1, 1, 0), (1, 56, 64, 256, 1, 1, 0), (1, 56, 64, 64, 3, 1, 1), (2, 28, 128, 128, 3, 1, 1), (1, 28, 512, 128, 1, 1, 0),
     (1, 14, 256, 256, 3, 1, 1), (3, 14, 1024, 256, 1, 1, 0), (1, 7, 512, 2048, 1, 1, 0), (2, 7, 2048, 512, 1, 1, 0),
-    (1, 7, 512, 512, 3, 1, 1), (9, 7, 512, 512, 3, 1, 1), (2, 28, 128, 512, 1, 1, 0)]
+    (1, 7, 512, 512, 3, 1, 1), (9, 7, 512, 512, 3, 1, 1), (2, 28, 128, 512, 1, 1, 0),
+    (1, 56, 128, 128, 3, 2, 1), (2, 28, 256, 256, 3, 2, 1), (1, 14, 512, 512, 3, 2, 1), (1, 56, 256, 512, 1, 2, 0), (3, 14, 1024, 2048, 1, 2, 0)]
 
 
 @pytest.mark.parametrize('case', CASES)
@@ -105,7 +106,8 @@ def test_plain_operand_and_statistics(L, case):
 
 CHAINS = [  # B, H, C0 (input of the producer), C1 (its output = operand channels), C2, k, stride of the consumer
     (1, 56, 64, 64, 64, 3, 1), (2, 56, 64, 128, 128, 1, 1), (1, 28, 128, 128, 512, 1, 1), (2, 14, 256, 256, 256, 3, 1), (1, 14, 256, 1024, 256, 1, 1),
-    (1, 28, 128, 128, 128, 3, 1), (3, 7, 512, 512, 2048, 1, 1), (1, 7, 512, 2048, 512, 1, 1), (2, 7, 256, 512, 512, 3, 1)]
+    (1, 28, 128, 128, 128, 3, 1), (3, 7, 512, 512, 2048, 1, 1), (1, 7, 512, 2048, 512, 1, 1), (2, 7, 256, 512, 512, 3, 1),
+    (1, 56, 64, 128, 128, 3, 2), (2, 28, 128, 256, 256, 3, 2), (1, 14, 256, 512, 512, 3, 2)]
 
 
 @pytest.mark.parametrize('case', CHAINS)
@@ -133,7 +135,7 @@ def test_groupnorm_on_load(L, case):
     check_output(p1, p1.a_out.permute(0, 3, 1, 2), w1, s, k // 2, case)
 
 
-@pytest.mark.parametrize('B,H,C,planes,stride', [(1, 56, 256, 64, 1), (2, 14, 1024, 256, 1), (1, 28, 512, 128, 1), (1, 7, 2048, 512, 1)])
+@pytest.mark.parametrize('B,H,C,planes,stride', [(1, 56, 256, 128, 2), (2, 14, 1024, 512, 2), (1, 28, 512, 128, 1), (1, 7, 2048, 512, 1), (1, 28, 512, 256, 2)])
 @pytest.mark.parametrize('mode', [2, 3])
 def test_block_output_on_load_two_problems(L, B, H, C, planes, stride, mode):
     """conv1 (+ the down-sampling 1x1 conv, second problem of the launch) of a bottleneck: the operand is the previous block's
@@ -210,27 +212,29 @@ def test_fused_forward_fills_the_same_tape_as_the_unfused_plan(L):
         assert ((G1 - G0).norm() / G0.norm()).item() < 2e-3, B
 
 
-WGRAD = [  # B, H, Cin, Cout, k
-    (1, 56, 64, 256, 1), (1, 28, 128, 128, 3), (2, 28, 512, 128, 1), (1, 14, 256, 256, 3), (3, 14, 1024, 256, 1), (1, 7, 512, 512, 3),
-    (2, 7, 512, 2048, 1), (9, 7, 2048, 512, 1), (1, 14, 256, 1024, 1)]
+WGRAD = [  # B, H (input), Cin, Cout, k, stride
+    (1, 56, 64, 256, 1, 1), (1, 28, 128, 128, 3, 1), (2, 28, 512, 128, 1, 1), (1, 14, 256, 256, 3, 1), (3, 14, 1024, 256, 1, 1), (1, 7, 512, 512, 3, 1),
+    (2, 7, 512, 2048, 1, 1), (9, 7, 2048, 512, 1, 1), (1, 14, 256, 1024, 1, 1), (1, 56, 128, 128, 3, 2), (2, 28, 256, 256, 3, 2), (1, 14, 512, 512, 3, 2),
+    (1, 56, 256, 512, 1, 2), (2, 14, 1024, 2048, 1, 2)]
 
 
 @pytest.mark.parametrize('case', WGRAD)
 def test_weight_gradient_on_tensor_cores_mn_major(L, case):
     """tcgen05 weight gradient with MN-major TMA operands (csrc/conv_wgrad_wide.cu) against the fp32 CUDA-core kernel and an fp64
     reference; dw is accumulated."""
-    B, H, Cin, Cout, k = case
+    B, H, Cin, Cout, k, st = case
     g = torch.Generator().manual_seed(sum(case) + 3)
+    Ho = H // st
     x = torch.randn(B, H, H, Cin, generator=g).cuda()
-    dy = torch.randn(B, H, H, Cout, generator=g).cuda()
+    dy = torch.randn(B, Ho, Ho, Cout, generator=g).cuda()
     K = k * k * Cin
     base = (torch.randn(Cout, K, generator=g) * 0.1).cuda()
     dw_tma, dw32 = base.clone(), base.clone()
-    L.call('dboa_conv2d_wgrad_tma', L.ptr(dy), L.ptr(x), L.ptr(dw_tma), B, H, H, Cin, Cout, k, 1, k // 2, K, L.stream())
+    L.call('dboa_conv2d_wgrad_tma', L.ptr(dy), L.ptr(x), L.ptr(dw_tma), B, H, H, Cin, Cout, k, st, k // 2, K, L.stream())
     ws = torch.empty(8 << 20, device='cuda')
-    L.call('dboa_conv2d_wgrad', L.ptr(dy), L.ptr(x), L.ptr(dw32), B, H, H, Cin, Cout, k, 1, k // 2, K, L.ptr(ws), ws.numel(), L.stream())
+    L.call('dboa_conv2d_wgrad', L.ptr(dy), L.ptr(x), L.ptr(dw32), B, H, H, Cin, Cout, k, st, k // 2, K, L.ptr(ws), ws.numel(), L.stream())
     torch.cuda.synchronize()
-    ref = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2).double(), (Cout, Cin, k, k), dy.permute(0, 3, 1, 2).double(), padding=k // 2)
+    ref = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2).double(), (Cout, Cin, k, k), dy.permute(0, 3, 1, 2).double(), stride=st, padding=k // 2)
     ref = ref.permute(0, 2, 3, 1).reshape(Cout, K)
     assert rel_err(dw_tma - base, ref) < 2e-5, case
     assert rel_err(dw_tma - base, dw32 - base) < 2e-5, case
