@@ -344,7 +344,7 @@ def run_ours(args, rank, world, local):
         roof = {'bound': 'hbm', 'kernel': f'dboa_hmr_forward b=1 ({fwd_launches} launches: fused plan -- stride-1 convs apply the GroupNorm of their operand on load)',
                 'achieved': achieved, 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': forward_traffic_mb(), 'traffic_unit': 'MB per forward (dram__bytes_read.sum + dram__bytes_write.sum, ncu capture '
-                'profiles/r01b_forward_traffic.json)', 'algorithmic_MB_per_launch': FWD_MB(1), 'ms_per_launch': fwd_ms,
+                'profiles/r02_forward_traffic.json)', 'algorithmic_MB_per_launch': FWD_MB(1), 'ms_per_launch': fwd_ms,
                 'step_model': {'algorithmic_GB_per_frame': 3.63, 'achieved_GBps': 3.63 / (ms_dev / 1000.0 / args.steps),
                                'frac': 3.63 / (ms_dev / 1000.0 / args.steps) / peak}}
         if world == 1 and not args.no_cpu_baseline:
