@@ -146,6 +146,23 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
                  "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
                  : "memory");
 }
+// shared memory through 32-bit shared-window addresses (the carve-up below goes through integer arithmetic, which makes the
+// compiler fall back to generic LD/ST with 64-bit address arithmetic otherwise)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ldc128(uint32_t a, uint32_t cta) {      // the same offset in the shared memory of CTA `cta` of the cluster
+    uint32_t ra;
+    float4 v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(cta));
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+    return v;
+}
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 #define PW(field) (second ? L.p[1].field : L.p[0].field)
@@ -309,16 +326,22 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
         // physical 16-byte chunk pc = t & 7, hence the same logical chunk lc = pc ^ (r0 & 7)) and float4 t of the weight tile
         // =====================================================================================
         const int r0 = tid >> 3, pc = tid & 7, lc = pc ^ (r0 & 7);
-        int oh[2], ow[2];                                   // output pixel (row inside the tile, column) of the two activation rows
-#pragma unroll
-        for (int q = 0; q < 2; ++q) { const int i = r0 + 64 * q; oh[q] = i / Wo; ow[q] = i - oh[q] * Wo; }
+        // per-thread invariants of the two activation rows: input coordinates of tap (0, 0), validity, tape pointer of tap (0, 0)
         float* ab = (MODE >= 1 && PW(a_out) != nullptr && nt == 0) ? PW(a_out) + (size_t)b * Hi * Wi * Cin : nullptr;
+        int hq[2], wq[2];
+        bool rowok[2];
+        float* abq[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int i = r0 + 64 * q, oh = i / Wo, ow = i - oh * Wo;
+            hq[q] = (h0 + oh) * stride - pad; wq[q] = ow * stride - pad; rowok[q] = i < rows_valid;
+            abq[q] = ab + ((long long)hq[q] * Wi + wq[q]) * Cin + lc * 4;      // only dereferenced for in-bounds taps
+        }
         int lgw = 0;
         while ((4 << lgw) < Cin) ++lgw;
         pdl_wait();
         pdl_trigger();
         FTL(2);
-        float mean[4] = {0.f, 0.f, 0.f, 0.f}, rstd[4] = {1.f, 1.f, 1.f, 1.f}, mean2[4] = {0.f, 0.f, 0.f, 0.f}, rstd2[4] = {1.f, 1.f, 1.f, 1.f};
         if (MODE >= 1) {
             // statistics of the operand's GroupNorm(s): 8 fixed-point sums per sample -> (mean, rstd)
             if (tid < (MODE == 3 ? 8 : 4)) {
@@ -330,12 +353,6 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
                 sstat[(tid >> 2) * 8 + 4 + (tid & 3)] = 1.0f / sqrtf((float)var + GN_EPS);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NTT) : "memory");
-#pragma unroll
-            for (int g = 0; g < 4; ++g) { mean[g] = sstat[g]; rstd[g] = sstat[4 + g]; }
-            if (MODE == 3) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) { mean2[g] = sstat[8 + g]; rstd2[g] = sstat[12 + g]; }
-            }
             if (mt == 0 && nt == 0 && rank == 0 && tid < 8) {
                 float* so = PW(stats_out);
                 if (so != nullptr) so[(b * 4 + (tid & 3)) * 2 + (tid >> 2)] = sstat[tid];
@@ -344,75 +361,90 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
                     if (so2 != nullptr) so2[(b * 4 + (tid & 3)) * 2 + (tid >> 2)] = sstat[8 + tid];
                 }
             }
+            // per-channel affine of the normalisation, folded once per CTA: a = x * sc + sh with sc = gamma * rstd,
+            // sh = beta - mean * sc (mode 3: the second operand's shift is folded into sh as well)
+            for (int i = tid; i < tcn; i += NTT) {
+                const int g = (tc0 + i) >> lgw;
+                const float sc = tab[i] * sstat[4 + g];
+                float sh = tab[L.tabc + i] - sstat[g] * sc;
+                if (MODE == 3) {
+                    const float sc2 = tab[2 * L.tabc + i] * sstat[12 + g];
+                    sh += tab[3 * L.tabc + i] - sstat[8 + g] * sc2;
+                    tab[2 * L.tabc + i] = sc2;
+                }
+                tab[i] = sc; tab[L.tabc + i] = sh;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NTT) : "memory");
         }
+        int r, s, c;
+        tap_of(kb_begin, r, s, c);
+        int sl = 0;
+        uint32_t ph_full = 0;
+        const uint32_t slots32 = smem_u32(slots), tab32 = smem_u32(tab), tabc4 = (uint32_t)L.tabc * 4u;
+        const uint32_t offA = (uint32_t)tid * 16u, offA2 = offA + (uint32_t)NTT * 16u;
+        const uint32_t lo_a32 = smem_u32(lo_a) + offA, lo_b32 = smem_u32(lo_b) + offA;
+        const uint32_t wofs = A_TILE * (HAS_RES ? 2 : 1);
+        uint32_t slot = slots32 + offA;                                  // this thread's first chunk inside the current slot
 #pragma unroll 1
         for (int it = 0; it < nkb; ++it) {
-            const int sl = it % D, ls = it & 1;
-            uint8_t* slot = slots + (size_t)sl * slot_bytes;
-            int r, s, c;
-            tap_of(kb_begin + it, r, s, c);
-            const int cch = c + lc * 4;                          // absolute input channel of this thread's chunk
-            float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f), ga2 = ga, be2 = be;
-            float mu = 0.f, rs = 1.f, mu2 = 0.f, rs2 = 1.f;
+            const int ls = it & 1;
+            const uint32_t ti = tab32 + (uint32_t)(c - tc0 + lc * 4) * 4u;   // this thread's chunk inside the channel table
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f), sc2 = sc;
             if (MODE >= 1) {
-                const int g = cch >> lgw, ti = cch - tc0;
-                ga = *reinterpret_cast<const float4*>(tab + ti); be = *reinterpret_cast<const float4*>(tab + L.tabc + ti);
-                mu = g == 0 ? mean[0] : (g == 1 ? mean[1] : (g == 2 ? mean[2] : mean[3]));
-                rs = g == 0 ? rstd[0] : (g == 1 ? rstd[1] : (g == 2 ? rstd[2] : rstd[3]));
-                ga.x *= rs; ga.y *= rs; ga.z *= rs; ga.w *= rs;
-                if (MODE == 3) {
-                    ga2 = *reinterpret_cast<const float4*>(tab + 2 * L.tabc + ti); be2 = *reinterpret_cast<const float4*>(tab + 3 * L.tabc + ti);
-                    mu2 = g == 0 ? mean2[0] : (g == 1 ? mean2[1] : (g == 2 ? mean2[2] : mean2[3]));
-                    rs2 = g == 0 ? rstd2[0] : (g == 1 ? rstd2[1] : (g == 2 ? rstd2[2] : rstd2[3]));
-                    ga2.x *= rs2; ga2.y *= rs2; ga2.z *= rs2; ga2.w *= rs2;
-                }
+                sc = lds128(ti); sh = lds128(ti + tabc4);
+                if (MODE == 3) sc2 = lds128(ti + 2 * tabc4);
             }
             // taps that together visit every input pixel exactly once (stride 2, 3x3: the four taps (1..2, 1..2))
-            const bool desig = ks == 1 ? stride == 1 : (stride == 1 ? (r == 1 && s == 1) : (r >= 1 && s >= 1));
+            const bool desig = ab != nullptr && (ks == 1 ? stride == 1 : (stride == 1 ? (r == 1 && s == 1) : (r >= 1 && s >= 1)));
+            const int tapoff = (r * Wi + s) * Cin + c;
             if (tid == 0) FTI(it, 0);
-            mbar_wait(&s_full[sl], (uint32_t)((it / D) & 1));
+            mbar_wait(&s_full[sl], ph_full);
             if (tid == 0) FTI(it, 1);
             if (it >= 2) mbar_wait(&l_empty[ls], (uint32_t)(((it >> 1) - 1) & 1));
             if (tid == 0) FTI(it, 2);
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const uint32_t off = (uint32_t)(tid + q * NTT) * 16u;
-                float4 v = *reinterpret_cast<const float4*>(slot + off);
-                if (MODE >= 1) {
-                    const int hi = (h0 + oh[q]) * stride + r - pad, wi = ow[q] * stride + s - pad;
-                    const bool inb = (r0 + 64 * q) < rows_valid && (unsigned)hi < (unsigned)Hi && (unsigned)wi < (unsigned)Wi;
-                    float4 o;
-                    o.x = (v.x - mu) * ga.x + be.x; o.y = (v.y - mu) * ga.y + be.y; o.z = (v.z - mu) * ga.z + be.z; o.w = (v.w - mu) * ga.w + be.w;
-                    if (MODE >= 2) {
-                        const float4 rr = *reinterpret_cast<const float4*>(slot + A_TILE + off);
-                        if (MODE == 2) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
-                        else {
-                            o.x += (rr.x - mu2) * ga2.x + be2.x; o.y += (rr.y - mu2) * ga2.y + be2.y;
-                            o.z += (rr.z - mu2) * ga2.z + be2.z; o.w += (rr.w - mu2) * ga2.w + be2.w;
-                        }
-                    }
-                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                    if (!inb) o = make_float4(0.f, 0.f, 0.f, 0.f);     // padding is zero in the ACTIVATION domain
-                    else if (ab != nullptr && desig) *reinterpret_cast<float4*>(ab + ((size_t)hi * Wi + wi) * Cin + cch) = o;
-                    v = o;
+            float4 v0 = lds128(slot), v1 = lds128(slot + NTT * 16u);
+            const float4 vw = lds128(slot + wofs);
+            if (MODE >= 1) {
+                float4 q0, q1;
+                if (MODE >= 2) { q0 = lds128(slot + A_TILE); q1 = lds128(slot + A_TILE + NTT * 16u); }
+                const bool in0 = rowok[0] && (unsigned)(hq[0] + r) < (unsigned)Hi && (unsigned)(wq[0] + s) < (unsigned)Wi;
+                const bool in1 = rowok[1] && (unsigned)(hq[1] + r) < (unsigned)Hi && (unsigned)(wq[1] + s) < (unsigned)Wi;
+                v0.x = fmaf(v0.x, sc.x, sh.x); v0.y = fmaf(v0.y, sc.y, sh.y); v0.z = fmaf(v0.z, sc.z, sh.z); v0.w = fmaf(v0.w, sc.w, sh.w);
+                v1.x = fmaf(v1.x, sc.x, sh.x); v1.y = fmaf(v1.y, sc.y, sh.y); v1.z = fmaf(v1.z, sc.z, sh.z); v1.w = fmaf(v1.w, sc.w, sh.w);
+                if (MODE == 2) {
+                    v0.x += q0.x; v0.y += q0.y; v0.z += q0.z; v0.w += q0.w;
+                    v1.x += q1.x; v1.y += q1.y; v1.z += q1.z; v1.w += q1.w;
+                } else if (MODE == 3) {
+                    v0.x = fmaf(q0.x, sc2.x, v0.x); v0.y = fmaf(q0.y, sc2.y, v0.y); v0.z = fmaf(q0.z, sc2.z, v0.z); v0.w = fmaf(q0.w, sc2.w, v0.w);
+                    v1.x = fmaf(q1.x, sc2.x, v1.x); v1.y = fmaf(q1.y, sc2.y, v1.y); v1.z = fmaf(q1.z, sc2.z, v1.z); v1.w = fmaf(q1.w, sc2.w, v1.w);
                 }
-                const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                *reinterpret_cast<float4*>(slot + off) = h;
-                *reinterpret_cast<float4*>(lo_a + ls * A_TILE + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                // padding is zero in the ACTIVATION domain
+                v0.x = in0 ? fmaxf(v0.x, 0.f) : 0.f; v0.y = in0 ? fmaxf(v0.y, 0.f) : 0.f; v0.z = in0 ? fmaxf(v0.z, 0.f) : 0.f; v0.w = in0 ? fmaxf(v0.w, 0.f) : 0.f;
+                v1.x = in1 ? fmaxf(v1.x, 0.f) : 0.f; v1.y = in1 ? fmaxf(v1.y, 0.f) : 0.f; v1.z = in1 ? fmaxf(v1.z, 0.f) : 0.f; v1.w = in1 ? fmaxf(v1.w, 0.f) : 0.f;
+                if (desig) {
+                    if (in0) *reinterpret_cast<float4*>(abq[0] + tapoff) = v0;
+                    if (in1) *reinterpret_cast<float4*>(abq[1] + tapoff) = v1;
+                }
             }
-            {
-                const uint32_t off = (uint32_t)tid * 16u;
-                uint8_t* wraw = slot + A_TILE * (HAS_RES ? 2 : 1);
-                const float4 v = *reinterpret_cast<const float4*>(wraw + off);
-                const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                *reinterpret_cast<float4*>(wraw + off) = h;
-                *reinterpret_cast<float4*>(lo_b + ls * B_TILE + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-            }
+            const float4 h0v = make_float4(tf32_hi(v0.x), tf32_hi(v0.y), tf32_hi(v0.z), tf32_hi(v0.w));
+            const float4 h1v = make_float4(tf32_hi(v1.x), tf32_hi(v1.y), tf32_hi(v1.z), tf32_hi(v1.w));
+            const float4 hw = make_float4(tf32_hi(vw.x), tf32_hi(vw.y), tf32_hi(vw.z), tf32_hi(vw.w));
+            sts128(slot, h0v);
+            sts128(slot + NTT * 16u, h1v);
+            sts128(slot + wofs, hw);
+            sts128(lo_a32 + ls * A_TILE, make_float4(v0.x - h0v.x, v0.y - h0v.y, v0.z - h0v.z, v0.w - h0v.w));
+            sts128(lo_a32 + ls * A_TILE + NTT * 16u, make_float4(v1.x - h1v.x, v1.y - h1v.y, v1.z - h1v.z, v1.w - h1v.w));
+            sts128(lo_b32 + ls * B_TILE, make_float4(vw.x - hw.x, vw.y - hw.y, vw.z - hw.z, vw.w - hw.w));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&l_full[ls]);
             if (tid == 0) FTI(it, 3);
             if (it == 0) FTL(3);
+            // next k-block: slot ring and reduction cursor (no divisions in the loop)
+            slot += slot_bytes;
+            if (++sl == D) { sl = 0; slot = slots32 + offA; ph_full ^= 1u; }
+            c += BK;
+            if (c >= Cin) { c = 0; if (++s == ks) { s = 0; ++r; } }
         }
     }
     FTL(4);
@@ -421,6 +453,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
     FTL(5);
 
     // ---- epilogue: TMEM -> shared memory (thread = row), split-K reduction over the cluster, output + statistics
+    const uint32_t red32 = smem_u32(red);
     if (warp < NTW) {
         const int q4 = warp & 3, cgp = warp >> 2;               // lane quadrant, 16-column group
         float facc[16];
@@ -428,9 +461,10 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
         for (int q = 0; q < 16; ++q) facc[q] = 0.f;
         const int nacc = nkb < NACC ? nkb : NACC;
 #pragma unroll 1
-        for (int a = 0; a < nacc; ++a) {
-            uint32_t r[16];
+        for (int a = 0; a < nacc; a += 2) {
+            uint32_t r[32];
             const uint32_t taddr = tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(a * BN + cgp * 16);
+            const bool two = a + 1 < nacc;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -438,54 +472,66 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                 : "r"(taddr)
                 : "memory");
+            if (two)
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr + (uint32_t)BN)
+                    : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int q = 0; q < 16; ++q) facc[q] += __uint_as_float(r[q]);
-        }
-        float* dstrow = red + (q4 * 32 + lane) * RED_LD + cgp * 16;
+            if (two) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4*>(dstrow + q * 4) = make_float4(facc[q * 4], facc[q * 4 + 1], facc[q * 4 + 2], facc[q * 4 + 3]);
+                for (int q = 0; q < 16; ++q) facc[q] += __uint_as_float(r[16 + q]);
+            }
+        }
+        const uint32_t dst = red32 + (uint32_t)((q4 * 32 + lane) * RED_LD + cgp * 16) * 4u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sts128(dst + q * 16, make_float4(facc[q * 4], facc[q * 4 + 1], facc[q * 4 + 2], facc[q * 4 + 3]));
     }
+    FTL(9);
     cg::cluster_group cluster = cg::this_cluster();
     if (nz == 1) __syncthreads(); else cluster.sync();
     FTL(6);
 
-    const int rows_per = BM / nz, items = rows_per * (BN / 4);
-    const int gw = Cout >> 2;
-    const int gpt = gw >= BN ? 1 : BN / gw;
-    const int lpg = 16 / gpt;
+    // rows [rank * rows_per, +rows_per) of the tile belong to this CTA: thread -> float4 column c4 of rows row0, row0 + 32, ...
+    const int rows_per = BM / nz;
+    const int gw = Cout >> 2;                               // channels per GroupNorm group of the OUTPUT
+    const int lg_lpg = gw >= BN ? 4 : (gw == 32 ? 3 : 2);   // lanes (float4 columns) per group inside the 64-column tile: 16, 8, 4
+    const int gpt = 16 >> lg_lpg;                           // groups per tile: 1, 2, 4
     // statistics of the band: every thread turns its own (count, mean, M2) -- exact about a thread-local pivot -- into 64-bit
-    // fixed-point contributions to (sum x, sum x^2); from there on everything is integer addition (warp shuffles, shared-memory
-    // atomics, two global atomics per group and CTA): associative, so the result does not depend on any order.
-    unsigned long long* sacc = reinterpret_cast<unsigned long long*>(wpart);      // [4 groups][2] in shared memory
-    if (tid < 8) sacc[tid] = 0ull;
-    __syncthreads();
+    // fixed-point contributions to (sum x, sum x^2); from there on everything is integer addition (warp shuffles, one shared
+    // slot per warp and group, two global atomics per group and CTA): associative, so the result does not depend on any order.
+    unsigned long long* wsum = reinterpret_cast<unsigned long long*>(wpart);      // [NTW][4 groups][2]
     if (warp < NTW) {
-        float* Y = PW(y) + ((size_t)b * Ho * Wo + m0) * Cout;
+        const int c4 = (tid & 15) * 4, row0 = tid >> 4;
+        int lr = rank * rows_per + row0;
+        float* Yp = PW(y) + ((size_t)b * Ho * Wo + m0 + lr) * Cout + n0 + c4;
+        const size_t ystep = (size_t)32 * Cout;
+        uint32_t ra = red32 + (uint32_t)(lr * RED_LD + c4) * 4u;
         float pv = 0.f, s1 = 0.f, s2 = 0.f;
         int cnt = 0;
 #pragma unroll 1
-        for (int v = tid; v < items; v += NTT) {
-            const int lr = rank * rows_per + (v >> 4), c4 = (v & 15) * 4;
+        for (int k = row0; k < rows_per; k += 32, lr += 32, ra += 32 * RED_LD * 4, Yp += ystep) {
             if (lr < rows_valid) {
                 float4 acc;
                 if (nz == 1) {
-                    acc = *reinterpret_cast<const float4*>(red + lr * RED_LD + c4);
+                    acc = lds128(ra);
                 } else {
-                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc = ldc128(ra, 0);
+                    const float4 q1 = ldc128(ra, 1);
+                    acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
 #pragma unroll 1
-                    for (int zb = 0; zb < nz; zb += 8) {
-                        float4 q[8];
-#pragma unroll
-                        for (int z = 0; z < 8; ++z)
-                            if (zb + z < nz) q[z] = *reinterpret_cast<const float4*>(cluster.map_shared_rank(red, zb + z) + lr * RED_LD + c4);
-#pragma unroll
-                        for (int z = 0; z < 8; ++z)
-                            if (zb + z < nz) { acc.x += q[z].x; acc.y += q[z].y; acc.z += q[z].z; acc.w += q[z].w; }
+                    for (int z = 2; z < nz; z += 2) {
+                        const float4 qa = ldc128(ra, z), qb = ldc128(ra, z + 1);
+                        acc.x += qa.x; acc.y += qa.y; acc.z += qa.z; acc.w += qa.w;
+                        acc.x += qb.x; acc.y += qb.y; acc.z += qb.z; acc.w += qb.w;
                     }
                 }
-                *reinterpret_cast<float4*>(Y + (size_t)lr * Cout + n0 + c4) = acc;
+                *reinterpret_cast<float4*>(Yp) = acc;
                 if (cnt == 0) pv = acc.x;
                 const float d0 = acc.x - pv, d1 = acc.y - pv, d2 = acc.z - pv, d3 = acc.w - pv;
                 s1 += (d0 + d1) + (d2 + d3);
@@ -493,23 +539,30 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
                 cnt += 4;
             }
         }
+        FTL(10);
         // sum x = n p + s1;  sum x^2 = s2 + 2 p s1 + n p^2   (double: exact to 2^-24 absolute after the scaling)
         const double dn = (double)cnt, dp = (double)pv, d1 = (double)s1;
         long long q1 = __double2ll_rn((dn * dp + d1) * FIX), q2 = __double2ll_rn(((double)s2 + 2.0 * dp * d1 + dn * dp * dp) * FIX);
-        // lanes of one group: the 16 / gpt float4 columns of both rows a warp covers per step
-#pragma unroll 1
-        for (int o = 16; o >= 1; o >>= 1) {
-            if (o == 16 || o < lpg) { q1 += __shfl_down_sync(0xffffffffu, q1, o); q2 += __shfl_down_sync(0xffffffffu, q2, o); }
-        }
-        if (lane < 16 && (lane % lpg) == 0) {
-            atomicAdd(&sacc[(lane / lpg) * 2], (unsigned long long)q1);
-            atomicAdd(&sacc[(lane / lpg) * 2 + 1], (unsigned long long)q2);
+        // lanes of one group: the 16 >> lg(gpt) float4 columns of both rows a warp covers per step
+        q1 += __shfl_xor_sync(0xffffffffu, q1, 16); q2 += __shfl_xor_sync(0xffffffffu, q2, 16);
+        if (lg_lpg > 3) { q1 += __shfl_xor_sync(0xffffffffu, q1, 8); q2 += __shfl_xor_sync(0xffffffffu, q2, 8); }
+        if (lg_lpg > 2) { q1 += __shfl_xor_sync(0xffffffffu, q1, 4); q2 += __shfl_xor_sync(0xffffffffu, q2, 4); }
+        q1 += __shfl_xor_sync(0xffffffffu, q1, 2); q2 += __shfl_xor_sync(0xffffffffu, q2, 2);
+        q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q2 += __shfl_xor_sync(0xffffffffu, q2, 1);
+        FTL(11);
+        if (lane < 16 && (lane & ((1 << lg_lpg) - 1)) == 0) {
+            unsigned long long* w = wsum + (warp * 4 + (lane >> lg_lpg)) * 2;
+            w[0] = (unsigned long long)q1; w[1] = (unsigned long long)q2;
         }
     }
     __syncthreads();
+    FTL(12);
     if (tid < 2 * gpt) {
         const int gi = tid >> 1, g = gw >= BN ? (nt * BN) / gw : nt * gpt + gi;
-        atomicAdd(PW(acc_out) + ((size_t)b * 4 + g) * 2 + (tid & 1), sacc[tid]);
+        unsigned long long t = 0ull;
+#pragma unroll
+        for (int w = 0; w < NTW; ++w) t += wsum[(w * 4 + gi) * 2 + (tid & 1)];
+        atomicAdd(PW(acc_out) + ((size_t)b * 4 + g) * 2 + (tid & 1), t);
     }
     FTL(7);
     if (nz > 1) cluster.sync();

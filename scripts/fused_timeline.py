@@ -47,7 +47,10 @@ for l in range(128):
     gap = (start - prev_end) / 1000.0 if prev_end is not None else 0.0
     span = (end - start) / 1000.0
     tot += span
-    print(f'        {l:5d} {rows.shape[0]:5d} | {gap:8.2f} {span:8.2f} | ' + ' '.join(f'{v:11.2f}' for v in med.tolist()))
+    ep = torch.stack([rows[:, 9] - rows[:, 5], rows[:, 6] - rows[:, 9], rows[:, 10] - rows[:, 6], rows[:, 11] - rows[:, 10],
+                      rows[:, 12] - rows[:, 11], rows[:, 7] - rows[:, 12]], 1).double().median(0).values / 1000.0
+    print(f'        {l:5d} {rows.shape[0]:5d} | {gap:8.2f} {span:8.2f} | ' + ' '.join(f'{v:11.2f}' for v in med.tolist())
+          + '  || epilogue: tmem->smem %.2f sync %.2f rows+store %.2f fixed-point+shfl %.2f smem atomics+sync %.2f global atomics %.2f' % tuple(ep.tolist()))
     prev_end = end
 print(f'sum of spans {tot:.1f} us')
 
