@@ -99,6 +99,22 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
                  "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
                  : "memory");
 }
+// shared memory through 32-bit shared-window addresses (see conv_wide.cu: the integer carve-up would otherwise cost generic LD/ST)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ldc128(uint32_t a, uint32_t cta) {      // the same offset in the shared memory of CTA `cta` of the cluster
+    uint32_t ra;
+    float4 v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(cta));
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+    return v;
+}
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 __global__ void __launch_bounds__(NT, 1) conv_wgrad_wide_kernel(const __grid_constant__ Launch L, const __grid_constant__ CUtensorMap tmdy,
@@ -180,20 +196,23 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_wide_kernel(const __grid_con
         }
     } else {
         // split pass: raw -> (hi in place, lo) at the same offsets; 2688 float4 per stage over 512 threads
+        const uint32_t raw32 = smem_u32(raw) + (uint32_t)tid * 16u;
+        constexpr uint32_t LO_OFS = 2 * STAGE, NV = STAGE / 16;
 #pragma unroll 1
         for (int it = 0; it < nkb; ++it) {
             const int st = it & 1;
             mbar_wait(&s_full[st], (uint32_t)((it >> 1) & 1));
-            float4* rp = reinterpret_cast<float4*>(raw + (size_t)st * STAGE);
-            float4* lp = reinterpret_cast<float4*>(lo + (size_t)st * STAGE);
+            const uint32_t rp = raw32 + (uint32_t)st * STAGE;
+            float4 v[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                if (j < 5 || tid + 5 * NTT < (int)NV) v[j] = lds128(rp + (uint32_t)j * NTT * 16u);
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                const int i = tid + j * NTT;
-                if (i < (int)(STAGE / 16)) {
-                    const float4 v = rp[i];
-                    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                    rp[i] = h;
-                    lp[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                if (j < 5 || tid + 5 * NTT < (int)NV) {
+                    const float4 h = make_float4(tf32_hi(v[j].x), tf32_hi(v[j].y), tf32_hi(v[j].z), tf32_hi(v[j].w));
+                    sts128(rp + (uint32_t)j * NTT * 16u, h);
+                    sts128(rp + LO_OFS + (uint32_t)j * NTT * 16u, make_float4(v[j].x - h.x, v[j].y - h.y, v[j].z - h.z, v[j].w - h.w));
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -222,40 +241,41 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_wide_kernel(const __grid_con
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = 0u;
         }
-        float* dstrow = red + (q4 * 32 + lane) * RED_LD + cgp * 16;
+        const uint32_t dst = smem_u32(red) + (uint32_t)((q4 * 32 + lane) * RED_LD + cgp * 16) * 4u;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4*>(dstrow + q * 4) = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
-                                                                     __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+            sts128(dst + q * 16, make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                                             __uint_as_float(v[q * 4 + 3])));
     }
     cg::cluster_group cluster = cg::this_cluster();
     if (nz == 1) __syncthreads(); else cluster.sync();
     if (warp < NTW) {
-        const int rows_per = BM / nz, items = rows_per * (BN / 4);
-        const int Kfull = L.k * L.k * L.Cin;
+        // rows [rank * rows_per, +rows_per) of the tile belong to this CTA: thread -> float4 column c4 of rows row0, row0 + 32, ...
+        const int rows_per = BM / nz, Kfull = L.k * L.k * L.Cin;
+        const int c4 = (tid & 15) * 4, row0 = tid >> 4;
+        int lr = rank * rows_per + row0;
+        float* dp = L.dw + (size_t)(m0 + lr) * Kfull + (size_t)tap * L.Cin + n0 + c4;
+        const size_t dstep = (size_t)32 * Kfull;
+        uint32_t ra = smem_u32(red) + (uint32_t)(lr * RED_LD + c4) * 4u;
 #pragma unroll 1
-        for (int i = tid; i < items; i += NTT) {
-            const int lr = rank * rows_per + (i >> 4), c4 = (i & 15) * 4;
+        for (int k = row0; k < rows_per; k += 32, ra += 32 * RED_LD * 4, dp += dstep) {
+            float4 cur = *reinterpret_cast<const float4*>(dp);
             float4 acc;
             if (nz == 1) {
-                acc = *reinterpret_cast<const float4*>(red + lr * RED_LD + c4);
+                acc = lds128(ra);
             } else {
-                acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                acc = ldc128(ra, 0);
+                const float4 q1 = ldc128(ra, 1);
+                acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
 #pragma unroll 1
-                for (int zb = 0; zb < nz; zb += 8) {
-                    float4 q[8];
-#pragma unroll
-                    for (int z = 0; z < 8; ++z)
-                        if (zb + z < nz) q[z] = *reinterpret_cast<const float4*>(cluster.map_shared_rank(red, zb + z) + lr * RED_LD + c4);
-#pragma unroll
-                    for (int z = 0; z < 8; ++z)
-                        if (zb + z < nz) { acc.x += q[z].x; acc.y += q[z].y; acc.z += q[z].z; acc.w += q[z].w; }
+                for (int z = 2; z < nz; z += 2) {
+                    const float4 qa = ldc128(ra, z), qb = ldc128(ra, z + 1);
+                    acc.x += qa.x; acc.y += qa.y; acc.z += qa.z; acc.w += qa.w;
+                    acc.x += qb.x; acc.y += qb.y; acc.z += qb.z; acc.w += qb.w;
                 }
             }
-            float4* dst = reinterpret_cast<float4*>(L.dw + (size_t)(m0 + lr) * Kfull + (size_t)tap * L.Cin + n0 + c4);
-            float4 cur = *dst;
             cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
-            *dst = cur;
+            *reinterpret_cast<float4*>(dp) = cur;
         }
     }
     if (nz > 1) cluster.sync();

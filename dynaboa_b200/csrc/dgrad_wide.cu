@@ -123,6 +123,28 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
                  "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
                  : "memory");
 }
+// shared memory through 32-bit shared-window addresses (see conv_wide.cu: the integer carve-up would otherwise cost generic LD/ST)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, const float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float4 ldc128(uint32_t a, uint32_t cta) {      // the same offset in the shared memory of CTA `cta` of the cluster
+    uint32_t ra;
+    float4 v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(cta));
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+    return v;
+}
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ long long to_fix(float v) { return __double2ll_rn((double)v * FIX); }
 
@@ -154,8 +176,6 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
     uint64_t* done = l_empty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
     float* sstat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);                     // [16]: mean, rstd, m1, m2 per group
-    unsigned long long* sacc = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(bars) + 256);    // [2 GN][4 groups][2]
-    unsigned long long* sgb = sacc + 16;                                                                  // [2 GN][64 channels][2]
     float* red = reinterpret_cast<float*>(lo_a);
 
     if (tid == 0) {
@@ -171,7 +191,6 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
     // gamma of layer c for the output channels this CTA reduces over (parameters: no dependency on the previous kernel)
     const int tc0 = ks == 1 ? kb_begin * BK : 0, tcn = ks == 1 ? nkb * BK : Cout;
     for (int i = tid; i < tcn; i += NT) tab[i] = __ldg(L.gamma_c + tc0 + i);
-    for (int i = tid; i < 16 + 2 * 128; i += NT) sacc[i] = 0ull;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -253,67 +272,83 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
     } else {
         // ---- transform warps: GroupNorm_c backward + TF32 split of (dz, y) -> dy hi / lo; split of the weight tile
         const int r0 = tid >> 3, pc = tid & 7, lc = pc ^ (r0 & 7);
-        int oh[2], ow[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) { const int i = r0 + 64 * q; oh[q] = i / W; ow[q] = i - oh[q] * W; }
         float* dyb = (L.dy_out != nullptr && nt == 0) ? L.dy_out + (size_t)b * H * W * Cout : nullptr;
+        int hq[2], wq[2];                                   // pixel of layer c's output the two rows read at tap (0, 0)
+        bool rowok[2];
+        float* dyq[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int i = r0 + 64 * q, oh = i / W, ow = i - oh * W;
+            hq[q] = h0 + oh + pad; wq[q] = ow + pad; rowok[q] = i < rows_valid;
+            dyq[q] = dyb + ((long long)hq[q] * W + wq[q]) * Cout + lc * 4;       // only dereferenced for in-bounds taps
+        }
         int lgw = 0;
         while ((4 << lgw) < Cout) ++lgw;
         pdl_wait();
         pdl_trigger();
-        if (tid < 4) {                                      // (mean, rstd, m1, m2) of group tid of sample b
+        // dy = rstd (dz gamma - m1 - x^ m2) = dz * A_c - (y - mean) * B_g + C_g  with A_c = gamma_c rstd, B_g = rstd^2 m2, C_g = -rstd m1
+        if (tid < 4) {
             const float* st = L.stats_c + ((size_t)b * 4 + tid) * 2;
             const long long* sm = L.sums_c + ((size_t)b * 4 + tid) * 2;
             const double N = (double)H * W * (Cout >> 2);
-            sstat[tid] = __ldcg(st); sstat[4 + tid] = __ldcg(st + 1);
-            sstat[8 + tid] = (float)((double)__ldcg(sm) / FIX / N);
-            sstat[12 + tid] = (float)((double)__ldcg(sm + 1) / FIX / N);
+            const float mu = __ldcg(st), rs = __ldcg(st + 1);
+            const float m1 = (float)((double)__ldcg(sm) / FIX / N), m2 = (float)((double)__ldcg(sm + 1) / FIX / N);
+            sstat[tid] = mu; sstat[4 + tid] = rs * rs * m2; sstat[8 + tid] = -rs * m1; sstat[12 + tid] = rs;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NTT) : "memory");
-        float gmean[4], grstd[4], gm1[4], gm2[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) { gmean[g] = sstat[g]; grstd[g] = sstat[4 + g]; gm1[g] = sstat[8 + g]; gm2[g] = sstat[12 + g]; }
+        for (int i = tid; i < tcn; i += NTT) tab[i] *= sstat[12 + ((tc0 + i) >> lgw)];
+        asm volatile("bar.sync 1, %0;" ::"n"(NTT) : "memory");
+        int r, s, c;
+        tap_of(kb_begin, r, s, c);
+        int sl = 0;
+        uint32_t ph_full = 0;
+        const uint32_t offA = (uint32_t)tid * 16u;
+        const uint32_t slots32 = smem_u32(slots) + offA, tab32 = smem_u32(tab), st32 = smem_u32(sstat);
+        const uint32_t lo_a32 = smem_u32(lo_a) + offA, lo_b32 = smem_u32(lo_b) + offA;
+        uint32_t slot = slots32;
 #pragma unroll 1
         for (int it = 0; it < nkb; ++it) {
-            const int sl = it % D, ls = it & 1;
-            uint8_t* slot = slots + (size_t)sl * SLOT;
-            int r, s, c;
-            tap_of(kb_begin + it, r, s, c);
-            const int cch = c + lc * 4, g = cch >> lgw;
-            const float4 ga = *reinterpret_cast<const float4*>(tab + (cch - tc0));
-            const float mu = g == 0 ? gmean[0] : (g == 1 ? gmean[1] : (g == 2 ? gmean[2] : gmean[3]));
-            const float rs = g == 0 ? grstd[0] : (g == 1 ? grstd[1] : (g == 2 ? grstd[2] : grstd[3]));
-            const float m1 = g == 0 ? gm1[0] : (g == 1 ? gm1[1] : (g == 2 ? gm1[2] : gm1[3]));
-            const float m2 = g == 0 ? gm2[0] : (g == 1 ? gm2[1] : (g == 2 ? gm2[2] : gm2[3]));
-            const bool desig = ks == 1 || (r == 1 && s == 1);
-            mbar_wait(&s_full[sl], (uint32_t)((it / D) & 1));
+            const int ls = it & 1;
+            const int cch = c + lc * 4;
+            const uint32_t sg = st32 + (uint32_t)(cch >> lgw) * 4u;
+            const float4 ga = lds128(tab32 + (uint32_t)(cch - tc0) * 4u);
+            const float mu = lds32(sg), gb = lds32(sg + 16), gc = lds32(sg + 32);
+            const bool desig = dyb != nullptr && (ks == 1 || (r == 1 && s == 1));
+            const int tapoff = c - (r * W + s) * Cout;
+            mbar_wait(&s_full[sl], ph_full);
             if (it >= 2) mbar_wait(&l_empty[ls], (uint32_t)(((it >> 1) - 1) & 1));
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const uint32_t off = (uint32_t)(tid + q * NTT) * 16u;
-                const float4 d = *reinterpret_cast<const float4*>(slot + off), yv = *reinterpret_cast<const float4*>(slot + A_TILE + off);
-                const int ho = h0 + oh[q] + pad - r, wo = ow[q] + pad - s;           // pixel of layer c's output this row reads
-                const bool inb = (r0 + 64 * q) < rows_valid && (unsigned)ho < (unsigned)H && (unsigned)wo < (unsigned)W;
-                float4 o;
-                o.x = rs * (d.x * ga.x - m1 - ((yv.x - mu) * rs) * m2); o.y = rs * (d.y * ga.y - m1 - ((yv.y - mu) * rs) * m2);
-                o.z = rs * (d.z * ga.z - m1 - ((yv.z - mu) * rs) * m2); o.w = rs * (d.w * ga.w - m1 - ((yv.w - mu) * rs) * m2);
-                if (!inb) o = make_float4(0.f, 0.f, 0.f, 0.f);
-                else if (dyb != nullptr && desig) *reinterpret_cast<float4*>(dyb + ((size_t)ho * W + wo) * Cout + cch) = o;
-                const float4 h = make_float4(tf32_hi(o.x), tf32_hi(o.y), tf32_hi(o.z), tf32_hi(o.w));
-                *reinterpret_cast<float4*>(slot + off) = h;
-                *reinterpret_cast<float4*>(lo_a + ls * A_TILE + off) = make_float4(o.x - h.x, o.y - h.y, o.z - h.z, o.w - h.w);
+            const float4 d0 = lds128(slot), d1 = lds128(slot + NTT * 16u);
+            const float4 y0 = lds128(slot + A_TILE), y1 = lds128(slot + A_TILE + NTT * 16u);
+            const float4 vw = lds128(slot + 2 * A_TILE);
+            const bool in0 = rowok[0] && (unsigned)(hq[0] - r) < (unsigned)H && (unsigned)(wq[0] - s) < (unsigned)W;
+            const bool in1 = rowok[1] && (unsigned)(hq[1] - r) < (unsigned)H && (unsigned)(wq[1] - s) < (unsigned)W;
+            float4 o0, o1;
+            o0.x = fmaf(mu - y0.x, gb, fmaf(d0.x, ga.x, gc)); o0.y = fmaf(mu - y0.y, gb, fmaf(d0.y, ga.y, gc));
+            o0.z = fmaf(mu - y0.z, gb, fmaf(d0.z, ga.z, gc)); o0.w = fmaf(mu - y0.w, gb, fmaf(d0.w, ga.w, gc));
+            o1.x = fmaf(mu - y1.x, gb, fmaf(d1.x, ga.x, gc)); o1.y = fmaf(mu - y1.y, gb, fmaf(d1.y, ga.y, gc));
+            o1.z = fmaf(mu - y1.z, gb, fmaf(d1.z, ga.z, gc)); o1.w = fmaf(mu - y1.w, gb, fmaf(d1.w, ga.w, gc));
+            if (!in0) o0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!in1) o1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (desig) {
+                if (in0) *reinterpret_cast<float4*>(dyq[0] + tapoff) = o0;
+                if (in1) *reinterpret_cast<float4*>(dyq[1] + tapoff) = o1;
             }
-            {
-                const uint32_t off = (uint32_t)tid * 16u;
-                uint8_t* wraw = slot + 2 * A_TILE;
-                const float4 v = *reinterpret_cast<const float4*>(wraw + off);
-                const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                *reinterpret_cast<float4*>(wraw + off) = h;
-                *reinterpret_cast<float4*>(lo_b + ls * B_TILE + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-            }
+            const float4 h0v = make_float4(tf32_hi(o0.x), tf32_hi(o0.y), tf32_hi(o0.z), tf32_hi(o0.w));
+            const float4 h1v = make_float4(tf32_hi(o1.x), tf32_hi(o1.y), tf32_hi(o1.z), tf32_hi(o1.w));
+            const float4 hw = make_float4(tf32_hi(vw.x), tf32_hi(vw.y), tf32_hi(vw.z), tf32_hi(vw.w));
+            sts128(slot, h0v);
+            sts128(slot + NTT * 16u, h1v);
+            sts128(slot + 2 * A_TILE, hw);
+            sts128(lo_a32 + ls * A_TILE, make_float4(o0.x - h0v.x, o0.y - h0v.y, o0.z - h0v.z, o0.w - h0v.w));
+            sts128(lo_a32 + ls * A_TILE + NTT * 16u, make_float4(o1.x - h1v.x, o1.y - h1v.y, o1.z - h1v.z, o1.w - h1v.w));
+            sts128(lo_b32 + ls * B_TILE, make_float4(vw.x - hw.x, vw.y - hw.y, vw.z - hw.z, vw.w - hw.w));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&l_full[ls]);
+            slot += SLOT;
+            if (++sl == D) { sl = 0; slot = slots32; ph_full ^= 1u; }
+            c += BK;
+            if (c >= Cout) { c = 0; if (++s == ks) { s = 0; ++r; } }
         }
     }
     if (nkb > 0) mbar_wait(done, 0u);
@@ -341,20 +376,28 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
 #pragma unroll
             for (int q = 0; q < 16; ++q) facc[q] += __uint_as_float(v[q]);
         }
-        float* dstrow = red + (q4 * 32 + lane) * RED_LD + cgp * 16;
+        const uint32_t dst = smem_u32(red) + (uint32_t)((q4 * 32 + lane) * RED_LD + cgp * 16) * 4u;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4*>(dstrow + q * 4) = make_float4(facc[q * 4], facc[q * 4 + 1], facc[q * 4 + 2], facc[q * 4 + 3]);
+        for (int q = 0; q < 4; ++q) sts128(dst + q * 16, make_float4(facc[q * 4], facc[q * 4 + 1], facc[q * 4 + 2], facc[q * 4 + 3]));
     }
     cg::cluster_group cluster = cg::this_cluster();
     if (nz == 1) __syncthreads(); else cluster.sync();
 
-    const int rows_per = BM / nz, items = rows_per * (BN / 4);
-    const int gw = Cin >> 2, gpt = gw >= BN ? 1 : BN / gw, lpg = 16 / gpt;
+    // rows [rank * rows_per, +rows_per) of the tile belong to this CTA: thread -> float4 column c4 of rows row0, row0 + 32, ...
+    const int rows_per = BM / nz;
+    const int gw = Cin >> 2;
+    const int lg_lpg = gw >= BN ? 4 : (gw == 32 ? 3 : 2), gpt = 16 >> lg_lpg;       // float4 columns per group inside the tile; groups per tile
     const bool prep = L.mask != nullptr;
+    // per-warp partial sums (plain stores, summed in a fixed order below): the operand slots are free after the last MMA
+    float* wsq = reinterpret_cast<float*>(slots);           // [NTW][2 GN][4 groups][2]: sum q, sum q x^
+    float* wdg = wsq + NTW * 16;                            // [NTW][2 GN][64]: d gamma
+    float* wdb = wdg + NTW * 128;                           // [NTW][64]: d beta
     if (warp < NTW) {
-        const size_t img = ((size_t)b * H * W + m0) * Cin;
-        const int c4 = (tid & 15) * 4, cabs = n0 + c4, g = cabs / gw;           // this thread's 4 channels: fixed over the loop
+        const int c4 = (tid & 15) * 4, cabs = n0 + c4, g = cabs / gw, row0 = tid >> 4;     // this thread's 4 channels: fixed over the loop
+        int lr = rank * rows_per + row0;
+        size_t e = ((size_t)b * H * W + m0 + lr) * Cin + cabs;
+        const size_t estep = (size_t)32 * Cin;
+        uint32_t ra = smem_u32(red) + (uint32_t)(lr * RED_LD + c4) * 4u;
         float4 sdg[2], sdb = make_float4(0.f, 0.f, 0.f, 0.f);
         sdg[0] = sdg[1] = make_float4(0.f, 0.f, 0.f, 0.f);
         float sq[2] = {0.f, 0.f}, sqx[2] = {0.f, 0.f};
@@ -369,26 +412,22 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
                 }
         }
 #pragma unroll 1
-        for (int v = tid; v < items; v += NTT) {
-            const int lr = rank * rows_per + (v >> 4);
+        for (int k = row0; k < rows_per; k += 32, lr += 32, ra += 32 * RED_LD * 4, e += estep) {
             if (lr < rows_valid) {
                 float4 acc;
                 if (nz == 1) {
-                    acc = *reinterpret_cast<const float4*>(red + lr * RED_LD + c4);
+                    acc = lds128(ra);
                 } else {
-                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc = ldc128(ra, 0);
+                    const float4 q1 = ldc128(ra, 1);
+                    acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
 #pragma unroll 1
-                    for (int zb = 0; zb < nz; zb += 8) {
-                        float4 q[8];
-#pragma unroll
-                        for (int z = 0; z < 8; ++z)
-                            if (zb + z < nz) q[z] = *reinterpret_cast<const float4*>(cluster.map_shared_rank(red, zb + z) + lr * RED_LD + c4);
-#pragma unroll
-                        for (int z = 0; z < 8; ++z)
-                            if (zb + z < nz) { acc.x += q[z].x; acc.y += q[z].y; acc.z += q[z].z; acc.w += q[z].w; }
+                    for (int z = 2; z < nz; z += 2) {
+                        const float4 qa = ldc128(ra, z), qb = ldc128(ra, z + 1);
+                        acc.x += qa.x; acc.y += qa.y; acc.z += qa.z; acc.w += qa.w;
+                        acc.x += qb.x; acc.y += qb.y; acc.z += qb.z; acc.w += qb.w;
                     }
                 }
-                const size_t e = img + (size_t)lr * Cin + cabs;
                 if (L.addend != nullptr) { const float4 a = __ldcg(reinterpret_cast<const float4*>(L.addend + e)); acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w; }
                 if (prep) {
                     const float4 m = __ldcg(reinterpret_cast<const float4*>(L.mask + e));
@@ -412,44 +451,56 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
             }
         }
         if (prep) {
-            // everything below is integer: per-thread sums -> 2^28 fixed point -> warp shuffles -> shared-memory atomics
+            // fixed-order reductions: warp butterflies, then one plain shared slot per warp; the cross-CTA step is integer (below)
+            const uint32_t wsq32 = smem_u32(wsq), wdg32 = smem_u32(wdg), wdb32 = smem_u32(wdb);
 #pragma unroll
             for (int j = 0; j < 2; ++j)
                 if (j < L.nprep) {
-                    long long a = to_fix(sq[j]), c = to_fix(sqx[j]);
-#pragma unroll 1
-                    for (int o = 16; o >= 1; o >>= 1)
-                        if (o == 16 || o < lpg) { a += __shfl_down_sync(0xffffffffu, a, o); c += __shfl_down_sync(0xffffffffu, c, o); }
-                    if (lane < 16 && (lane % lpg) == 0) {
-                        atomicAdd(&sacc[j * 8 + (lane / lpg) * 2], (unsigned long long)a);
-                        atomicAdd(&sacc[j * 8 + (lane / lpg) * 2 + 1], (unsigned long long)c);
+                    float a = sq[j], c = sqx[j];
+                    a += __shfl_xor_sync(0xffffffffu, a, 16); c += __shfl_xor_sync(0xffffffffu, c, 16);
+                    if (lg_lpg > 3) { a += __shfl_xor_sync(0xffffffffu, a, 8); c += __shfl_xor_sync(0xffffffffu, c, 8); }
+                    if (lg_lpg > 2) { a += __shfl_xor_sync(0xffffffffu, a, 4); c += __shfl_xor_sync(0xffffffffu, c, 4); }
+                    a += __shfl_xor_sync(0xffffffffu, a, 2); c += __shfl_xor_sync(0xffffffffu, c, 2);
+                    a += __shfl_xor_sync(0xffffffffu, a, 1); c += __shfl_xor_sync(0xffffffffu, c, 1);
+                    if (lane < 16 && (lane & ((1 << lg_lpg) - 1)) == 0) {
+                        const uint32_t w = wsq32 + (uint32_t)(((warp * 2 + j) * 4 + (lane >> lg_lpg)) * 2) * 4u;
+                        sts32(w, a); sts32(w + 4, c);
                     }
-                    // per-channel d gamma (this GroupNorm) and d beta (the same for both): rows of lanes l and l + 16
-                    long long dg[4] = {to_fix(sdg[j].x), to_fix(sdg[j].y), to_fix(sdg[j].z), to_fix(sdg[j].w)};
-                    long long db[4] = {to_fix(sdb.x), to_fix(sdb.y), to_fix(sdb.z), to_fix(sdb.w)};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { dg[e] += __shfl_down_sync(0xffffffffu, dg[e], 16); db[e] += __shfl_down_sync(0xffffffffu, db[e], 16); }
-                    if (lane < 16) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            atomicAdd(&sgb[(j * 64 + c4 + e) * 2], (unsigned long long)dg[e]);
-                            atomicAdd(&sgb[(j * 64 + c4 + e) * 2 + 1], (unsigned long long)db[e]);
-                        }
-                    }
+                    // per-channel d gamma: rows of lanes l and l + 16
+                    float4 dg = sdg[j];
+                    dg.x += __shfl_xor_sync(0xffffffffu, dg.x, 16); dg.y += __shfl_xor_sync(0xffffffffu, dg.y, 16);
+                    dg.z += __shfl_xor_sync(0xffffffffu, dg.z, 16); dg.w += __shfl_xor_sync(0xffffffffu, dg.w, 16);
+                    if (lane < 16) sts128(wdg32 + (uint32_t)((warp * 2 + j) * 64 + c4) * 4u, dg);
                 }
+            float4 db = sdb;                                 // d beta: the same for both GroupNorms
+            db.x += __shfl_xor_sync(0xffffffffu, db.x, 16); db.y += __shfl_xor_sync(0xffffffffu, db.y, 16);
+            db.z += __shfl_xor_sync(0xffffffffu, db.z, 16); db.w += __shfl_xor_sync(0xffffffffu, db.w, 16);
+            if (lane < 16) sts128(wdb32 + (uint32_t)(warp * 64 + c4) * 4u, db);
         }
     }
     __syncthreads();
     if (prep) {
-        for (int j = 0; j < L.nprep; ++j) {
-            if (tid < 2 * gpt) {
-                const int gi = tid >> 1, g = gw >= BN ? (nt * BN) / gw : nt * gpt + gi;
-                atomicAdd(L.p[j].sums + ((size_t)b * 4 + g) * 2 + (tid & 1), sacc[j * 8 + tid]);
+        // per CTA and quantity: 16 warp partials added in warp order, then ONE 64-bit fixed-point atomic (exact, order independent)
+        if (tid < 16 * L.nprep) {
+            const int j = tid >> 4, i = tid & 15, gi = i >> 1;
+            if (gi < gpt) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < NTW; ++w) t += wsq[((w * 2 + j) * 4 + gi) * 2 + (i & 1)];
+                const int g = gw >= BN ? (nt * BN) / gw : nt * gpt + gi;
+                atomicAdd(L.p[j].sums + ((size_t)b * 4 + g) * 2 + (i & 1), (unsigned long long)to_fix(t));
             }
-            if (tid >= 64 && tid < 64 + 128) {
-                const int i = tid - 64;
-                atomicAdd(L.p[j].dgb + (size_t)(n0 + (i >> 1)) * 2 + (i & 1), sgb[j * 128 + i]);
+        } else if (tid >= 64 && tid < 64 + 128 * L.nprep) {
+            const int j = (tid - 64) >> 7, i = (tid - 64) & 127, ch = i >> 1;
+            float t = 0.f;
+            if (i & 1) {
+#pragma unroll
+                for (int w = 0; w < NTW; ++w) t += wdb[w * 64 + ch];
+            } else {
+#pragma unroll
+                for (int w = 0; w < NTW; ++w) t += wdg[(w * 2 + j) * 64 + ch];
             }
+            atomicAdd(L.p[j].dgb + (size_t)(n0 + ch) * 2 + (i & 1), (unsigned long long)to_fix(t));
         }
     }
     if (nz > 1) cluster.sync();
@@ -537,7 +588,7 @@ int dgrad_wide(const DgradFused& f, const ConvDims& d, cudaStream_t st, bool pdl
     L.bh = d.Hi * d.Hi <= dz::BM ? d.Hi : dz::BM / d.Hi;
     L.tps = ceil_div(d.Hi, L.bh); L.ntiles = d.Cin / dz::BN;
     const int tiles = d.B * L.tps * L.ntiles, nkb = d.kh * d.kw * d.Cout / dz::BK;
-    static const int budget = [] { const char* e = getenv("DBOA_DGRAD_MAX_CTAS"); int v = e ? atoi(e) : 128; return v; }();
+    static const int budget = [] { const char* e = getenv("DBOA_DGRAD_MAX_CTAS"); int v = e ? atoi(e) : 64; return v; }();
     int nz = 1;
     while (nz < 16 && tiles * nz * 2 <= (budget > 2 * tiles ? budget : (2 * tiles < 128 ? 2 * tiles : 128)) && nkb / (nz * 2) >= 2) nz *= 2;
     while (nz > 1 && (nz - 1) * ceil_div(nkb, nz) >= nkb) nz >>= 1;

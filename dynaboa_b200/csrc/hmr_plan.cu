@@ -257,12 +257,13 @@ static const int g_wgrad_streams = [] { const char* e = getenv("DBOA_WGRAD_STREA
 
 static ConvDims dims_of(const ConvLayer& c, int B);
 
-// DBOA_FUSED_BWD=1 (or dboa_set_fused_backward(1)) selects the fused data-gradient chain (dgrad_wide.cu).  It is parity-green and
-// saves 96 launches per frame, but measured SLOWER end to end (C2, 1 x B200: 151.5 frames/s at best against 155.3): every fused
-// launch owns its SMs (576 threads, ~150 KB of shared memory per CTA), so the weight-gradient side streams no longer overlap
-// the chain, and the ~10 us fixed cost of a launch is not lower than GroupNorm-backward + data-gradient of round 1
-// (profiles/r02_summary.md).  Default: the round-1 chain with the tcgen05 / TMA weight gradient.
-static bool g_fused_bwd = [] { const char* e = getenv("DBOA_FUSED_BWD"); return e && e[0] == '1'; }();
+// Fused data-gradient chain (dgrad_wide.cu): GroupNorm backward on operand load, ReLU mask / residual addend / the sums of the
+// next GroupNorm backward in the epilogue -- 96 launches fewer per frame.  Default ON since the kernel went on its instruction
+// diet (32-bit shared addressing, folded coefficient tables, plain per-warp partials instead of shared CAS loops): C2, 1 x B200,
+// 178.4 frames/s against 169.9 for the round-1 chain (gn_bwd_fused -> conv dgrad -> relu_mask), profiles/r02_summary.md.
+// DBOA_FUSED_BWD=0 (or dboa_set_fused_backward(0)) selects the round-1 chain (kept as the A/B reference; same tape, same results
+// to rounding).
+static bool g_fused_bwd = [] { const char* e = getenv("DBOA_FUSED_BWD"); return !(e && e[0] == '0'); }();
 void hmr_set_fused_backward(bool on) { g_fused_bwd = on; }
 // DBOA_FUSED_FWD=0 in the environment (or dboa_set_fused_forward(0)) selects the round-1 forward: one convolution launch and
 // one GroupNorm launch per layer (kept as the A/B reference of the fused path; both fill the same tape)

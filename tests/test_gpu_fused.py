@@ -351,7 +351,7 @@ def test_fused_backward_chain_matches_the_unfused_chain(L):
                 torch.cuda.synchronize()
                 G.append(g)
             finally:
-                lib.dboa_set_fused_backward(0)
+                lib.dboa_set_fused_backward(1)
         assert ((G[1] - G[0]).norm() / G[0].norm()).item() < 1e-4, B
         lay = hmr_mod.layout()
         for name, a, b in zip(lay.names, lay.views(G[0]), lay.views(G[1])):
