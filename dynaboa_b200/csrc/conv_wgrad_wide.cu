@@ -115,6 +115,19 @@ __device__ __forceinline__ float4 ldc128(uint32_t a, uint32_t cta) {      // the
     asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
     return v;
 }
+// one lane of a converged warp (elect.sync): the compiler knows the guarded region runs on a single thread and keeps tcgen05
+// instructions on the uniform datapath without its per-thread ELECT / BRA.U.ANY wrapper loops
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 __global__ void __launch_bounds__(NT, 1) conv_wgrad_wide_kernel(const __grid_constant__ Launch L, const __grid_constant__ CUtensorMap tmdy,
@@ -172,7 +185,8 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_wide_kernel(const __grid_con
             }
         }
     } else if (warp == W_MMA) {
-        if (lane == 0 && nkb > 0) {
+        // warp-uniform loop, one elected lane issues (see conv_wide.cu)
+        if (nkb > 0) {
             // D = F32, A = B = TF32, both MN-major (bits 15, 16), N >> 3, M >> 4
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             const uint64_t draw = desc_mn(smem_u32(raw)), dlo = desc_mn(smem_u32(lo));
@@ -182,17 +196,21 @@ __global__ void __launch_bounds__(NT, 1) conv_wgrad_wide_kernel(const __grid_con
                 const int st = it & 1;
                 mbar_wait(&l_full[st], (uint32_t)((it >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t so = (uint64_t)((st * STAGE) >> 4);
+                const uint64_t so = (uint64_t)(st * (STAGE >> 4));
                 const uint64_t dah = draw + so, dbh = dah + (A_BYTES >> 4), dal = dlo + so, dbl = dal + (A_BYTES >> 4);
+                const uint32_t first = it > 0 ? 1u : 0u;
+                if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < KB / 8; ++kk) {
-                    mma_tf32(tmem_d, dah + kk * KSTEP, dbh + kk * KSTEP, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                    mma_tf32(tmem_d, dah + kk * KSTEP, dbl + kk * KSTEP, idesc, 1u);
-                    mma_tf32(tmem_d, dal + kk * KSTEP, dbh + kk * KSTEP, idesc, 1u);
+                    for (int kk = 0; kk < KB / 8; ++kk) {
+                        mma_tf32(tmem_d, dah + kk * KSTEP, dbh + kk * KSTEP, idesc, kk > 0 ? 1u : first);
+                        mma_tf32(tmem_d, dah + kk * KSTEP, dbl + kk * KSTEP, idesc, 1u);
+                        mma_tf32(tmem_d, dal + kk * KSTEP, dbh + kk * KSTEP, idesc, 1u);
+                    }
+                    umma_commit(&s_empty[st]);
                 }
-                umma_commit(&s_empty[st]);
+                __syncwarp();
             }
-            umma_commit(done);
+            if (elect_one()) umma_commit(done);
         }
     } else {
         // split pass: raw -> (hi in place, lo) at the same offsets; 2688 float4 per stage over 512 threads

@@ -163,6 +163,19 @@ __device__ __forceinline__ float4 ldc128(uint32_t a, uint32_t cta) {      // the
     asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
     return v;
 }
+// one lane of a converged warp (elect.sync): the compiler knows the guarded region runs on a single thread and keeps tcgen05
+// instructions on the uniform datapath without its per-thread ELECT / BRA.U.ANY wrapper loops
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 #define PW(field) (second ? L.p[1].field : L.p[0].field)
@@ -292,31 +305,40 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
         // ~n * 2^-25 (measured: 2e-5 after 72 k-blocks).  k-block `it` therefore goes to accumulator it % 4 (4 x 64 TMEM
         // columns); the epilogue adds the four in fp32 with round-to-nearest.
         // =====================================================================================
-        if (lane == 0 && nkb > 0) {
+        // The whole warp runs the loop (warp-uniform control flow keeps the descriptor arithmetic on the uniform datapath: under a
+        // divergent `if (lane == 0)` every tcgen05.mma paid four R2UR moves with their latency); lane 0 issues.
+        if (nkb > 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             const uint64_t dslot = desc_sw128(smem_u32(slots)), dloa = desc_sw128(smem_u32(lo_a)), dlob = desc_sw128(smem_u32(lo_b));
             constexpr uint64_t KSTEP = 32 >> 4;
+            const uint32_t slot16 = slot_bytes >> 4, wofs16 = (A_TILE * (HAS_RES ? 2 : 1)) >> 4;
+            int sl = 0;
 #pragma unroll 1
             for (int it = 0; it < nkb; ++it) {
-                const int sl = it % D, ls = it & 1;
+                const int ls = it & 1;
                 mbar_wait(&l_full[ls], (uint32_t)((it >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 FTI(it, 5);
-                const uint64_t dah = dslot + (uint64_t)((sl * slot_bytes) >> 4);
-                const uint64_t dbh = dah + (uint64_t)((A_TILE * (HAS_RES ? 2 : 1)) >> 4);
-                const uint64_t dal = dloa + (uint64_t)((ls * A_TILE) >> 4), dbl = dlob + (uint64_t)((ls * B_TILE) >> 4);
+                const uint64_t dah = dslot + (uint64_t)(sl * slot16);
+                const uint64_t dbh = dah + (uint64_t)wofs16;
+                const uint64_t dal = dloa + (uint64_t)(ls * (A_TILE >> 4)), dbl = dlob + (uint64_t)(ls * (B_TILE >> 4));
+                const uint32_t dacc = tmem_d + (uint32_t)((it & (NACC - 1)) * BN);
+                const uint32_t first = it >= NACC ? 1u : 0u;
+                if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < BK / 8; ++kk) {
-                    const uint32_t dacc = tmem_d + (uint32_t)((it & (NACC - 1)) * BN);
-                    mma_tf32(dacc, dah + kk * KSTEP, dbh + kk * KSTEP, idesc, (it >= NACC || kk > 0) ? 1u : 0u);
-                    mma_tf32(dacc, dah + kk * KSTEP, dbl + kk * KSTEP, idesc, 1u);
-                    mma_tf32(dacc, dal + kk * KSTEP, dbh + kk * KSTEP, idesc, 1u);
+                    for (int kk = 0; kk < BK / 8; ++kk) {
+                        mma_tf32(dacc, dah + kk * KSTEP, dbh + kk * KSTEP, idesc, kk > 0 ? 1u : first);
+                        mma_tf32(dacc, dah + kk * KSTEP, dbl + kk * KSTEP, idesc, 1u);
+                        mma_tf32(dacc, dal + kk * KSTEP, dbh + kk * KSTEP, idesc, 1u);
+                    }
+                    umma_commit(&l_empty[ls]);
+                    umma_commit(&s_empty[sl]);
                 }
-                umma_commit(&l_empty[ls]);
-                umma_commit(&s_empty[sl]);
+                __syncwarp();
                 FTI(it, 6);
+                if (++sl == D) sl = 0;
             }
-            umma_commit(done);
+            if (elect_one()) umma_commit(done);
         }
         pdl_wait();
         pdl_trigger();
@@ -339,6 +361,11 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
         }
         int lgw = 0;
         while ((4 << lgw) < Cin) ++lgw;
+        // everything that does not depend on the producing kernel happens before the dependency wait (double-precision
+        // divisions included: 1 / (N * 2^24) turns the fixed-point sums into means with one multiplication each)
+        const double inv_nfix = 1.0 / ((double)Hi * Wi * (Cin >> 2) * FIX);
+        int r, s, c;
+        tap_of(kb_begin, r, s, c);
         pdl_wait();
         pdl_trigger();
         FTL(2);
@@ -346,9 +373,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
             // statistics of the operand's GroupNorm(s): 8 fixed-point sums per sample -> (mean, rstd)
             if (tid < (MODE == 3 ? 8 : 4)) {
                 const long long* acc = (tid < 4 ? PW(acc_in) : PW(acc2_in)) + ((size_t)b * 4 + (tid & 3)) * 2;
-                const double N = (double)Hi * Wi * (Cin >> 2);
-                const double s1 = (double)__ldcg(acc) / FIX, s2 = (double)__ldcg(acc + 1) / FIX;
-                const double mu = s1 / N, var = fmax(s2 / N - mu * mu, 0.0);
+                const double mu = (double)__ldcg(acc) * inv_nfix, var = fmax((double)__ldcg(acc + 1) * inv_nfix - mu * mu, 0.0);
                 sstat[(tid >> 2) * 8 + (tid & 3)] = (float)mu;
                 sstat[(tid >> 2) * 8 + 4 + (tid & 3)] = 1.0f / sqrtf((float)var + GN_EPS);
             }
@@ -376,8 +401,6 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NTT) : "memory");
         }
-        int r, s, c;
-        tap_of(kb_begin, r, s, c);
         int sl = 0;
         uint32_t ph_full = 0;
         const uint32_t slots32 = smem_u32(slots), tab32 = smem_u32(tab), tabc4 = (uint32_t)L.tabc * 4u;

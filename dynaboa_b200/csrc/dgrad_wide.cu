@@ -145,6 +145,19 @@ __device__ __forceinline__ float4 ldc128(uint32_t a, uint32_t cta) {      // the
     asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
     return v;
 }
+// one lane of a converged warp (elect.sync): the compiler knows the guarded region runs on a single thread and keeps tcgen05
+// instructions on the uniform datapath without its per-thread ELECT / BRA.U.ANY wrapper loops
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ long long to_fix(float v) { return __double2ll_rn((double)v * FIX); }
 
@@ -240,32 +253,39 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
             pdl_trigger();
         }
     } else if (warp == W_MMA) {
-        if (lane == 0 && nkb > 0) {
+        // warp-uniform loop, one elected lane issues (see conv_wide.cu)
+        if (nkb > 0) {
             // D = F32, A = B = TF32, A K-major, B MN-major (bit 16), N >> 3, M >> 4
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             const uint64_t dslot = desc_sw128(smem_u32(slots)), dloa = desc_sw128(smem_u32(lo_a));
             const uint64_t dwslot = desc_mn(smem_u32(slots + 2 * A_TILE)), dlob = desc_mn(smem_u32(lo_b));
             constexpr uint64_t KSTEP_A = 32 >> 4;            // 8 channels = 32 bytes inside the 128-byte row
             constexpr uint64_t KSTEP_B = 1024 >> 4;          // 8 output channels = 8 rows of the MN-major tile
+            int sl = 0;
 #pragma unroll 1
             for (int it = 0; it < nkb; ++it) {
-                const int sl = it % D, ls = it & 1;
+                const int ls = it & 1;
                 mbar_wait(&l_full[ls], (uint32_t)((it >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t so = (uint64_t)((sl * SLOT) >> 4);
+                const uint64_t so = (uint64_t)(sl * (SLOT >> 4));
                 const uint64_t dah = dslot + so, dbh = dwslot + so;
-                const uint64_t dal = dloa + (uint64_t)((ls * A_TILE) >> 4), dbl = dlob + (uint64_t)((ls * B_TILE) >> 4);
+                const uint64_t dal = dloa + (uint64_t)(ls * (A_TILE >> 4)), dbl = dlob + (uint64_t)(ls * (B_TILE >> 4));
+                const uint32_t dacc = tmem_d + (uint32_t)((it & (NACC - 1)) * BN);      // truncating accumulation: short chains
+                const uint32_t first = it >= NACC ? 1u : 0u;
+                if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < BK / 8; ++kk) {
-                    const uint32_t dacc = tmem_d + (uint32_t)((it & (NACC - 1)) * BN);      // truncating accumulation: short chains
-                    mma_tf32(dacc, dah + kk * KSTEP_A, dbh + kk * KSTEP_B, idesc, (it >= NACC || kk > 0) ? 1u : 0u);
-                    mma_tf32(dacc, dah + kk * KSTEP_A, dbl + kk * KSTEP_B, idesc, 1u);
-                    mma_tf32(dacc, dal + kk * KSTEP_A, dbh + kk * KSTEP_B, idesc, 1u);
+                    for (int kk = 0; kk < BK / 8; ++kk) {
+                        mma_tf32(dacc, dah + kk * KSTEP_A, dbh + kk * KSTEP_B, idesc, kk > 0 ? 1u : first);
+                        mma_tf32(dacc, dah + kk * KSTEP_A, dbl + kk * KSTEP_B, idesc, 1u);
+                        mma_tf32(dacc, dal + kk * KSTEP_A, dbh + kk * KSTEP_B, idesc, 1u);
+                    }
+                    umma_commit(&l_empty[ls]);
+                    umma_commit(&s_empty[sl]);
                 }
-                umma_commit(&l_empty[ls]);
-                umma_commit(&s_empty[sl]);
+                __syncwarp();
+                if (++sl == D) sl = 0;
             }
-            umma_commit(done);
+            if (elect_one()) umma_commit(done);
         }
         pdl_wait();
         pdl_trigger();
@@ -284,22 +304,22 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
         }
         int lgw = 0;
         while ((4 << lgw) < Cout) ++lgw;
+        const double inv_nfix = 1.0 / ((double)H * W * (Cout >> 2) * FIX);      // before the wait: no division after it
+        int r, s, c;
+        tap_of(kb_begin, r, s, c);
         pdl_wait();
         pdl_trigger();
         // dy = rstd (dz gamma - m1 - x^ m2) = dz * A_c - (y - mean) * B_g + C_g  with A_c = gamma_c rstd, B_g = rstd^2 m2, C_g = -rstd m1
         if (tid < 4) {
             const float* st = L.stats_c + ((size_t)b * 4 + tid) * 2;
             const long long* sm = L.sums_c + ((size_t)b * 4 + tid) * 2;
-            const double N = (double)H * W * (Cout >> 2);
             const float mu = __ldcg(st), rs = __ldcg(st + 1);
-            const float m1 = (float)((double)__ldcg(sm) / FIX / N), m2 = (float)((double)__ldcg(sm + 1) / FIX / N);
+            const float m1 = (float)((double)__ldcg(sm) * inv_nfix), m2 = (float)((double)__ldcg(sm + 1) * inv_nfix);
             sstat[tid] = mu; sstat[4 + tid] = rs * rs * m2; sstat[8 + tid] = -rs * m1; sstat[12 + tid] = rs;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NTT) : "memory");
         for (int i = tid; i < tcn; i += NTT) tab[i] *= sstat[12 + ((tc0 + i) >> lgw)];
         asm volatile("bar.sync 1, %0;" ::"n"(NTT) : "memory");
-        int r, s, c;
-        tap_of(kb_begin, r, s, c);
         int sl = 0;
         uint32_t ph_full = 0;
         const uint32_t offA = (uint32_t)tid * 16u;
