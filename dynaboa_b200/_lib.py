@@ -23,7 +23,7 @@ class SmplModelStruct(C.Structure):
 class LossArgsStruct(C.Structure):
     _fields_ = ([('B', I)] + [(n, P) for n in ('p2d', 'j3d', 'R', 'beta', 'kp', 'prior_b', 't_p2d', 't_j3d', 't_beta',
                                                  't_R', 'gt_s3d')]
-                + [('w', F * 8), ('terms', P), ('dp2d', P), ('dj3d', P), ('dR', P), ('dbeta', P), ('dR_accumulate', I)])
+                + [('w', F * 8), ('terms', P), ('dp2d', P), ('dj3d', P), ('dR', P), ('dbeta', P), ('dR_accumulate', I), ('kp_first', I), ('kp_count', I)])
 
 
 class FusedConvStruct(C.Structure):
@@ -88,6 +88,7 @@ SIGNATURES = {
     'dboa_gmm_prior': (I, [P, P, P, P, P, P, F, I, P]),
     'dboa_loss_multi': (I, [C.POINTER(LossArgsStruct), P]),
     'dboa_loss_motion': (I, [P, P, P, P, F, P, P, P, I, I, P]),
+    'dboa_loss_motion_joints': (I, [P, P, P, P, F, P, P, P, I, I, I, I, P]),
     'dboa_sgd_update': (I, [P, P, P, F, L, P]),
     'dboa_adam_ema': (I, [P, P, P, P, P, L, F, F, F, F, I, F, P]),
     'dboa_ema_update': (I, [P, P, L, F, P]),

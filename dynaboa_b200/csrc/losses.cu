@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(256) loss_multi_kernel(LossArgs a) {
     __shared__ float red[32];
     __shared__ float sterm[8];
     const int t = threadIdx.x, B = a.B;
+    const int kf = a.kp_count > 0 ? a.kp_first : 25, kn = a.kp_count > 0 ? a.kp_count : 24;      // joints of the re-projection term
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
     // ---- 2D terms over (b, joint, xy)
@@ -166,12 +167,12 @@ __global__ void __launch_bounds__(256) loss_multi_kernel(LossArgs a) {
         const int j = (i / 2) % 49, b = i / 98;
         const float p = a.p2d[i];
         float g = 0.f;
-        if (a.kp != nullptr && j >= 25) {
+        if (a.kp != nullptr && j >= kf && j < kf + kn) {
             const float conf = a.kp[(size_t)(b * 49 + j) * 3 + 2];
             const float k = a.kp[(size_t)(b * 49 + j) * 3 + (i & 1)];
             const float d = p - k;
             acc[0] += d * d * conf;
-            g += a.w[0] * 2.0f * conf * d / (float)(B * 48);
+            g += a.w[0] * 2.0f * conf * d / (float)(B * kn * 2);
         }
         if (a.t_p2d != nullptr) {
             const float d = p - a.t_p2d[i];
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(256) loss_multi_kernel(LossArgs a) {
             }
     }
     // ---- scalar terms
-    const float norm[8] = {1.0f / (B * 48), 1.0f / B, 1.0f, 1.0f / (B * 98), 1.0f / (B * 147), 1.0f / (B * 10), 1.0f / (B * 216),
+    const float norm[8] = {1.0f / (B * kn * 2), 1.0f / B, 1.0f, 1.0f / (B * 98), 1.0f / (B * 147), 1.0f / (B * 10), 1.0f / (B * 216),
                            1.0f / (B * 72)};
     for (int k = 0; k < 8; ++k) {
         float s = block_sum(acc[k], red);
@@ -257,40 +258,43 @@ __global__ void __launch_bounds__(256) loss_multi_kernel(LossArgs a) {
 }
 int loss_multi_launch(const LossArgs& a, cudaStream_t st) {
     if (a.B < 1 || a.B > 256) return DBOA_ERR_SHAPE;
+    if (a.kp_count < 0 || a.kp_first < 0 || a.kp_first + a.kp_count > 49) return DBOA_ERR_ARG;
     return launch_ex(loss_multi_kernel, dim3(1), dim3(256), 0, st, dim3(1, 1, 1), true, a);
 }
 
 // ---------------------------------------------------------------------------------------------
 // motion loss between the current prediction (a) and the prediction on the history frame (h)
-//   L = mean_{B*24*2} [conf_a + conf_h == 2] * ((pa - ph) - (ka - kh))^2   on joints 25..48
+//   L = mean_{B*count*2} [conf_a + conf_h == 2] * ((pa - ph) - (ka - kh))^2   on joints [first, first + count)  (benchmark: 25..48)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) loss_motion_kernel(const float* __restrict__ pa, const float* __restrict__ ph,
                                                           const float* __restrict__ ka, const float* __restrict__ kh, float w,
                                                           float* __restrict__ term, float* __restrict__ dpa, float* __restrict__ dph,
-                                                          int B, int acc_a) {
+                                                          int B, int acc_a, int first, int count) {
     pdl_wait();
     pdl_trigger();
     __shared__ float red[32];
     float acc = 0.f;
+    const float n = (float)(B * count * 2);
     for (int i = threadIdx.x; i < B * 98; i += 256) {
         const int j = (i / 2) % 49, b = i / 98;
         float g = 0.f;
-        if (j >= 25) {
+        if (j >= first && j < first + count) {
             const size_t kb = (size_t)(b * 49 + j) * 3;
             const float conf = (ka[kb + 2] + kh[kb + 2]) == 2.0f ? 1.0f : 0.0f;
             const float d = (pa[i] - ph[i]) - (ka[kb + (i & 1)] - kh[kb + (i & 1)]);
             acc += conf * d * d;
-            g = w * 2.0f * conf * d / (float)(B * 48);
+            g = w * 2.0f * conf * d / n;
         }
         dpa[i] = acc_a ? dpa[i] + g : g;
         dph[i] = -g;
     }
     acc = block_sum(acc, red);
-    if (threadIdx.x == 0) term[0] = acc / (float)(B * 48);
+    if (threadIdx.x == 0) term[0] = acc / n;
 }
 int loss_motion_launch(const float* pa, const float* ph, const float* ka, const float* kh, float w, float* term, float* dpa, float* dph,
-                       int B, int acc_a, cudaStream_t st) {
-    return launch_ex(loss_motion_kernel, dim3(1), dim3(256), 0, st, dim3(1, 1, 1), true, pa, ph, ka, kh, w, term, dpa, dph, B, acc_a);
+                       int B, int acc_a, int first, int count, cudaStream_t st) {
+    if (first < 0 || count < 1 || first + count > 49) return DBOA_ERR_ARG;
+    return launch_ex(loss_motion_kernel, dim3(1), dim3(256), 0, st, dim3(1, 1, 1), true, pa, ph, ka, kh, w, term, dpa, dph, B, acc_a, first, count);
 }
 
 }  // namespace dboa

@@ -94,6 +94,7 @@ def _loss_head(ad, p, w, kp=None, t_p2d=None, t_j3d=None, t_beta=None, t_R=None,
     for i in range(8):
         a.w[i] = float(w[i])
     a.dR_accumulate = 1 if prior_b is not None else 0
+    a.kp_first, a.kp_count = getattr(ad, 'kp_range', (25, 24))      # joints of the re-projection term (webcam client: (0, 25))
     _lib.call('dboa_loss_multi', C.byref(a), stream())
     return terms, dp2d, dj3d, dR, dbeta
 
@@ -197,8 +198,9 @@ def level_backward(ad, arena, buffers, image, kp, lower, grad_arena, main=None, 
         mterm = torch.empty(1, dtype=torch.float32, device=image.device)
         p_hist = main.p2d[nb:] if batched else hist.p2d
         dph = dp2d[nb:] if batched else torch.empty_like(hist.p2d)
-        _lib.call('dboa_loss_motion', ptr(main.p2d), ptr(p_hist), ptr(kp), ptr(hist_kp.contiguous()), float(o.motionloss_weight), ptr(mterm),
-                  ptr(dp2d), ptr(dph), nb, 1, stream())
+        kf, kn = getattr(ad, 'kp_range', (25, 24))
+        _lib.call('dboa_loss_motion_joints', ptr(main.p2d), ptr(p_hist), ptr(kp), ptr(hist_kp.contiguous()), float(o.motionloss_weight),
+                  ptr(mterm), ptr(dp2d), ptr(dph), nb, 1, kf, kn, stream())
         if not batched:
             backward_graph(ad, arena, hist, dph, torch.zeros_like(hist.joints), torch.zeros_like(hist.rot), torch.zeros_like(hist.shape),
                            grad_arena)

@@ -209,10 +209,16 @@ typedef struct dboa_loss_args {
     float* terms;                           /* (9,) out: the 8 unweighted terms, then the weighted total */
     float *dp2d, *dj3d, *dR, *dbeta;        /* out: gradients of the weighted total (NULL to skip) */
     int dR_accumulate;                      /* 1: dR already holds the pose-prior gradient */
+    int kp_first, kp_count;                 /* joints [kp_first, kp_first + kp_count) of the 49 carry the 2D re-projection term; 0, 0 = the
+                                               benchmark's 24 ground-truth joints (25, 24); the webcam client compares the 25 OpenPose
+                                               joints (0, 25), reference dynaboa_webcam.py:236,246,262 */
 } dboa_loss_args;
 int dboa_loss_multi(const dboa_loss_args* args, dboa_stream_t stream);        /* :234-241,283-291,331-337,360-370,401,412-422 */
 int dboa_loss_motion(const float* p_cur, const float* p_hist, const float* kp_cur, const float* kp_hist, float weight, float* term,
                      float* dp_cur, float* dp_hist, int B, int accumulate_cur, dboa_stream_t stream);               /* :379-398 */
+/* the same on joints [first, first + count): reference dynaboa_webcam.py:161-181 uses the 25 OpenPose joints (0, 25) */
+int dboa_loss_motion_joints(const float* p_cur, const float* p_hist, const float* kp_cur, const float* kp_hist, float weight, float* term,
+                            float* dp_cur, float* dp_hist, int B, int accumulate_cur, int first, int count, dboa_stream_t stream);
 
 /* ---- whole-model sweeps, feature test, retrieval -------------------------------------------- */
 int dboa_sgd_update(const float* p, const float* g, float* out, float lr, long long n, dboa_stream_t stream);   /* l2l maml_update */

@@ -514,6 +514,105 @@ def golden_eval():
     print('eval_metrics.npz', mpjpe, pampjpe, pve)
 
 
+# ---------------------------------------------------------------------------------------
+# part 3: the webcam client -- the reference ``Adaptor`` CLASS of dynaboa_webcam.py executed unmodified on CPU
+# ---------------------------------------------------------------------------------------
+def _load_webcam_class():
+    """dynaboa_webcam.py cannot be imported (cv2, OpenPose bindings, an ffmpeg loop at import): take its ``Adaptor`` class
+    definition out of the syntax tree and execute exactly that, in a namespace holding the names its methods use."""
+    import ast
+    from torchvision.transforms import Normalize
+    sys.path.insert(0, REF)
+    geometry = importlib.import_module('utils.geometry')
+    model = importlib.import_module('model')
+    prior = importlib.import_module('utils.smplify.prior')
+    path = os.path.join(REF, 'dynaboa_webcam.py')
+    tree = ast.parse(open(path).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == 'Adaptor')
+    ns = dict(torch=torch, nn=torch.nn, F=torch.nn.functional, np=np, random=random, os=os, l2l=sys.modules['learn2learn'],
+              Normalize=Normalize, constants=importlib.import_module('constants'), config=importlib.import_module('config'),
+              hmr=model.hmr, SMPL=model.SMPL, MaxMixturePrior=prior.MaxMixturePrior,
+              perspective_projection=geometry.perspective_projection,
+              rotation_matrix_to_angle_axis=geometry.rotation_matrix_to_angle_axis, crop=None, transform=None)
+    exec(compile(ast.Module(body=[cls], type_ignores=[]), path, 'exec'), ns)
+    return ns['Adaptor'], ns
+
+
+def webcam_detections(batch, t):
+    """(B, 25, 3) OpenPose-style detections of a synthetic frame: the projected OpenPose joints with noise, some of them
+    undetected (confidence 0) in a pattern that changes from frame to frame."""
+    kp = batch['op_j2d'][:, :25].clone()
+    kp[:, (3 * t) % 25, 2] = 0.0
+    kp[:, (7 * t + 11) % 25, 2] = 0.0
+    return kp
+
+
+def golden_webcam(workdir, n_frames=6):
+    from . import webcam_ref
+    opts = webcam_ref.webcam_options(interval=2, dynamic_boa=1, cos_sim_threshold=1e-7, optim_steps=2)
+    opts.model_file, opts.test_basemodel = 'data/basemodel.pt', 0
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    try:
+        if not os.path.exists('data/gmm_08.pkl'):
+            os.symlink(os.path.join(REF, 'data/gmm_08.pkl'), 'data/gmm_08.pkl')
+        RefAdaptor, ns = _load_webcam_class()
+        ad = RefAdaptor.__new__(RefAdaptor)
+        ad.options, ad.device = opts, torch.device('cpu')
+        ad.seed_everything(opts.seed)
+        ad.history, ad.global_step = {}, 0
+        # _initialize_training (:45-83) with the device fixed to the CPU instead of 'cuda'
+        ck = torch.load(opts.model_file, weights_only=False)
+        ad.model = ns['l2l'].algorithms.MAML(ns['hmr'](ns['config'].SMPL_MEAN_PARAMS), lr=opts.fastlr, first_order=True)
+        ad.model.load_state_dict(ck['model'], strict=True)
+        ad.model.eval()
+        ad.teacher = ns['hmr'](ns['config'].SMPL_MEAN_PARAMS)
+        for p in ad.teacher.parameters():
+            p.detach_()
+        ad.teacher.load_state_dict({k.replace('module.', ''): v for k, v in ck['model'].items()}, strict=True)
+        ad.teacher.eval()
+        ad.optimizer = torch.optim.Adam(ad.model.parameters(), lr=opts.lr, betas=(opts.beta1, opts.beta2))
+        ad.gmm_f = ns['MaxMixturePrior'](prior_folder='data/', num_gaussians=8, dtype=torch.float32)
+        ad.smpl_neutral = ns['SMPL'](ns['config'].SMPL_MODEL_DIR, create_transl=False)
+    finally:
+        os.chdir(cwd)
+    oracle = webcam_ref.OracleWebcam(
+        opts, synthetic.make_basemodel(), {g: synthetic.make_smpl_model(g) for g in ('neutral', 'male', 'female')},
+        synthetic.make_extra_regressors(), dict(np.load(os.path.join(REPO, 'dynaboa_b200/assets/gmm_08.npz'))),
+        joint_map=C.JOINT_MAP_49, vertex_ids=C.SMPL_EXTRA_VERTEX_IDS, h36m_to_j14=C.H36M_TO_J14)
+    stream = synthetic.SyntheticStream(length=n_frames, batch_size=1)
+    names = [k for k, _ in ad.model.module.named_parameters()]
+    rec = {k: [] for k in ('kp25', 'verts_sub', 'cam', 'theta_samples', 'dyn_steps')}
+    n_outer = 0
+    for t in range(n_frames):
+        batch = stream[t]
+        kp = webcam_detections(batch, t)
+        # the input processing (:197-218) is replaced by already processed tensors: skimage is not in this image, the crop is
+        # pinned separately (golden_dataprocess); everything from save_hist on is the reference's code
+        ad.dataprocess = lambda img, k, scaleFactor=1.0, _b=batch, _k=kp: (_b['image'].clone(), _k.clone(), np.array([[112., 112., 200.]]))
+        ad.optimized_step = 0
+        res = ad.online_adaptation(None, np.zeros((1, 25, 3)))
+        steps = oracle.online_adaptation(batch['image'], kp)
+        dyn = min(int(ad.optimized_step), opts.optim_steps)
+        assert dyn == min(steps, opts.optim_steps), (t, ad.optimized_step, steps)
+        n_outer += 1 + dyn
+        bound = 4 * opts.lr * n_outer
+        for k, p in ad.model.module.named_parameters():
+            err = (oracle.theta[k].detach() - p.detach()).abs().max().item()
+            assert err <= bound, f'webcam frame {t} theta[{k}] err {err:.3e} > {bound:.3e}'
+        for k, p in ad.teacher.named_parameters():
+            assert (oracle.teacher[k] - p.detach()).abs().max().item() <= bound, (t, k)
+        pred = oracle.predict(batch['image'])
+        _same(pred['vertices'], res['vts'].detach(), 'webcam verts', tol=1e-3)
+        rec['kp25'].append(kp.numpy()); rec['verts_sub'].append(res['vts'].detach()[:, ::10].numpy()); rec['cam'].append(res['cam'].detach().numpy())
+        rec['theta_samples'].append(_theta_samples(list(ad.model.module.named_parameters())))
+        rec['dyn_steps'].append(dyn)
+        print(f'  webcam frame {t}: dyn={dyn} |cam|={float(res["cam"].abs().sum()):.5f}')
+    np.savez_compressed(os.path.join(OUT, 'adapt_webcam.npz'), param_names=np.array(names),
+                        options=np.array(repr(sorted(vars(opts).items()))), **{k: np.stack([np.asarray(x) for x in v]) for k, v in rec.items()})
+    print('adapt webcam ok')
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -522,7 +621,7 @@ def main():
         synthetic.write_asset_dir(os.path.join(workdir, 'data'))
         os.makedirs(os.path.join(workdir, 'data/spin_data'), exist_ok=True)
         os.symlink(os.path.join(REF, 'data/gmm_08.pkl'), os.path.join(workdir, 'data/spin_data/gmm_08.pkl'))
-        which = sys.argv[1:] or ['geometry', 'prior', 'hmr', 'smpl', 'eval', 'c2', 'c3', 'c5', 'dp2', 'dataprocess']
+        which = sys.argv[1:] or ['geometry', 'prior', 'hmr', 'smpl', 'eval', 'c2', 'c3', 'c5', 'dp2', 'dataprocess', 'webcam']
         if 'dp2' in which:
             golden_dp()
         if 'dataprocess' in which:
@@ -547,6 +646,8 @@ def main():
         if 'c5' in which:   # dynamic loop exercised (threshold lowered so it fires on random weights)
             golden_adapt(workdir, 'c5', 2, inner_step=1, retrieval=1, sample_num=1, lower_level_mixtrain=1,
                          upper_level_mixtrain=1, dynamic_boa=1, cos_sim_threshold=1e-7, optim_steps=2)
+        if 'webcam' in which:   # third client (dynaboa_webcam.py): OpenPose joints, motion + teacher in the upper level, dynamic loop
+            golden_webcam(workdir)
     finally:
         shutil.rmtree(workdir, ignore_errors=True)
 
