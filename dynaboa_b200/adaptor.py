@@ -48,11 +48,27 @@ class Adaptor(BaseAdaptor):
             self.write_summaries(self.fit_losses)
             mpjpe_all.append(mpjpe); pampjpe_all.append(pampjpe); pve_all.append(pve)
         summary = dict(mpjpe=float(np.mean(mpjpe_all)), pampjpe=float(np.mean(pampjpe_all)), pve=float(np.mean(pve_all)))
-        torch.save({'mpjpe': mpjpe_all, 'pampjpe': pampjpe_all, 'pve': pve_all}, osp.join(self.exppath, 'res.pt'))
-        torch.save({'step': self.optim_step_record}, osp.join(self.exppath, 'optim_step_record.pt'))
-        with open(osp.join(self.exppath, 'res.txt'), 'w') as f:
-            f.write(f"Step:{self.global_step}: MPJPE:{summary['mpjpe']}, PAMPJPE:{summary['pampjpe']}, PVE:{summary['pve']}\n")
+        self.save_records(mpjpe_all, pampjpe_all, pve_all)
         return summary
+
+    def save_records(self, mpjpe_all, pampjpe_all, pve_all):
+        """The eight result files of the reference driver, same names, same joblib pickles, same keys
+        (dynaboa_benchmark.py:111-123)."""
+        import joblib
+        p = lambda name: osp.join(self.exppath, name)
+        joblib.dump({'kp2dloss': [float(x) for x in self.kp2dlosses_lower]}, p('lowerlevel_kp2dloss.pt'))
+        joblib.dump({'kp2dloss': {k: float(v) for k, v in self.kp2dlosses_upper.items()}}, p('upperlevel_kp2dloss.pt'))
+        joblib.dump({'mpjpe': mpjpe_all, 'pampjpe': pampjpe_all, 'pve': pve_all}, p('res.pt'))
+        joblib.dump({'mpjpe': self.mpjpe_all_lower, 'pampjpe': self.pampjpe_all_lower}, p('lower_res.pt'))
+        joblib.dump({'mpjpe': self.mpjpe_statistics, 'pampjpe': self.pampjpe_statistics}, p('steps_statistic_res.pt'))
+        joblib.dump({'feat': self.feat_sims}, p('feat_sims.pt'))
+        joblib.dump({'step': self.optim_step_record}, p('optim_step_record.pt'))
+        with open(p('res.txt'), 'w') as f:
+            f.write(f'Step:{self.global_step}: MPJPE:{np.mean(mpjpe_all)}, PAMPJPE:{np.mean(pampjpe_all)}, PVE:{np.mean(pve_all)}\n')
+            for i in range(self.options.inner_step):
+                lo_m = np.mean(self.mpjpe_all_lower[i]) if len(self.mpjpe_all_lower[i]) else float('nan')
+                lo_p = np.mean(self.pampjpe_all_lower[i]) if len(self.pampjpe_all_lower[i]) else float('nan')
+                f.write(f'Lower-level  Step:{i} MPJPE:{lo_m}, PAMPJPE:{lo_p}\n')
 
     def _outer_step(self, loss):
         self.optimizer.zero_grad()
@@ -152,8 +168,9 @@ class Adaptor(BaseAdaptor):
             mpjpe, pampjpe, pve = metrics[:, 0], metrics[:, 1], float(metrics[:, 2].mean())
         if getattr(self.options, 'cache_results', 1):        # the reference always dumps Pred_<step>.pt (:250-254); 0 turns the disk write off
             cam_t = torch.stack([pred_cam[:, 1], pred_cam[:, 2], 2 * 5000. / (constants.IMG_RES * pred_cam[:, 0] + 1e-9)], dim=-1)
-            torch.save({'verts': pred_vertices.cpu().numpy(), 'cam': cam_t.cpu().numpy(), 'rotmat': pred_rotmat.cpu().numpy(),
-                        'beta': pred_shape.cpu().numpy()}, osp.join(self.exppath, 'result', f'Pred_{self.global_step}.pt'))
+            import joblib
+            joblib.dump({'verts': pred_vertices.cpu().numpy(), 'cam': cam_t.cpu().numpy(), 'rotmat': pred_rotmat.cpu().numpy(),
+                         'beta': pred_shape.cpu().numpy()}, osp.join(self.exppath, 'result', f'Pred_{self.global_step}.pt'))
         if need_feature:
             return mpjpe * 1000, pampjpe * 1000, pve * 1000, out[3]
         return mpjpe * 1000, pampjpe * 1000, pve * 1000
@@ -216,6 +233,7 @@ class InternetAdaptor(Adaptor):
         cam_t = torch.stack([pred_cam[:, 1], pred_cam[:, 2], 2 * 5000. / (constants.IMG_RES * pred_cam[:, 0] + 1e-9)], dim=-1)
         res = {'verts': pred_vertices, 'cam': cam_t, 'rotmat': pred_rotmat, 'beta': pred_shape}
         if getattr(self.options, 'cache_results', 1):
-            torch.save({k: v.cpu().numpy() for k, v in res.items()}, osp.join(self.exppath, 'result', f'Pred_{self.global_step}.pt'))
+            import joblib
+            joblib.dump({k: v.cpu().numpy() for k, v in res.items()}, osp.join(self.exppath, 'result', f'Pred_{self.global_step}.pt'))
         zero = np.zeros(pred_rotmat.shape[0], np.float32)
         return (zero, zero, 0.0, out[3]) if need_feature else (zero, zero, 0.0)

@@ -100,8 +100,23 @@ def test_excute_loop_runs(asset_dir, tmp_path, golden):
     gd = golden('adapt_c2')
     ad, _ = build_adaptor(asset_dir, tmp_path, gd)
     ad.teacher.eval()
+    ad.options.cache_results = 1          # Pred_<step>.pt as the reference always writes them
     out = ad.excute(max_frames=3)
-    assert np.isfinite(out['mpjpe']) and np.isfinite(out['pampjpe']) and os.path.exists(os.path.join(ad.exppath, 'res.txt'))
+    assert np.isfinite(out['mpjpe']) and np.isfinite(out['pampjpe'])
+    # the eight result files of the reference driver (dynaboa_benchmark.py:111-123): same names, joblib pickles, same keys
+    import joblib
+    keys = {'lowerlevel_kp2dloss.pt': ['kp2dloss'], 'upperlevel_kp2dloss.pt': ['kp2dloss'], 'res.pt': ['mpjpe', 'pampjpe', 'pve'],
+            'lower_res.pt': ['mpjpe', 'pampjpe'], 'steps_statistic_res.pt': ['mpjpe', 'pampjpe'], 'feat_sims.pt': ['feat'],
+            'optim_step_record.pt': ['step']}
+    for name, ks in keys.items():
+        d = joblib.load(os.path.join(ad.exppath, name))
+        assert sorted(d) == sorted(ks), name
+    res = joblib.load(os.path.join(ad.exppath, 'res.pt'))
+    assert len(res['mpjpe']) == 3 and abs(np.mean(res['mpjpe']) - out['mpjpe']) < 1e-6
+    assert len(joblib.load(os.path.join(ad.exppath, 'lowerlevel_kp2dloss.pt'))['kp2dloss']) == 3
+    lines = open(os.path.join(ad.exppath, 'res.txt')).read().splitlines()
+    assert lines[0].startswith('Step:2: MPJPE:') and lines[1].startswith('Lower-level  Step:0 MPJPE:')
+    assert sorted(joblib.load(os.path.join(ad.exppath, 'result', 'Pred_2.pt'))) == ['beta', 'cam', 'rotmat', 'verts']
 
 
 def test_output_forward_on_side_stream_is_equivalent(asset_dir, tmp_path, golden):
