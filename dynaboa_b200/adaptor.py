@@ -148,6 +148,8 @@ class Adaptor(BaseAdaptor):
             ev = torch.cuda.Event()
             ev.record(side)
         image.record_stream(side)
+        for v in out.values():                             # allocated on the side stream, read by the caller's stream after the event
+            v.record_stream(cur)
         self.optimizer.wait_before_write.append(ev)
         return out, ev
 

@@ -118,7 +118,7 @@ int dboa_conv2d_wgrad(const float* dy, const float* x, float* dw, int B, int Hi,
 int dboa_conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin, int Cout, float* ws, long long ws_floats,
                         dboa_stream_t stream) {
     if (!x || !w || !y) return DBOA_ERR_ARG;
-    conv_tc_set_workspace(ws, ws ? (size_t)ws_floats : 0);
+    (void)ws; (void)ws_floats;                 /* kept in the signature: the split-K reduction lives in shared memory (DSMEM) now */
     return conv1x1_tc_fwd(x, w, y, M, Cin, Cout, ST(stream), cabi_pdl());
 }
 int dboa_conv2d_tc_fwd(const float* x, const float* w, float* y, int B, int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad,

@@ -47,7 +47,6 @@ bool conv_tc_bwd_enabled() { return g_tc_mode >= 2; }
 bool conv_tc_wgrad_enabled() { return g_tc_mode == 2; }
 void conv_tc_set_enabled(bool on) { g_tc_mode = on ? 2 : 0; }
 void conv_tc_set_mode(int mode) { g_tc_mode = mode; }
-void conv_tc_set_workspace(float*, size_t) {}
 
 namespace tc {
 

@@ -229,6 +229,17 @@ struct BwdAsync {
 };
 static BwdAsync g_async;
 
+// One process drives one GPU (one rank per GPU, as bench.py / torchrun launch it): the side streams and event rings above, the
+// tensor-map caches and the per-function attribute cache of launch_ex belong to the device that was current at the first
+// call.  A call from another device is refused (DBOA_ERR_UNSUPPORTED) instead of failing later with invalid-handle errors.
+static int device_guard() {
+    static int first = -1;
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) return DBOA_ERR_CUDA;
+    if (first < 0) first = d;
+    return d == first ? DBOA_OK : DBOA_ERR_UNSUPPORTED;
+}
+
 // Gradient buckets for the data-parallel all-reduce ("bucketed in reverse layer order and overlapped with
 // backward").  The backward produces gradients head -> layer4 -> ... -> stem; the arena is laid out stem, layer1..4, head.
 // Bucket 0 = [layer4 .. end), 1 = [layer3, layer4), 2 = [0, layer3).  When a caller hands over three events, event k is
@@ -378,10 +389,6 @@ namespace dboa {
 __global__ void rot6d_rows_fwd_kernel(const float* __restrict__ params3, float* __restrict__ rotmat, int B) {
     pdl_wait();
     pdl_trigger();
-    pdl_wait();
-    pdl_trigger();
-    pdl_wait();
-    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * 24) return;
     int b = i / 24, j = i - b * 24;
@@ -410,6 +417,7 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
                 const float* drop_masks, float* T, float* scratch, float* rotmat, float* shape, float* cam, float* pose6d,
                 cudaStream_t st) {
     if (B < 1 || B > 64) return DBOA_ERR_SHAPE;
+    DBOA_TRY(device_guard());
     const Net& n = net();
     const Tape& t = tape_for(B);
     Scratch sc(scratch, B);
@@ -419,7 +427,6 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
         return gn_fwd_fused(T + t.conv[ci].y, P + c.g_off, P + c.b_off, res, out, T + t.conv[ci].stats, T + t.conv[ci].part, B, HW,
                             c.cout, relu, st);
     };
-    conv_tc_set_workspace(sc.ws, (size_t)kConvWs);
     if (g_fused_fwd && conv_tc_enabled())
         cudaMemsetAsync(T + t.acc, 0, n.convs.size() * (size_t)B * 16 * sizeof(float), st);      // statistics accumulators of this forward
     DBOA_TRY(nchw_to_nhwc(image, T + t.x0, B, 3, 224, 224, st));
@@ -533,6 +540,7 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
 int hmr_backward(const float* P, const float* T, int B, int masked_in, const float* d_rotmat, const float* d_shape, const float* d_cam,
                  float* G, float* scratch, cudaStream_t st) {
     if (B < 1 || B > 64) return DBOA_ERR_SHAPE;
+    DBOA_TRY(device_guard());
     const Net& n = net();
     const Tape& t = tape_for(B);
     Scratch sc(scratch, B);

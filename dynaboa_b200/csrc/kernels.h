@@ -28,7 +28,6 @@ int conv1x1_tc_fwd(const float* x, const float* w, float* y, int M, int Cin, int
 bool conv_tc_enabled();
 void conv_tc_set_enabled(bool on);
 void conv_tc_set_mode(int mode);                      // 0 off, 1 forward, 2 forward + dgrad + wgrad, 3 forward + dgrad
-void conv_tc_set_workspace(float* ws, size_t floats);
 
 // ---- description of one fused convolution (conv_wide.cu)
 struct FusedConv {
