@@ -13,8 +13,10 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = '/root/reference'
 DST = os.path.join(REPO, 'baseline', '_ref')
-FILES = ['dynaboa_benchmark.py', 'dynaboa_internet.py', 'base_adaptor.py', 'constants.py', 'config.py', 'model/hmr.py', 'model/smpl.py',
-         'utils/geometry.py', 'utils/pose_utils.py', 'utils/smplify/prior.py', 'utils/dataprocess.py', 'data/gmm_08.pkl']
+FILES = ['dynaboa_benchmark.py', 'dynaboa_internet.py', 'base_adaptor.py', 'constants.py', 'config.py', 'model/__init__.py', 'model/hmr.py',
+         'model/smpl.py', 'utils/__init__.py', 'utils/geometry.py', 'utils/pose_utils.py', 'utils/dataprocess.py', 'utils/smplify/__init__.py',
+         'utils/smplify/prior.py', 'utils/smplify/smplify.py', 'utils/smplify/losses.py', 'boa_dataset/__init__.py', 'boa_dataset/pw3d.py',
+         'boa_dataset/internet_data.py', 'data/gmm_08.pkl']
 
 
 def install():
