@@ -323,7 +323,10 @@ int conv_wgrad_wide(const float* dy, const float* x, float* dw, const ConvDims& 
     // K-slices are limited to a CTA budget that leaves room for the chain (DBOA_WGRAD_MAX_CTAS)
     static const int budget = [] { const char* e = getenv("DBOA_WGRAD_MAX_CTAS"); int v = e ? atoi(e) : 128; return v < 1 ? 1 : v; }();
     int nz = 1;
-    while (nz < 16 && tiles * nz * 2 <= budget && L.nkb_total / (nz * 2) >= 1) nz *= 2;
+    // DBOA_WGRAD_MAX_NZ: largest cluster (K-slices of one tile).  A cluster needs that many free SMs inside ONE GPC, so large
+    // clusters cannot start next to another stream's kernel that has CTAs in every GPC.
+    static const int max_nz = [] { const char* e = getenv("DBOA_WGRAD_MAX_NZ"); int v = e ? atoi(e) : 16; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
+    while (nz < max_nz && tiles * nz * 2 <= budget && L.nkb_total / (nz * 2) >= 1) nz *= 2;
     while (nz > 1 && (nz - 1) * ceil_div(L.nkb_total, nz) >= L.nkb_total) nz >>= 1;
     L.nz = nz; L.per = ceil_div(L.nkb_total, nz);
     const CUtensorMap* tmdy = static_cast<const CUtensorMap*>(tma_act_map(dy, d.B, d.Ho, d.Wo, d.Cout, W, bh, true, 1));

@@ -711,7 +711,8 @@ int conv_wide_plan(const FusedConv* d, int nprob, int B) {
         const int soft = g_cta_budget > 2 * tiles ? g_cta_budget : 2 * tiles;
         return g_cta_budget > 0 && soft < hw ? soft : hw;
     };
-    while (nz < 16 && tiles * nz * 2 <= cap(nz * 2) && nkb / (nz * 2) >= min_kb) nz *= 2;
+    static const int max_nz = [] { const char* e = getenv("DBOA_FUSED_MAX_NZ"); int v = e ? atoi(e) : 16; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
+    while (nz < max_nz && tiles * nz * 2 <= cap(nz * 2) && nkb / (nz * 2) >= min_kb) nz *= 2;
     while (nz > 1 && (nz - 1) * ceil_div(nkb, nz) >= nkb) nz >>= 1;
     return nz;
 }

@@ -610,7 +610,8 @@ int dgrad_wide(const DgradFused& f, const ConvDims& d, cudaStream_t st, bool pdl
     const int tiles = d.B * L.tps * L.ntiles, nkb = d.kh * d.kw * d.Cout / dz::BK;
     static const int budget = [] { const char* e = getenv("DBOA_DGRAD_MAX_CTAS"); int v = e ? atoi(e) : 64; return v; }();
     int nz = 1;
-    while (nz < 16 && tiles * nz * 2 <= (budget > 2 * tiles ? budget : (2 * tiles < 128 ? 2 * tiles : 128)) && nkb / (nz * 2) >= 2) nz *= 2;
+    static const int max_nz = [] { const char* e = getenv("DBOA_DGRAD_MAX_NZ"); int v = e ? atoi(e) : 16; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
+    while (nz < max_nz && tiles * nz * 2 <= (budget > 2 * tiles ? budget : (2 * tiles < 128 ? 2 * tiles : 128)) && nkb / (nz * 2) >= 2) nz *= 2;
     while (nz > 1 && (nz - 1) * ceil_div(nkb, nz) >= nkb) nz >>= 1;
     L.nz = nz; L.per = ceil_div(nkb, nz);
     L.tabc = d.kh == 1 ? L.per * dz::BK : d.Cout;

@@ -51,6 +51,10 @@ int gn_acc_res_avgpool(const float* y, const float* res, const float* acc, const
                        float* out, int B, int HW, int C, int ld, int ncopy, size_t copy_stride, cudaStream_t st);
 
 // ---- conv_wgrad_wide.cu (tcgen05 weight gradient, MN-major operands through TMA); dw is accumulated (+=)
+// 7x7 / stride-2 stem weight gradient: row-per-CTA partials + fixed-order reduction (stem_wgrad.cu); needs 64 * 147 floats of
+// workspace per partial (DBOA_ERR_UNSUPPORTED for any other shape or without workspace)
+bool stem_wgrad_ok(const ConvDims& d);
+int stem_wgrad(const float* dy, const float* x, float* dw, const ConvDims& d, float* ws, size_t ws_floats, cudaStream_t st);
 bool conv_wgrad_wide_ok(const ConvDims& d);
 int conv_wgrad_wide(const float* dy, const float* x, float* dw, const ConvDims& d, cudaStream_t st, bool pdl);
 

@@ -36,7 +36,8 @@ def ohwi(w, pitch=None):
 
 
 CONV_CASES = [  # B, H, Cin, Cout, k, stride, pad
-    (1, 224, 3, 64, 7, 2, 3),      # stem (scalar gather path, padded pitch)
+    (1, 224, 3, 64, 7, 2, 3),      # stem (scalar gather path, padded pitch; row-per-CTA weight gradient)
+    (3, 224, 3, 64, 7, 2, 3),      # stem, several output rows per CTA
     (2, 56, 64, 64, 1, 1, 0),
     (1, 56, 64, 64, 3, 1, 1),
     (2, 28, 128, 128, 3, 2, 1),    # stride-2 3x3
