@@ -5,7 +5,7 @@
 // critical path of the frame.  As an implicit GEMM it is M = 64 output channels, N = 147 (tap, ci), K = 12544 B pixels: the
 // generic CUDA-core kernel has 3 tiles and a 16-CTA cluster split -- 48 CTAs of 49 serial iterations, 81 us at batch 1.  Here
 // one CTA owns whole output rows: the 112 x 64 dy row and the 7 zero-padded input rows it touches are staged in shared memory
-// once, thread (co, q) keeps 37 of the 147 accumulators of its output channel in registers (operand reads are warp-wide
+// once, thread (co, q) keeps 19 of the 147 accumulators of its output channel in registers (operand reads are warp-wide
 // broadcasts), and the per-CTA partials [64][147] go to a workspace that a second small launch adds into the gradient arena in
 // a fixed order (deterministic).  112 CTAs at batch 1.
 #include <stdint.h>
@@ -17,7 +17,7 @@ namespace dboa {
 namespace stem {
 
 constexpr int CO = 64, KK = 147, HO = 112, HI = 224, ROWF = (HI + 6) * 3;      // 690 floats per zero-padded input row
-constexpr int NT = 256, JPT = 37;                                               // accumulators per thread: 37, 37, 37, 36
+constexpr int NT = 512, JPT = 19;                                               // 8 thread groups x 19 accumulators (the last one 14)
 constexpr int SMEM_FLOATS = HO * CO + 7 * ROWF;                                 // 7168 + 4830 (>= 64 * 147 for the transpose)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
