@@ -530,44 +530,60 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
 }
 
 // Stand-alone version of the epilogue above for the seams with the unfused kernels (after avgpool_bwd; after a stride-2 block):
-// dz = dA * (a > 0) -> out; sums / d gamma / d beta of GroupNorm_p.  grid (ceil(HW * C / 4 / 256 / 8), B): one thread = one
-// float4 column, 8 rows apart... simple elementwise layout: thread t owns channel vector cv = t % (C/4) of rows t / (C/4) + k * rstep.
+// dz = dA * (a > 0) -> out; sums / d gamma / d beta of GroupNorm_p.  grid (ceil(HW / rows_per_cta), B), 256 threads: a thread keeps
+// its channel vector(s) over the (few) rows of the CTA, all loads of a row group in flight together; the two group sums go
+// through a warp butterfly before they touch shared memory (a warp's 32 channel vectors lie in one group for C >= 512; for
+// narrower layers the segments are 16 / 8 lanes), so the shared 64-bit adds see at most 8 contenders instead of 256.
 __global__ void __launch_bounds__(256) gn_bwd_prep_kernel(const float* __restrict__ dA, const float* __restrict__ mask, float* __restrict__ out,
                                                           Prep p, int HW, int C, int rows_per_cta) {
     __shared__ unsigned long long sacc[8];
     pdl_wait();
     pdl_trigger();
-    const int b = blockIdx.y, C4 = C >> 2, gw = C >> 2;
+    const int b = blockIdx.y, C4 = C >> 2, gw = C >> 2, lane = threadIdx.x & 31;
+    const int cvg = C4 >> 2;                                 // channel vectors per group (a power of two >= 4 for the backbone widths)
+    const int seg = cvg >= 32 ? 32 : cvg;                    // lanes of a warp that share a group
     if (threadIdx.x < 8) sacc[threadIdx.x] = 0ull;
     __syncthreads();
     const int r_begin = blockIdx.x * rows_per_cta, r_end = min(HW, r_begin + rows_per_cta);
-    // threads stride over channel vectors; every thread keeps its channel vector over all rows of the CTA (C4 <= 512: up to 2 per thread)
-    for (int cv = threadIdx.x; cv < C4; cv += 256) {
-        const int c = cv * 4, g = c / gw;
-        const float4 ga = ldg4(p.gamma + c);
-        const float mu = __ldg(p.stats + ((size_t)b * 4 + g) * 2), rs = __ldg(p.stats + ((size_t)b * 4 + g) * 2 + 1);
+    for (int cv0 = 0; cv0 < C4; cv0 += 256) {                // uniform trip count: every lane takes part in the butterflies
+        const int cv = cv0 + threadIdx.x;
+        const bool live = cv < C4;
+        const int c = live ? cv * 4 : 0, g = c / gw;
         float4 sdg = make_float4(0.f, 0.f, 0.f, 0.f), sdb = sdg;
         float sq = 0.f, sqx = 0.f;
-        for (int r = r_begin; r < r_end; ++r) {
-            const size_t e = ((size_t)b * HW + r) * C + c;
-            float4 d = ldg4(dA + e);
-            const float4 m = ldg4(mask + e), yv = ldg4(p.y + e);
-            d.x = m.x > 0.f ? d.x : 0.f; d.y = m.y > 0.f ? d.y : 0.f; d.z = m.z > 0.f ? d.z : 0.f; d.w = m.w > 0.f ? d.w : 0.f;
-            *reinterpret_cast<float4*>(out + e) = d;
-            const float x0 = (yv.x - mu) * rs, x1 = (yv.y - mu) * rs, x2 = (yv.z - mu) * rs, x3 = (yv.w - mu) * rs;
-            const float q0 = d.x * ga.x, q1 = d.y * ga.y, q2 = d.z * ga.z, q3 = d.w * ga.w;
-            sdg.x += d.x * x0; sdg.y += d.y * x1; sdg.z += d.z * x2; sdg.w += d.w * x3;
-            sdb.x += d.x; sdb.y += d.y; sdb.z += d.z; sdb.w += d.w;
-            sq += (q0 + q1) + (q2 + q3);
-            sqx += (q0 * x0 + q1 * x1) + (q2 * x2 + q3 * x3);
+        if (live) {
+            const float4 ga = ldg4(p.gamma + c);
+            const float mu = __ldg(p.stats + ((size_t)b * 4 + g) * 2), rs = __ldg(p.stats + ((size_t)b * 4 + g) * 2 + 1);
+#pragma unroll 4
+            for (int r = r_begin; r < r_end; ++r) {
+                const size_t e = ((size_t)b * HW + r) * C + c;
+                float4 d = __ldcg(reinterpret_cast<const float4*>(dA + e));
+                const float4 m = __ldcg(reinterpret_cast<const float4*>(mask + e)), yv = __ldcg(reinterpret_cast<const float4*>(p.y + e));
+                d.x = m.x > 0.f ? d.x : 0.f; d.y = m.y > 0.f ? d.y : 0.f; d.z = m.z > 0.f ? d.z : 0.f; d.w = m.w > 0.f ? d.w : 0.f;
+                *reinterpret_cast<float4*>(out + e) = d;
+                const float x0 = (yv.x - mu) * rs, x1 = (yv.y - mu) * rs, x2 = (yv.z - mu) * rs, x3 = (yv.w - mu) * rs;
+                const float q0 = d.x * ga.x, q1 = d.y * ga.y, q2 = d.z * ga.z, q3 = d.w * ga.w;
+                sdg.x += d.x * x0; sdg.y += d.y * x1; sdg.z += d.z * x2; sdg.w += d.w * x3;
+                sdb.x += d.x; sdb.y += d.y; sdb.z += d.z; sdb.w += d.w;
+                sq += (q0 + q1) + (q2 + q3);
+                sqx += (q0 * x0 + q1 * x1) + (q2 * x2 + q3 * x3);
+            }
         }
-        atomicAdd(&sacc[g * 2], (unsigned long long)to_fix(sq));
-        atomicAdd(&sacc[g * 2 + 1], (unsigned long long)to_fix(sqx));
-        const float dgv[4] = {sdg.x, sdg.y, sdg.z, sdg.w}, dbv[4] = {sdb.x, sdb.y, sdb.z, sdb.w};
+        long long a1 = to_fix(sq), a2 = to_fix(sqx);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            atomicAdd(p.dgb + (size_t)(c + e) * 2, (unsigned long long)to_fix(dgv[e]));
-            atomicAdd(p.dgb + (size_t)(c + e) * 2 + 1, (unsigned long long)to_fix(dbv[e]));
+        for (int o = 16; o >= 1; o >>= 1)
+            if (o < seg) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+        if (live && (lane & (seg - 1)) == 0) {
+            atomicAdd(&sacc[g * 2], (unsigned long long)a1);
+            atomicAdd(&sacc[g * 2 + 1], (unsigned long long)a2);
+        }
+        if (live) {
+            const float dgv[4] = {sdg.x, sdg.y, sdg.z, sdg.w}, dbv[4] = {sdb.x, sdb.y, sdb.z, sdb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                atomicAdd(p.dgb + (size_t)(c + e) * 2, (unsigned long long)to_fix(dgv[e]));
+                atomicAdd(p.dgb + (size_t)(c + e) * 2 + 1, (unsigned long long)to_fix(dbv[e]));
+            }
         }
     }
     __syncthreads();
@@ -631,7 +647,9 @@ int gn_bwd_prep(const float* dA, const float* mask, float* out, const DgradPrep&
     if (C % 4 != 0 || C / 4 > 512) return DBOA_ERR_SHAPE;
     dz::Prep pp;
     pp.y = p.y; pp.stats = p.stats; pp.gamma = p.gamma; pp.sums = reinterpret_cast<unsigned long long*>(p.sums); pp.dgb = reinterpret_cast<unsigned long long*>(p.dgb);
-    const int rows_per = HW >= 784 ? 28 : (HW >= 196 ? 14 : 7);
+    // enough CTAs to cover the GPU with SHORT row loops (the kernel is a latency chain: a row is one memory round trip)
+    int rows_per = 1;
+    while (rows_per < 8 && ceil_div(HW, rows_per * 2) * B >= 148) rows_per *= 2;
     return launch_ex(dz::gn_bwd_prep_kernel, dim3(ceil_div(HW, rows_per), B), dim3(256), 0, st, dim3(1, 1, 1), true, dA, mask, out, pp, HW, C, rows_per);
 }
 
