@@ -48,6 +48,8 @@ SIGNATURES = {
     'dboa_get_fused_forward': (I, []),
     'dboa_set_fused_backward': (I, [I]),
     'dboa_set_forward_cta_budget': (I, [I]),
+    'dboa_set_operand_tmem': (I, [I]),
+    'dboa_get_operand_tmem': (I, []),
     'dboa_dgrad_fused': (I, [C.POINTER(DgradFusedStruct), I, I, I, I, I, P]),
     'dboa_conv_fused_part_floats': (L, [I, I, I]),
     'dboa_conv_fused_fwd': (I, [C.POINTER(FusedConvStruct), I, I, P]),

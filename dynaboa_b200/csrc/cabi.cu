@@ -75,6 +75,8 @@ int dboa_set_fused_forward(int enable) { hmr_set_fused_forward(enable != 0); ret
 int dboa_get_fused_forward(void) { return hmr_fused_forward() ? 1 : 0; }
 int dboa_set_fused_backward(int enable) { hmr_set_fused_backward(enable != 0); return DBOA_OK; }
 int dboa_set_forward_cta_budget(int n) { conv_wide_set_cta_budget(n < 0 ? 0 : n); return DBOA_OK; }
+int dboa_set_operand_tmem(int enable) { conv_wide_set_operand_tmem(enable != 0); return DBOA_OK; }
+int dboa_get_operand_tmem(void) { return conv_wide_operand_tmem() ? 1 : 0; }
 
 int dboa_hmr_num_params(void) { return hmr_num_params(); }
 long long dboa_hmr_arena_floats(void) { return hmr_arena_floats(); }

@@ -105,6 +105,24 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
         "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand read from tensor memory (lane = tile row, one 32-bit column per TF32 element): the tensor core fetches only B from
+// shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 8 consecutive 32-bit columns of this thread's TMEM lane (lane = 32 * (warp % 4) + lane id)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float4 a, const float4 b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(a.x)),
+                 "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)),
+                 "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w))
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -181,7 +199,8 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 #define PW(field) (second ? L.p[1].field : L.p[0].field)
 
 // tensor maps: tmx = operand x of problem 0 / 1, tmr = second operand (modes 2, 3), tmw = weights
-template <int MODE>
+// ATM: the transformed activation operand (hi and lo parts) lives in tensor memory instead of shared memory (see the transform warps)
+template <int MODE, bool ATM>
 __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant__ Launch L, const __grid_constant__ CUtensorMap tmx0,
                                                           const __grid_constant__ CUtensorMap tmx1, const __grid_constant__ CUtensorMap tmr0,
                                                           const __grid_constant__ CUtensorMap tmr1, const __grid_constant__ CUtensorMap tmw0,
@@ -233,7 +252,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN * NACC) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(ATM ? 512 : BN * NACC) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     const int tc0 = ks == 1 ? kb_begin * BK : 0, tcn = ks == 1 ? nkb * BK : Cin;
@@ -325,11 +344,22 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
                 const uint32_t dacc = tmem_d + (uint32_t)((it & (NACC - 1)) * BN);
                 const uint32_t first = it >= NACC ? 1u : 0u;
                 if (elect_one()) {
+                    if constexpr (ATM) {
+                        // A hi / lo of stage ls: TMEM columns ACOL + 64 ls + {0..31, 32..63}, 8 columns per k-step
+                        const uint32_t tah = tmem_d + (uint32_t)(BN * NACC + ls * 2 * BK), tal = tah + (uint32_t)BK;
 #pragma unroll
-                    for (int kk = 0; kk < BK / 8; ++kk) {
-                        mma_tf32(dacc, dah + kk * KSTEP, dbh + kk * KSTEP, idesc, kk > 0 ? 1u : first);
-                        mma_tf32(dacc, dah + kk * KSTEP, dbl + kk * KSTEP, idesc, 1u);
-                        mma_tf32(dacc, dal + kk * KSTEP, dbh + kk * KSTEP, idesc, 1u);
+                        for (int kk = 0; kk < BK / 8; ++kk) {
+                            mma_tf32_ts(dacc, tah + kk * 8, dbh + kk * KSTEP, idesc, kk > 0 ? 1u : first);
+                            mma_tf32_ts(dacc, tah + kk * 8, dbl + kk * KSTEP, idesc, 1u);
+                            mma_tf32_ts(dacc, tal + kk * 8, dbh + kk * KSTEP, idesc, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < BK / 8; ++kk) {
+                            mma_tf32(dacc, dah + kk * KSTEP, dbh + kk * KSTEP, idesc, kk > 0 ? 1u : first);
+                            mma_tf32(dacc, dah + kk * KSTEP, dbl + kk * KSTEP, idesc, 1u);
+                            mma_tf32(dacc, dal + kk * KSTEP, dbh + kk * KSTEP, idesc, 1u);
+                        }
                     }
                     umma_commit(&l_empty[ls]);
                     umma_commit(&s_empty[sl]);
@@ -347,7 +377,9 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
         // transform warps: thread t owns float4 t and t + 512 of the activation tile (rows r0 = t >> 3 and r0 + 64, the same
         // physical 16-byte chunk pc = t & 7, hence the same logical chunk lc = pc ^ (r0 & 7)) and float4 t of the weight tile
         // =====================================================================================
-        const int r0 = tid >> 3, pc = tid & 7, lc = pc ^ (r0 & 7);
+        // ATM: thread = tile row (= its TMEM lane: 32 * (warp % 4) + lane) x 8 channels kc * 8 .. + 7 of the k-block, plus float4 t of the
+        // weight tile; only entry 0 of the per-row arrays is used
+        const int r0 = ATM ? (warp & 3) * 32 + lane : tid >> 3, pc = tid & 7, lc = pc ^ (r0 & 7), kc = warp >> 2;
         // per-thread invariants of the two activation rows: input coordinates of tap (0, 0), validity, tape pointer of tap (0, 0)
         float* ab = (MODE >= 1 && PW(a_out) != nullptr && nt == 0) ? PW(a_out) + (size_t)b * Hi * Wi * Cin : nullptr;
         int hq[2], wq[2];
@@ -357,7 +389,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
         for (int q = 0; q < 2; ++q) {
             const int i = r0 + 64 * q, oh = i / Wo, ow = i - oh * Wo;
             hq[q] = (h0 + oh) * stride - pad; wq[q] = ow * stride - pad; rowok[q] = i < rows_valid;
-            abq[q] = ab + ((long long)hq[q] * Wi + wq[q]) * Cin + lc * 4;      // only dereferenced for in-bounds taps
+            abq[q] = ab + ((long long)hq[q] * Wi + wq[q]) * Cin + (ATM ? kc * 8 : lc * 4);      // only dereferenced for in-bounds taps
         }
         int lgw = 0;
         while ((4 << lgw) < Cin) ++lgw;
@@ -408,6 +440,76 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
         const uint32_t lo_a32 = smem_u32(lo_a) + offA, lo_b32 = smem_u32(lo_b) + offA;
         const uint32_t wofs = A_TILE * (HAS_RES ? 2 : 1);
         uint32_t slot = slots32 + offA;                                  // this thread's first chunk inside the current slot
+        if constexpr (ATM) {
+            // The transformed activation tile goes to TENSOR memory (tcgen05.st, thread = row) and the MMAs read it from there: per
+            // k-block the shared-memory pipe carries 24 KB of raw reads + 16 KB of weight hi / lo writes + 24 KB of tensor-core B
+            // reads instead of 24 + 48 + 72 KB (measured: the k-loop of the all-shared-memory variant is shared-memory-bandwidth
+            // bound, L1/TEX throughput ~90 % inside the loop).  Row r's logical 16-byte chunk j sits at physical chunk j ^ (r & 7)
+            // (128-byte swizzle of the TMA box): a quarter warp reads 8 different physical chunks -> conflict-free.
+            const uint32_t rowofs = (uint32_t)r0 * 128u, sw = (uint32_t)(r0 & 7);
+            const uint32_t pa0 = rowofs + (((uint32_t)(2 * kc) ^ sw) << 4), pa1 = rowofs + (((uint32_t)(2 * kc + 1) ^ sw) << 4);
+            const uint32_t ta = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN * NACC + kc * 8);
+            uint32_t sbase = slots32;
+#pragma unroll 1
+            for (int it = 0; it < nkb; ++it) {
+                const int ls = it & 1;
+                const uint32_t ti = tab32 + (uint32_t)(c - tc0 + kc * 8) * 4u;   // this warp's 8 channels inside the channel table (broadcast reads)
+                float4 sca = make_float4(1.f, 1.f, 1.f, 1.f), scb = sca, sha = make_float4(0.f, 0.f, 0.f, 0.f), shb = sha, s2a = sca, s2b = sca;
+                if (MODE >= 1) {
+                    sca = lds128(ti); scb = lds128(ti + 16); sha = lds128(ti + tabc4); shb = lds128(ti + tabc4 + 16);
+                    if (MODE == 3) { s2a = lds128(ti + 2 * tabc4); s2b = lds128(ti + 2 * tabc4 + 16); }
+                }
+                const bool desig = ab != nullptr && (ks == 1 ? stride == 1 : (stride == 1 ? (r == 1 && s == 1) : (r >= 1 && s >= 1)));
+                const int tapoff = (r * Wi + s) * Cin + c;
+                mbar_wait(&s_full[sl], ph_full);
+                if (it >= 2) mbar_wait(&l_empty[ls], (uint32_t)(((it >> 1) - 1) & 1));
+                float4 v0 = lds128(sbase + pa0), v1 = lds128(sbase + pa1);
+                const float4 vw = lds128(sbase + wofs + offA);
+                const bool in0 = rowok[0] && (unsigned)(hq[0] + r) < (unsigned)Hi && (unsigned)(wq[0] + s) < (unsigned)Wi;
+                if (MODE >= 1) {
+                    float4 q0, q1;
+                    if (MODE >= 2) { q0 = lds128(sbase + A_TILE + pa0); q1 = lds128(sbase + A_TILE + pa1); }
+                    v0.x = fmaf(v0.x, sca.x, sha.x); v0.y = fmaf(v0.y, sca.y, sha.y); v0.z = fmaf(v0.z, sca.z, sha.z); v0.w = fmaf(v0.w, sca.w, sha.w);
+                    v1.x = fmaf(v1.x, scb.x, shb.x); v1.y = fmaf(v1.y, scb.y, shb.y); v1.z = fmaf(v1.z, scb.z, shb.z); v1.w = fmaf(v1.w, scb.w, shb.w);
+                    if (MODE == 2) {
+                        v0.x += q0.x; v0.y += q0.y; v0.z += q0.z; v0.w += q0.w;
+                        v1.x += q1.x; v1.y += q1.y; v1.z += q1.z; v1.w += q1.w;
+                    } else if (MODE == 3) {
+                        v0.x = fmaf(q0.x, s2a.x, v0.x); v0.y = fmaf(q0.y, s2a.y, v0.y); v0.z = fmaf(q0.z, s2a.z, v0.z); v0.w = fmaf(q0.w, s2a.w, v0.w);
+                        v1.x = fmaf(q1.x, s2b.x, v1.x); v1.y = fmaf(q1.y, s2b.y, v1.y); v1.z = fmaf(q1.z, s2b.z, v1.z); v1.w = fmaf(q1.w, s2b.w, v1.w);
+                    }
+                    // padding is zero in the ACTIVATION domain
+                    v0.x = in0 ? fmaxf(v0.x, 0.f) : 0.f; v0.y = in0 ? fmaxf(v0.y, 0.f) : 0.f; v0.z = in0 ? fmaxf(v0.z, 0.f) : 0.f; v0.w = in0 ? fmaxf(v0.w, 0.f) : 0.f;
+                    v1.x = in0 ? fmaxf(v1.x, 0.f) : 0.f; v1.y = in0 ? fmaxf(v1.y, 0.f) : 0.f; v1.z = in0 ? fmaxf(v1.z, 0.f) : 0.f; v1.w = in0 ? fmaxf(v1.w, 0.f) : 0.f;
+                    if (desig && in0) {
+                        *reinterpret_cast<float4*>(abq[0] + tapoff) = v0;
+                        *reinterpret_cast<float4*>(abq[0] + tapoff + 4) = v1;
+                    }
+                } else if (!rowok[0]) {
+                    // rows the box did not deliver hold stale shared memory: keep them finite
+                    v0 = make_float4(0.f, 0.f, 0.f, 0.f); v1 = v0;
+                }
+                const float4 h0v = make_float4(tf32_hi(v0.x), tf32_hi(v0.y), tf32_hi(v0.z), tf32_hi(v0.w));
+                const float4 h1v = make_float4(tf32_hi(v1.x), tf32_hi(v1.y), tf32_hi(v1.z), tf32_hi(v1.w));
+                const float4 hw = make_float4(tf32_hi(vw.x), tf32_hi(vw.y), tf32_hi(vw.z), tf32_hi(vw.w));
+                const uint32_t tah = ta + (uint32_t)(ls * 2 * BK);
+                tmem_st8(tah, h0v, h1v);
+                tmem_st8(tah + BK, make_float4(v0.x - h0v.x, v0.y - h0v.y, v0.z - h0v.z, v0.w - h0v.w),
+                         make_float4(v1.x - h1v.x, v1.y - h1v.y, v1.z - h1v.z, v1.w - h1v.w));
+                sts128(sbase + wofs + offA, hw);
+                sts128(lo_b32 + ls * B_TILE, make_float4(vw.x - hw.x, vw.y - hw.y, vw.z - hw.z, vw.w - hw.w));
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&l_full[ls]);
+                if (it == 0) FTL(3);
+                sbase += slot_bytes;
+                if (++sl == D) { sl = 0; sbase = slots32; ph_full ^= 1u; }
+                c += BK;
+                if (c >= Cin) { c = 0; if (++s == ks) { s = 0; ++r; } }
+            }
+        } else {
 #pragma unroll 1
         for (int it = 0; it < nkb; ++it) {
             const int ls = it & 1;
@@ -468,6 +570,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
             if (++sl == D) { sl = 0; slot = slots32 + offA; ph_full ^= 1u; }
             c += BK;
             if (c >= Cin) { c = 0; if (++s == ks) { s = 0; ++r; } }
+        }
         }
     }
     FTL(4);
@@ -592,7 +695,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
     FTL(8);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN * NACC) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(ATM ? 512 : BN * NACC) : "memory");
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -696,6 +799,10 @@ bool conv_wide_ok(const FusedConv& d) {
 // ~150-200 KB shared memory per SM), so two full-width launches would simply alternate.
 // Measured (bench.py, C2, 1 x B200): 143.3 frames/s with all 148 SMs per launch, 151.8 with 96, 151.2 with 74, 148.1 with 64; the
 // isolated forward is also slightly faster with fewer K-slices (0.831 vs 0.855 ms).  Default 96; DBOA_FUSED_MAX_CTAS overrides.
+// activation operand of the fused kernels in tensor memory (DBOA_OPERAND_TMEM=0 / dboa_set_operand_tmem(0): all-shared-memory variant)
+static bool g_operand_tmem = [] { const char* e = getenv("DBOA_OPERAND_TMEM"); return e ? e[0] != '0' : false; }();
+void conv_wide_set_operand_tmem(bool on) { g_operand_tmem = on; }
+bool conv_wide_operand_tmem() { return g_operand_tmem; }
 static int g_cta_budget = [] { const char* e = getenv("DBOA_FUSED_MAX_CTAS"); int v = e ? atoi(e) : 96; return v; }();
 void conv_wide_set_cta_budget(int n) { g_cta_budget = n; }
 int conv_wide_plan(const FusedConv* d, int nprob, int B) {
@@ -768,12 +875,16 @@ int conv_wide_launch(const FusedConv* d, int nprob, int B, int nz, const float* 
     const size_t smem = fixed + (size_t)D * slot;
     if (smem > 227 * 1024) return DBOA_ERR_SHAPE;
     const dim3 grid(total * nz), block(wz::NT), cl(nz, 1, 1);
+#define DBOA_WIDE_LAUNCH(M)                                                                                                                          \
+    (g_operand_tmem ? launch_ex(wz::conv_wide_kernel<M, true>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr[0], *tmr[1], *tmw[0], *tmw[1]) \
+                    : launch_ex(wz::conv_wide_kernel<M, false>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr[0], *tmr[1], *tmw[0], *tmw[1]))
     switch (d[0].mode) {
-        case 0: return launch_ex(wz::conv_wide_kernel<0>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr[0], *tmr[1], *tmw[0], *tmw[1]);
-        case 1: return launch_ex(wz::conv_wide_kernel<1>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr[0], *tmr[1], *tmw[0], *tmw[1]);
-        case 2: return launch_ex(wz::conv_wide_kernel<2>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr[0], *tmr[1], *tmw[0], *tmw[1]);
-        default: return launch_ex(wz::conv_wide_kernel<3>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr[0], *tmr[1], *tmw[0], *tmw[1]);
+        case 0: return DBOA_WIDE_LAUNCH(0);
+        case 1: return DBOA_WIDE_LAUNCH(1);
+        case 2: return DBOA_WIDE_LAUNCH(2);
+        default: return DBOA_WIDE_LAUNCH(3);
     }
+#undef DBOA_WIDE_LAUNCH
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -83,6 +83,22 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
         "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from tensor memory, 8-column tensor-memory store of a thread's lane (see conv_wide.cu)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float4 a, const float4 b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(a.x)),
+                 "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)),
+                 "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w))
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -161,6 +177,8 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ long long to_fix(float v) { return __double2ll_rn((double)v * FIX); }
 
+// ATM: the transformed operand dy (hi and lo parts) lives in tensor memory instead of shared memory (conv_wide.cu explains why)
+template <bool ATM>
 __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant__ Launch L, const __grid_constant__ CUtensorMap tmdz,
                                                            const __grid_constant__ CUtensorMap tmy, const __grid_constant__ CUtensorMap tmw) {
     extern __shared__ uint8_t smem_raw[];
@@ -198,7 +216,7 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN * NACC) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(ATM ? 512 : BN * NACC) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // gamma of layer c for the output channels this CTA reduces over (parameters: no dependency on the previous kernel)
@@ -273,11 +291,21 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
                 const uint32_t dacc = tmem_d + (uint32_t)((it & (NACC - 1)) * BN);      // truncating accumulation: short chains
                 const uint32_t first = it >= NACC ? 1u : 0u;
                 if (elect_one()) {
+                    if constexpr (ATM) {
+                        const uint32_t tah = tmem_d + (uint32_t)(BN * NACC + ls * 2 * BK), tal = tah + (uint32_t)BK;
 #pragma unroll
-                    for (int kk = 0; kk < BK / 8; ++kk) {
-                        mma_tf32(dacc, dah + kk * KSTEP_A, dbh + kk * KSTEP_B, idesc, kk > 0 ? 1u : first);
-                        mma_tf32(dacc, dah + kk * KSTEP_A, dbl + kk * KSTEP_B, idesc, 1u);
-                        mma_tf32(dacc, dal + kk * KSTEP_A, dbh + kk * KSTEP_B, idesc, 1u);
+                        for (int kk = 0; kk < BK / 8; ++kk) {
+                            mma_tf32_ts(dacc, tah + kk * 8, dbh + kk * KSTEP_B, idesc, kk > 0 ? 1u : first);
+                            mma_tf32_ts(dacc, tah + kk * 8, dbl + kk * KSTEP_B, idesc, 1u);
+                            mma_tf32_ts(dacc, tal + kk * 8, dbh + kk * KSTEP_B, idesc, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < BK / 8; ++kk) {
+                            mma_tf32(dacc, dah + kk * KSTEP_A, dbh + kk * KSTEP_B, idesc, kk > 0 ? 1u : first);
+                            mma_tf32(dacc, dah + kk * KSTEP_A, dbl + kk * KSTEP_B, idesc, 1u);
+                            mma_tf32(dacc, dal + kk * KSTEP_A, dbh + kk * KSTEP_B, idesc, 1u);
+                        }
                     }
                     umma_commit(&l_empty[ls]);
                     umma_commit(&s_empty[sl]);
@@ -291,7 +319,8 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
         pdl_trigger();
     } else {
         // ---- transform warps: GroupNorm_c backward + TF32 split of (dz, y) -> dy hi / lo; split of the weight tile
-        const int r0 = tid >> 3, pc = tid & 7, lc = pc ^ (r0 & 7);
+        // ATM: thread = tile row (= its TMEM lane) x 8 channels kc * 8 .. + 7 of the k-block; only entry 0 of the per-row arrays is used
+        const int r0 = ATM ? (warp & 3) * 32 + lane : tid >> 3, pc = tid & 7, lc = pc ^ (r0 & 7), kc = warp >> 2;
         float* dyb = (L.dy_out != nullptr && nt == 0) ? L.dy_out + (size_t)b * H * W * Cout : nullptr;
         int hq[2], wq[2];                                   // pixel of layer c's output the two rows read at tap (0, 0)
         bool rowok[2];
@@ -300,7 +329,7 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
         for (int q = 0; q < 2; ++q) {
             const int i = r0 + 64 * q, oh = i / W, ow = i - oh * W;
             hq[q] = h0 + oh + pad; wq[q] = ow + pad; rowok[q] = i < rows_valid;
-            dyq[q] = dyb + ((long long)hq[q] * W + wq[q]) * Cout + lc * 4;       // only dereferenced for in-bounds taps
+            dyq[q] = dyb + ((long long)hq[q] * W + wq[q]) * Cout + (ATM ? kc * 8 : lc * 4);       // only dereferenced for in-bounds taps
         }
         int lgw = 0;
         while ((4 << lgw) < Cout) ++lgw;
@@ -326,6 +355,56 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
         const uint32_t slots32 = smem_u32(slots) + offA, tab32 = smem_u32(tab), st32 = smem_u32(sstat);
         const uint32_t lo_a32 = smem_u32(lo_a) + offA, lo_b32 = smem_u32(lo_b) + offA;
         uint32_t slot = slots32;
+        if constexpr (ATM) {
+            const uint32_t rowofs = (uint32_t)r0 * 128u, sw = (uint32_t)(r0 & 7);
+            const uint32_t pa0 = rowofs + (((uint32_t)(2 * kc) ^ sw) << 4), pa1 = rowofs + (((uint32_t)(2 * kc + 1) ^ sw) << 4);
+            const uint32_t ta = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN * NACC + kc * 8);
+            uint32_t sbase = smem_u32(slots);
+#pragma unroll 1
+            for (int it = 0; it < nkb; ++it) {
+                const int ls = it & 1;
+                const int cch = c + kc * 8;                      // 8 channels of one GroupNorm group (groups are >= 16 channels wide)
+                const uint32_t sg = st32 + (uint32_t)(cch >> lgw) * 4u;
+                const float4 ga0 = lds128(tab32 + (uint32_t)(cch - tc0) * 4u), ga1 = lds128(tab32 + (uint32_t)(cch - tc0) * 4u + 16u);
+                const float mu = lds32(sg), gb = lds32(sg + 16), gc = lds32(sg + 32);
+                const bool desig = dyb != nullptr && (ks == 1 || (r == 1 && s == 1));
+                const int tapoff = c - (r * W + s) * Cout;
+                mbar_wait(&s_full[sl], ph_full);
+                if (it >= 2) mbar_wait(&l_empty[ls], (uint32_t)(((it >> 1) - 1) & 1));
+                const float4 d0 = lds128(sbase + pa0), d1 = lds128(sbase + pa1);
+                const float4 y0 = lds128(sbase + A_TILE + pa0), y1 = lds128(sbase + A_TILE + pa1);
+                const float4 vw = lds128(sbase + 2 * A_TILE + offA);
+                const bool in0 = rowok[0] && (unsigned)(hq[0] - r) < (unsigned)H && (unsigned)(wq[0] - s) < (unsigned)W;
+                float4 o0, o1;
+                o0.x = fmaf(mu - y0.x, gb, fmaf(d0.x, ga0.x, gc)); o0.y = fmaf(mu - y0.y, gb, fmaf(d0.y, ga0.y, gc));
+                o0.z = fmaf(mu - y0.z, gb, fmaf(d0.z, ga0.z, gc)); o0.w = fmaf(mu - y0.w, gb, fmaf(d0.w, ga0.w, gc));
+                o1.x = fmaf(mu - y1.x, gb, fmaf(d1.x, ga1.x, gc)); o1.y = fmaf(mu - y1.y, gb, fmaf(d1.y, ga1.y, gc));
+                o1.z = fmaf(mu - y1.z, gb, fmaf(d1.z, ga1.z, gc)); o1.w = fmaf(mu - y1.w, gb, fmaf(d1.w, ga1.w, gc));
+                if (!in0) { o0 = make_float4(0.f, 0.f, 0.f, 0.f); o1 = o0; }
+                if (desig && in0) {
+                    *reinterpret_cast<float4*>(dyq[0] + tapoff) = o0;
+                    *reinterpret_cast<float4*>(dyq[0] + tapoff + 4) = o1;
+                }
+                const float4 h0v = make_float4(tf32_hi(o0.x), tf32_hi(o0.y), tf32_hi(o0.z), tf32_hi(o0.w));
+                const float4 h1v = make_float4(tf32_hi(o1.x), tf32_hi(o1.y), tf32_hi(o1.z), tf32_hi(o1.w));
+                const float4 hw = make_float4(tf32_hi(vw.x), tf32_hi(vw.y), tf32_hi(vw.z), tf32_hi(vw.w));
+                const uint32_t tah = ta + (uint32_t)(ls * 2 * BK);
+                tmem_st8(tah, h0v, h1v);
+                tmem_st8(tah + BK, make_float4(o0.x - h0v.x, o0.y - h0v.y, o0.z - h0v.z, o0.w - h0v.w),
+                         make_float4(o1.x - h1v.x, o1.y - h1v.y, o1.z - h1v.z, o1.w - h1v.w));
+                sts128(sbase + 2 * A_TILE + offA, hw);
+                sts128(lo_b32 + ls * B_TILE, make_float4(vw.x - hw.x, vw.y - hw.y, vw.z - hw.z, vw.w - hw.w));
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&l_full[ls]);
+                sbase += SLOT;
+                if (++sl == D) { sl = 0; sbase = smem_u32(slots); ph_full ^= 1u; }
+                c += BK;
+                if (c >= Cout) { c = 0; if (++s == ks) { s = 0; ++r; } }
+            }
+        } else {
 #pragma unroll 1
         for (int it = 0; it < nkb; ++it) {
             const int ls = it & 1;
@@ -369,6 +448,7 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
             if (++sl == D) { sl = 0; slot = slots32; ph_full ^= 1u; }
             c += BK;
             if (c >= Cout) { c = 0; if (++s == ks) { s = 0; ++r; } }
+        }
         }
     }
     if (nkb > 0) mbar_wait(done, 0u);
@@ -526,7 +606,7 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
     if (nz > 1) cluster.sync();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN * NACC) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(ATM ? 512 : BN * NACC) : "memory");
 }
 
 // Stand-alone version of the epilogue above for the seams with the unfused kernels (after avgpool_bwd; after a stride-2 block):
@@ -640,7 +720,8 @@ int dgrad_wide(const DgradFused& f, const ConvDims& d, cudaStream_t st, bool pdl
     const CUtensorMap* tmy = static_cast<const CUtensorMap*>(tma_act_map(f.y_c, d.B, d.Hi, d.Wi, d.Cout, d.Wi, L.bh, false, 1));
     const CUtensorMap* tmw = static_cast<const CUtensorMap*>(tma_weight_map_mn(f.w, d.kh * d.kw * d.Cin, d.Cout));
     if (!tmdz || !tmy || !tmw) return DBOA_ERR_CUDA;
-    return launch_ex(dz::dgrad_wide_kernel, dim3(tiles * nz), dim3(dz::NT), smem, st, dim3(nz, 1, 1), pdl, L, *tmdz, *tmy, *tmw);
+    return conv_wide_operand_tmem() ? launch_ex(dz::dgrad_wide_kernel<true>, dim3(tiles * nz), dim3(dz::NT), smem, st, dim3(nz, 1, 1), pdl, L, *tmdz, *tmy, *tmw)
+                                    : launch_ex(dz::dgrad_wide_kernel<false>, dim3(tiles * nz), dim3(dz::NT), smem, st, dim3(nz, 1, 1), pdl, L, *tmdz, *tmy, *tmw);
 }
 
 int gn_bwd_prep(const float* dA, const float* mask, float* out, const DgradPrep& p, int B, int HW, int C, cudaStream_t st) {

@@ -46,6 +46,8 @@ struct FusedConv {
 bool conv_wide_ok(const FusedConv& d);
 int conv_wide_plan(const FusedConv* d, int nprob, int B);
 void conv_wide_set_cta_budget(int n);                                  // 0: all SMs
+void conv_wide_set_operand_tmem(bool on);                              // transformed activation operand of conv_wide / dgrad_wide in tensor memory
+bool conv_wide_operand_tmem();
 int conv_wide_launch(const FusedConv* d, int nprob, int B, int nz, const float* next_w, size_t next_bytes, cudaStream_t st, bool pdl);
 int gn_acc_res_avgpool(const float* y, const float* res, const float* acc, const float* gamma, const float* beta, float* a_out, float* stats_out,
                        float* out, int B, int HW, int C, int ld, int ncopy, size_t copy_stride, cudaStream_t st);

@@ -45,6 +45,12 @@ int dboa_set_fused_backward(int enable);
 /* CTAs (= SMs) the fused convolutions of the following dboa_hmr_forward calls may use; 0 = all.  Forwards issued side by side
  * on different streams share the device when each is given about half of it (a fused launch owns its SMs). */
 int dboa_set_forward_cta_budget(int n);
+/* 1: the fused convolution / data-gradient kernels keep the transformed activation operand (TF32 hi and lo parts) in tensor
+ * memory and the tensor core reads only the weight operand from shared memory; 0: both operands in shared memory (the A/B
+ * reference of the same kernels).  Same results to fp32 rounding of the same products (the split is identical).
+ * Environment: DBOA_OPERAND_TMEM. */
+int dboa_set_operand_tmem(int enable);
+int dboa_get_operand_tmem(void);
 
 /* ---- HMR regressor: parameter arena and tape layout ----------------------------------------
  * replaces: model/hmr.py:67-124 (HMR.__init__/_make_layer state_dict contract).

@@ -10,7 +10,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 for B in (1, 2, 9):
     x = torch.randn(B, 3, 224, 224, device='cuda')
     tape = torch.empty(hmr_mod.tape_floats(B), device='cuda')
-    for fused in (0, 1):
+    for fused in ((1,) if os.environ.get('FWD_FUSED_ONLY') == '1' else (0, 1)):
         lib.dboa_set_fused_forward(fused)
         for flush_l2 in (True, False):
             ts = []
