@@ -50,6 +50,8 @@ SIGNATURES = {
     'dboa_set_forward_cta_budget': (I, [I]),
     'dboa_set_operand_tmem': (I, [I]),
     'dboa_get_operand_tmem': (I, []),
+    'dboa_set_chain_flags': (I, [I]),
+    'dboa_get_chain_flags': (I, []),
     'dboa_dgrad_fused': (I, [C.POINTER(DgradFusedStruct), I, I, I, I, I, P]),
     'dboa_conv_fused_part_floats': (L, [I, I, I]),
     'dboa_conv_fused_fwd': (I, [C.POINTER(FusedConvStruct), I, I, P]),

@@ -19,6 +19,8 @@ void hmr_arm_bucket_events(cudaEvent_t e0, cudaEvent_t e1, cudaEvent_t e2);
 long long hmr_bucket_offset(int k);
 void hmr_set_fused_forward(bool on);
 void hmr_set_fused_backward(bool on);
+void hmr_set_chain_flags(bool on);
+bool hmr_chain_flags();
 bool hmr_fused_forward();
 int hmr_num_params();
 long long hmr_arena_floats();
@@ -76,6 +78,8 @@ int dboa_get_fused_forward(void) { return hmr_fused_forward() ? 1 : 0; }
 int dboa_set_fused_backward(int enable) { hmr_set_fused_backward(enable != 0); return DBOA_OK; }
 int dboa_set_forward_cta_budget(int n) { conv_wide_set_cta_budget(n < 0 ? 0 : n); return DBOA_OK; }
 int dboa_set_operand_tmem(int enable) { conv_wide_set_operand_tmem(enable != 0); return DBOA_OK; }
+int dboa_set_chain_flags(int enable) { hmr_set_chain_flags(enable != 0); return DBOA_OK; }
+int dboa_get_chain_flags(void) { return hmr_chain_flags() ? 1 : 0; }
 int dboa_get_operand_tmem(void) { return conv_wide_operand_tmem() ? 1 : 0; }
 
 int dboa_hmr_num_params(void) { return hmr_num_params(); }

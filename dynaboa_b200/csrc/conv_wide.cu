@@ -63,6 +63,11 @@ struct Launch {
     int nprob, nz, per, D, tabc;
     const float* next_w;         // weights of the NEXT launch: prefetched into L2 by this one
     unsigned long long next_bytes;
+    // chain dependency (see chain_wait): counter every CTA of the PREVIOUS fused launch increments when its outputs are stored,
+    // the value it reaches, and this launch's own counter; NULL = ordinary programmatic dependency (griddepcontrol.wait)
+    const unsigned* dep_flag;
+    unsigned dep_expect;
+    unsigned* done_flag;
     int launch_id;
 };
 
@@ -70,6 +75,8 @@ struct Launch {
 // launch at the phase boundaries, g_ftl[launch][cta][16], and per-k-block stamps of CTA 0; compiled out of the product library.
 #ifdef DBOA_TIMELINE
 __device__ unsigned long long* g_ftl = nullptr;
+__device__ int g_knobs = 0;          // diagnostic knobs (results are WRONG with any of them set): 1 no MMAs, 2 no transform body, 4 no cluster reduction
+#define KNOB(b) ((g_knobs & (b)) != 0)
 #define FTL(i)                                                                                          \
     do {                                                                                                \
         if (threadIdx.x == 0 && g_ftl != nullptr && blockIdx.x < 256 && L.launch_id < 128) {           \
@@ -89,6 +96,7 @@ __device__ unsigned long long* g_ftl = nullptr;
 #else
 #define FTL(i)
 #define FTI(it, j)
+#define KNOB(b) false
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -194,6 +202,24 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+// Dependency of a fused launch on the previous fused launch of the same forward WITHOUT waiting for that grid to complete:
+// griddepcontrol.wait returns only when every CTA of the producer has exited and its memory is flushed, which puts the producer's
+// exit barrier (cluster.sync: peers still read this CTA's shared memory), its tear-down and the completion signalling (~1.5 us) on
+// the critical path of every layer.  Here every producer CTA increments a counter right after its last global store / atomic
+// (fence + atomic = release), and the consumer's two readers of producer data -- the thread that issues the activation TMA loads
+// and the threads that read the statistics accumulators -- spin on it with acquire loads.  No deadlock: a dependent grid is only
+// launched once every CTA of its predecessor has executed griddepcontrol.launch_dependents, i.e. is resident, so a spinning
+// consumer never holds an SM that its producer still needs.  Bounded: a protocol error traps instead of hanging the device.
+__device__ __forceinline__ void chain_wait(const unsigned* flag, unsigned expect) {
+    long long t0 = 0;
+    while (true) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= expect) break;
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 #define PW(field) (second ? L.p[1].field : L.p[0].field)
@@ -247,7 +273,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
 
     if (tid == 0) {
         for (int s = 0; s < DMAX; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&l_full[s], NTW); mbar_init(&l_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&l_full[s], ATM ? NTW / 2 : NTW); mbar_init(&l_empty[s], 1); }
         mbar_init(done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -288,8 +314,14 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
                 mbar_expect_tx(&s_full[it], a_bytes * (HAS_RES ? 2 : 1) + B_TILE);
                 tma_load_2d(smem_u32(slots + (size_t)it * slot_bytes + A_TILE * (HAS_RES ? 2 : 1)), tmw, (kb_begin + it) * BK, n0, &s_full[it]);
             }
-            pdl_wait();
-            pdl_trigger();
+            if (L.dep_flag != nullptr) {
+                pdl_trigger();
+                chain_wait(L.dep_flag, L.dep_expect);
+                asm volatile("fence.proxy.async;" ::: "memory");        // the producer's generic-proxy stores before this thread's TMA reads
+            } else {
+                pdl_wait();
+                pdl_trigger();
+            }
             for (int it = 0; it < nkb; ++it) {
                 const int sl = it % D;
                 uint8_t* slot = slots + (size_t)sl * slot_bytes;
@@ -314,7 +346,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
                 for (unsigned long long o = beg + (unsigned long long)(lane - 1) * 1024; o < beg + chunk && o + 1024 <= L.next_bytes; o += 31 * 1024)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], 1024;" ::"l"(reinterpret_cast<const char*>(L.next_w) + o) : "memory");
             }
-            pdl_wait();
+            if (L.dep_flag == nullptr) pdl_wait();
             pdl_trigger();
         }
     } else if (warp == W_MMA) {
@@ -344,7 +376,8 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
                 const uint32_t dacc = tmem_d + (uint32_t)((it & (NACC - 1)) * BN);
                 const uint32_t first = it >= NACC ? 1u : 0u;
                 if (elect_one()) {
-                    if constexpr (ATM) {
+                    if (KNOB(1)) {
+                    } else if constexpr (ATM) {
                         // A hi / lo of stage ls: TMEM columns ACOL + 64 ls + {0..31, 32..63}, 8 columns per k-step
                         const uint32_t tah = tmem_d + (uint32_t)(BN * NACC + ls * 2 * BK), tal = tah + (uint32_t)BK;
 #pragma unroll
@@ -370,16 +403,16 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
             }
             if (elect_one()) umma_commit(done);
         }
-        pdl_wait();
+        if (L.dep_flag == nullptr) pdl_wait();
         pdl_trigger();
     } else {
         // =====================================================================================
         // transform warps: thread t owns float4 t and t + 512 of the activation tile (rows r0 = t >> 3 and r0 + 64, the same
         // physical 16-byte chunk pc = t & 7, hence the same logical chunk lc = pc ^ (r0 & 7)) and float4 t of the weight tile
         // =====================================================================================
-        // ATM: thread = tile row (= its TMEM lane: 32 * (warp % 4) + lane) x 8 channels kc * 8 .. + 7 of the k-block, plus float4 t of the
-        // weight tile; only entry 0 of the per-row arrays is used
-        const int r0 = ATM ? (warp & 3) * 32 + lane : tid >> 3, pc = tid & 7, lc = pc ^ (r0 & 7), kc = warp >> 2;
+        // ATM: thread = tile row (= its TMEM lane: 32 * (warp % 4) + lane) x 16 channels kh * 16 .. + 15 of every second k-block; only
+        // entry 0 of the per-row arrays is used
+        const int r0 = ATM ? (warp & 3) * 32 + lane : tid >> 3, pc = tid & 7, lc = pc ^ (r0 & 7), kh = (warp >> 2) & 1, grp = warp >> 3;
         // per-thread invariants of the two activation rows: input coordinates of tap (0, 0), validity, tape pointer of tap (0, 0)
         float* ab = (MODE >= 1 && PW(a_out) != nullptr && nt == 0) ? PW(a_out) + (size_t)b * Hi * Wi * Cin : nullptr;
         int hq[2], wq[2];
@@ -389,7 +422,7 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
         for (int q = 0; q < 2; ++q) {
             const int i = r0 + 64 * q, oh = i / Wo, ow = i - oh * Wo;
             hq[q] = (h0 + oh) * stride - pad; wq[q] = ow * stride - pad; rowok[q] = i < rows_valid;
-            abq[q] = ab + ((long long)hq[q] * Wi + wq[q]) * Cin + (ATM ? kc * 8 : lc * 4);      // only dereferenced for in-bounds taps
+            abq[q] = ab + ((long long)hq[q] * Wi + wq[q]) * Cin + (ATM ? kh * 16 : lc * 4);      // only dereferenced for in-bounds taps
         }
         int lgw = 0;
         while ((4 << lgw) < Cin) ++lgw;
@@ -398,8 +431,14 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
         const double inv_nfix = 1.0 / ((double)Hi * Wi * (Cin >> 2) * FIX);
         int r, s, c;
         tap_of(kb_begin, r, s, c);
-        pdl_wait();
-        pdl_trigger();
+        if (L.dep_flag != nullptr) {
+            // only the threads that read the statistics accumulators wait; the barrier after them orders everybody else
+            pdl_trigger();
+            if (MODE == 0 || tid < (MODE == 3 ? 8 : 4)) chain_wait(L.dep_flag, L.dep_expect);
+        } else {
+            pdl_wait();
+            pdl_trigger();
+        }
         FTL(2);
         if (MODE >= 1) {
             // statistics of the operand's GroupNorm(s): 8 fixed-point sums per sample -> (mean, rstd)
@@ -436,78 +475,118 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
         int sl = 0;
         uint32_t ph_full = 0;
         const uint32_t slots32 = smem_u32(slots), tab32 = smem_u32(tab), tabc4 = (uint32_t)L.tabc * 4u;
-        const uint32_t offA = (uint32_t)tid * 16u, offA2 = offA + (uint32_t)NTT * 16u;
+        const uint32_t offA = (uint32_t)tid * 16u;
         const uint32_t lo_a32 = smem_u32(lo_a) + offA, lo_b32 = smem_u32(lo_b) + offA;
         const uint32_t wofs = A_TILE * (HAS_RES ? 2 : 1);
         uint32_t slot = slots32 + offA;                                  // this thread's first chunk inside the current slot
         if constexpr (ATM) {
             // The transformed activation tile goes to TENSOR memory (tcgen05.st, thread = row) and the MMAs read it from there: per
             // k-block the shared-memory pipe carries 24 KB of raw reads + 16 KB of weight hi / lo writes + 24 KB of tensor-core B
-            // reads instead of 24 + 48 + 72 KB (measured: the k-loop of the all-shared-memory variant is shared-memory-bandwidth
-            // bound, L1/TEX throughput ~90 % inside the loop).  Row r's logical 16-byte chunk j sits at physical chunk j ^ (r & 7)
-            // (128-byte swizzle of the TMA box): a quarter warp reads 8 different physical chunks -> conflict-free.
+            // reads instead of 24 + 48 + 72 KB.  Row r's logical 16-byte chunk j sits at physical chunk j ^ (r & 7) (128-byte
+            // swizzle of the TMA box): a quarter warp reads 8 different physical chunks -> conflict-free.
+            // TWO GROUPS of 8 warps alternate k-blocks (group g: k-blocks g, g + 2, ...; stage g of the TMEM operand and of the
+            // weight lo tile): one k-block is a dependent chain  barrier wait -> LDS -> FMA -> STTM / STS -> wait::st -> proxy
+            // fence -> arrive  of ~600 cycles that 16 warps in lock step cannot hide (stall samples of the one-group loop: LDS
+            // scoreboard, FENCE.VIEW.ASYNC and the barrier polls); with two groups the chains of consecutive k-blocks overlap.
+            // Thread = row r0 x 16 channels (logical chunks 4 kh .. 4 kh + 3) + float4 tg and tg + 256 of the weight tile.
             const uint32_t rowofs = (uint32_t)r0 * 128u, sw = (uint32_t)(r0 & 7);
-            const uint32_t pa0 = rowofs + (((uint32_t)(2 * kc) ^ sw) << 4), pa1 = rowofs + (((uint32_t)(2 * kc + 1) ^ sw) << 4);
-            const uint32_t ta = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN * NACC + kc * 8);
-            uint32_t sbase = slots32;
+            uint32_t pa[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pa[j] = rowofs + (((uint32_t)(4 * kh + j) ^ sw) << 4);
+            const uint32_t ta = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN * NACC + grp * 2 * BK + kh * 16);
+            const uint32_t offW = (uint32_t)((warp & 7) * 32 + lane) * 16u;
+            const uint32_t lob = smem_u32(lo_b) + (uint32_t)grp * B_TILE + offW;
+            auto step = [&]() { c += BK; if (c >= Cin) { c = 0; if (++s == ks) { s = 0; ++r; } } };
+            if (grp == 1) step();
+            int sl = grp % D;
+            uint32_t ph_full = (uint32_t)((grp / D) & 1);
+            uint32_t sbase = slots32 + (uint32_t)sl * slot_bytes;
 #pragma unroll 1
-            for (int it = 0; it < nkb; ++it) {
-                const int ls = it & 1;
-                const uint32_t ti = tab32 + (uint32_t)(c - tc0 + kc * 8) * 4u;   // this warp's 8 channels inside the channel table (broadcast reads)
-                float4 sca = make_float4(1.f, 1.f, 1.f, 1.f), scb = sca, sha = make_float4(0.f, 0.f, 0.f, 0.f), shb = sha, s2a = sca, s2b = sca;
-                if (MODE >= 1) {
-                    sca = lds128(ti); scb = lds128(ti + 16); sha = lds128(ti + tabc4); shb = lds128(ti + tabc4 + 16);
-                    if (MODE == 3) { s2a = lds128(ti + 2 * tabc4); s2b = lds128(ti + 2 * tabc4 + 16); }
-                }
+            for (int it = grp; it < nkb; it += 2) {
+                const uint32_t ti = tab32 + (uint32_t)(c - tc0 + kh * 16) * 4u;   // this warp's 16 channels inside the channel table (broadcast reads)
                 const bool desig = ab != nullptr && (ks == 1 ? stride == 1 : (stride == 1 ? (r == 1 && s == 1) : (r >= 1 && s >= 1)));
                 const int tapoff = (r * Wi + s) * Cin + c;
-                mbar_wait(&s_full[sl], ph_full);
-                if (it >= 2) mbar_wait(&l_empty[ls], (uint32_t)(((it >> 1) - 1) & 1));
-                float4 v0 = lds128(sbase + pa0), v1 = lds128(sbase + pa1);
-                const float4 vw = lds128(sbase + wofs + offA);
                 const bool in0 = rowok[0] && (unsigned)(hq[0] + r) < (unsigned)Hi && (unsigned)(wq[0] + s) < (unsigned)Wi;
+                if ((tid & 255) == 0) FTI(it, 0);
+                mbar_wait(&s_full[sl], ph_full);
+                if ((tid & 255) == 0) FTI(it, 1);
+                float4 v[4], q[4];
+                if (KNOB(2)) {
+                    if (it >= 2) mbar_wait(&l_empty[grp], (uint32_t)(((it >> 1) - 1) & 1));
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&l_full[grp]);
+                    sl += 2;
+                    while (sl >= D) { sl -= D; ph_full ^= 1u; }
+                    sbase = slots32 + (uint32_t)sl * slot_bytes;
+                    step(); step();
+                    continue;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = lds128(sbase + pa[j]);
+                if (MODE >= 2) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) q[j] = lds128(sbase + A_TILE + pa[j]);
+                }
+                const float4 w0 = lds128(sbase + wofs + offW), w1 = lds128(sbase + wofs + offW + 4096u);
                 if (MODE >= 1) {
-                    float4 q0, q1;
-                    if (MODE >= 2) { q0 = lds128(sbase + A_TILE + pa0); q1 = lds128(sbase + A_TILE + pa1); }
-                    v0.x = fmaf(v0.x, sca.x, sha.x); v0.y = fmaf(v0.y, sca.y, sha.y); v0.z = fmaf(v0.z, sca.z, sha.z); v0.w = fmaf(v0.w, sca.w, sha.w);
-                    v1.x = fmaf(v1.x, scb.x, shb.x); v1.y = fmaf(v1.y, scb.y, shb.y); v1.z = fmaf(v1.z, scb.z, shb.z); v1.w = fmaf(v1.w, scb.w, shb.w);
-                    if (MODE == 2) {
-                        v0.x += q0.x; v0.y += q0.y; v0.z += q0.z; v0.w += q0.w;
-                        v1.x += q1.x; v1.y += q1.y; v1.z += q1.z; v1.w += q1.w;
-                    } else if (MODE == 3) {
-                        v0.x = fmaf(q0.x, s2a.x, v0.x); v0.y = fmaf(q0.y, s2a.y, v0.y); v0.z = fmaf(q0.z, s2a.z, v0.z); v0.w = fmaf(q0.w, s2a.w, v0.w);
-                        v1.x = fmaf(q1.x, s2b.x, v1.x); v1.y = fmaf(q1.y, s2b.y, v1.y); v1.z = fmaf(q1.z, s2b.z, v1.z); v1.w = fmaf(q1.w, s2b.w, v1.w);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 sc = lds128(ti + 16 * j), sh = lds128(ti + tabc4 + 16 * j);
+                        v[j].x = fmaf(v[j].x, sc.x, sh.x); v[j].y = fmaf(v[j].y, sc.y, sh.y); v[j].z = fmaf(v[j].z, sc.z, sh.z); v[j].w = fmaf(v[j].w, sc.w, sh.w);
+                        if (MODE == 2) {
+                            v[j].x += q[j].x; v[j].y += q[j].y; v[j].z += q[j].z; v[j].w += q[j].w;
+                        } else if (MODE == 3) {
+                            const float4 s2 = lds128(ti + 2 * tabc4 + 16 * j);
+                            v[j].x = fmaf(q[j].x, s2.x, v[j].x); v[j].y = fmaf(q[j].y, s2.y, v[j].y); v[j].z = fmaf(q[j].z, s2.z, v[j].z); v[j].w = fmaf(q[j].w, s2.w, v[j].w);
+                        }
+                        // padding is zero in the ACTIVATION domain
+                        v[j].x = in0 ? fmaxf(v[j].x, 0.f) : 0.f; v[j].y = in0 ? fmaxf(v[j].y, 0.f) : 0.f;
+                        v[j].z = in0 ? fmaxf(v[j].z, 0.f) : 0.f; v[j].w = in0 ? fmaxf(v[j].w, 0.f) : 0.f;
                     }
-                    // padding is zero in the ACTIVATION domain
-                    v0.x = in0 ? fmaxf(v0.x, 0.f) : 0.f; v0.y = in0 ? fmaxf(v0.y, 0.f) : 0.f; v0.z = in0 ? fmaxf(v0.z, 0.f) : 0.f; v0.w = in0 ? fmaxf(v0.w, 0.f) : 0.f;
-                    v1.x = in0 ? fmaxf(v1.x, 0.f) : 0.f; v1.y = in0 ? fmaxf(v1.y, 0.f) : 0.f; v1.z = in0 ? fmaxf(v1.z, 0.f) : 0.f; v1.w = in0 ? fmaxf(v1.w, 0.f) : 0.f;
                     if (desig && in0) {
-                        *reinterpret_cast<float4*>(abq[0] + tapoff) = v0;
-                        *reinterpret_cast<float4*>(abq[0] + tapoff + 4) = v1;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(abq[0] + tapoff + 4 * j) = v[j];
                     }
                 } else if (!rowok[0]) {
                     // rows the box did not deliver hold stale shared memory: keep them finite
-                    v0 = make_float4(0.f, 0.f, 0.f, 0.f); v1 = v0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                const float4 h0v = make_float4(tf32_hi(v0.x), tf32_hi(v0.y), tf32_hi(v0.z), tf32_hi(v0.w));
-                const float4 h1v = make_float4(tf32_hi(v1.x), tf32_hi(v1.y), tf32_hi(v1.z), tf32_hi(v1.w));
-                const float4 hw = make_float4(tf32_hi(vw.x), tf32_hi(vw.y), tf32_hi(vw.z), tf32_hi(vw.w));
-                const uint32_t tah = ta + (uint32_t)(ls * 2 * BK);
-                tmem_st8(tah, h0v, h1v);
-                tmem_st8(tah + BK, make_float4(v0.x - h0v.x, v0.y - h0v.y, v0.z - h0v.z, v0.w - h0v.w),
-                         make_float4(v1.x - h1v.x, v1.y - h1v.y, v1.z - h1v.z, v1.w - h1v.w));
-                sts128(sbase + wofs + offA, hw);
-                sts128(lo_b32 + ls * B_TILE, make_float4(vw.x - hw.x, vw.y - hw.y, vw.z - hw.z, vw.w - hw.w));
+                float4 h[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    h[j] = make_float4(tf32_hi(v[j].x), tf32_hi(v[j].y), tf32_hi(v[j].z), tf32_hi(v[j].w));
+                    v[j] = make_float4(v[j].x - h[j].x, v[j].y - h[j].y, v[j].z - h[j].z, v[j].w - h[j].w);
+                }
+                const float4 hw0 = make_float4(tf32_hi(w0.x), tf32_hi(w0.y), tf32_hi(w0.z), tf32_hi(w0.w));
+                const float4 hw1 = make_float4(tf32_hi(w1.x), tf32_hi(w1.y), tf32_hi(w1.z), tf32_hi(w1.w));
+                // the MMAs of k-block it - 2 (the previous user of this group's TMEM / lo stage) must have completed
+                if ((tid & 255) == 0) FTI(it, 2);
+                if (it >= 2) mbar_wait(&l_empty[grp], (uint32_t)(((it >> 1) - 1) & 1));
+                if ((tid & 255) == 0) FTI(it, 4);
+                tmem_st8(ta, h[0], h[1]);
+                tmem_st8(ta + 8, h[2], h[3]);
+                tmem_st8(ta + BK, v[0], v[1]);
+                tmem_st8(ta + BK + 8, v[2], v[3]);
+                sts128(sbase + wofs + offW, hw0);
+                sts128(sbase + wofs + offW + 4096u, hw1);
+                sts128(lob, make_float4(w0.x - hw0.x, w0.y - hw0.y, w0.z - hw0.z, w0.w - hw0.w));
+                sts128(lob + 4096u, make_float4(w1.x - hw1.x, w1.y - hw1.y, w1.z - hw1.z, w1.w - hw1.w));
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&l_full[ls]);
+                if (lane == 0) mbar_arrive(&l_full[grp]);
+                if ((tid & 255) == 0) FTI(it, 3);
                 if (it == 0) FTL(3);
-                sbase += slot_bytes;
-                if (++sl == D) { sl = 0; sbase = slots32; ph_full ^= 1u; }
-                c += BK;
-                if (c >= Cin) { c = 0; if (++s == ks) { s = 0; ++r; } }
+                // this group's next k-block: two steps of the slot ring and of the reduction cursor
+                sl += 2;
+                while (sl >= D) { sl -= D; ph_full ^= 1u; }
+                sbase = slots32 + (uint32_t)sl * slot_bytes;
+                step(); step();
             }
         } else {
 #pragma unroll 1
@@ -644,17 +723,28 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
         for (int k = row0; k < rows_per; k += 32, lr += 32, ra += 32 * RED_LD * 4, Yp += ystep) {
             if (lr < rows_valid) {
                 float4 acc;
-                if (nz == 1) {
+                if (nz == 1 || KNOB(4)) {
                     acc = lds128(ra);
                 } else {
+                    // four DSMEM loads in flight per round (one remote-latency round per four K-slices); the additions keep the
+                    // order of the slices
                     acc = ldc128(ra, 0);
                     const float4 q1 = ldc128(ra, 1);
-                    acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
+                    if (nz >= 4) {
+                        const float4 q2 = ldc128(ra, 2), q3 = ldc128(ra, 3);
+                        acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
+                        acc.x += q2.x; acc.y += q2.y; acc.z += q2.z; acc.w += q2.w;
+                        acc.x += q3.x; acc.y += q3.y; acc.z += q3.z; acc.w += q3.w;
 #pragma unroll 1
-                    for (int z = 2; z < nz; z += 2) {
-                        const float4 qa = ldc128(ra, z), qb = ldc128(ra, z + 1);
-                        acc.x += qa.x; acc.y += qa.y; acc.z += qa.z; acc.w += qa.w;
-                        acc.x += qb.x; acc.y += qb.y; acc.z += qb.z; acc.w += qb.w;
+                        for (int z = 4; z < nz; z += 4) {
+                            const float4 qa = ldc128(ra, z), qb = ldc128(ra, z + 1), qc = ldc128(ra, z + 2), qd = ldc128(ra, z + 3);
+                            acc.x += qa.x; acc.y += qa.y; acc.z += qa.z; acc.w += qa.w;
+                            acc.x += qb.x; acc.y += qb.y; acc.z += qb.z; acc.w += qb.w;
+                            acc.x += qc.x; acc.y += qc.y; acc.z += qc.z; acc.w += qc.w;
+                            acc.x += qd.x; acc.y += qd.y; acc.z += qd.z; acc.w += qd.w;
+                        }
+                    } else {
+                        acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
                     }
                 }
                 *reinterpret_cast<float4*>(Yp) = acc;
@@ -689,6 +779,14 @@ __global__ void __launch_bounds__(NT, 1) conv_wide_kernel(const __grid_constant_
 #pragma unroll
         for (int w = 0; w < NTW; ++w) t += wsum[(w * 4 + gi) * 2 + (tid & 1)];
         atomicAdd(PW(acc_out) + ((size_t)b * 4 + g) * 2 + (tid & 1), t);
+    }
+    if (L.done_flag != nullptr && warp == 0) {
+        // outputs (stored before the barrier above), tape writes and the statistics atomics of this CTA are complete: release
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            atomicAdd(L.done_flag, 1u);
+        }
     }
     FTL(7);
     if (nz > 1) cluster.sync();
@@ -800,7 +898,7 @@ bool conv_wide_ok(const FusedConv& d) {
 // Measured (bench.py, C2, 1 x B200): 143.3 frames/s with all 148 SMs per launch, 151.8 with 96, 151.2 with 74, 148.1 with 64; the
 // isolated forward is also slightly faster with fewer K-slices (0.831 vs 0.855 ms).  Default 96; DBOA_FUSED_MAX_CTAS overrides.
 // activation operand of the fused kernels in tensor memory (DBOA_OPERAND_TMEM=0 / dboa_set_operand_tmem(0): all-shared-memory variant)
-static bool g_operand_tmem = [] { const char* e = getenv("DBOA_OPERAND_TMEM"); return e ? e[0] != '0' : false; }();
+static bool g_operand_tmem = [] { const char* e = getenv("DBOA_OPERAND_TMEM"); return e ? e[0] != '0' : true; }();
 void conv_wide_set_operand_tmem(bool on) { g_operand_tmem = on; }
 bool conv_wide_operand_tmem() { return g_operand_tmem; }
 static int g_cta_budget = [] { const char* e = getenv("DBOA_FUSED_MAX_CTAS"); int v = e ? atoi(e) : 96; return v; }();
@@ -826,13 +924,15 @@ int conv_wide_plan(const FusedConv* d, int nprob, int B) {
 
 #ifdef DBOA_TIMELINE
 static int g_wide_launch_id = 0;
+extern "C" int dboa_debug_set_fused_knobs(int knobs) { return cudaMemcpyToSymbol(wz::g_knobs, &knobs, sizeof(knobs)) == cudaSuccess ? 0 : -3; }
 extern "C" int dboa_debug_set_fused_timeline(unsigned long long* buf) {
     g_wide_launch_id = 0;
     return cudaMemcpyToSymbol(wz::g_ftl, &buf, sizeof(buf)) == cudaSuccess ? 0 : -3;
 }
 #endif
 
-int conv_wide_launch(const FusedConv* d, int nprob, int B, int nz, const float* next_w, size_t next_bytes, cudaStream_t st, bool pdl) {
+int conv_wide_launch(const FusedConv* d, int nprob, int B, int nz, const float* next_w, size_t next_bytes, cudaStream_t st, bool pdl,
+                     const ChainDep* dep) {
     if (nprob < 1 || nprob > 2 || B < 1) return DBOA_ERR_ARG;
     wz::Launch L;
     memset(&L, 0, sizeof L);
@@ -875,6 +975,11 @@ int conv_wide_launch(const FusedConv* d, int nprob, int B, int nz, const float* 
     const size_t smem = fixed + (size_t)D * slot;
     if (smem > 227 * 1024) return DBOA_ERR_SHAPE;
     const dim3 grid(total * nz), block(wz::NT), cl(nz, 1, 1);
+    if (dep != nullptr) {
+        // mode 0 has no statistics barrier behind which the other transform threads could be ordered: every thread waits there
+        L.dep_flag = pdl ? dep->wait_flag : nullptr; L.dep_expect = dep->wait_count; L.done_flag = dep->signal_flag;
+        if (dep->signal_count != nullptr) *dep->signal_count = grid.x;
+    }
 #define DBOA_WIDE_LAUNCH(M)                                                                                                                          \
     (g_operand_tmem ? launch_ex(wz::conv_wide_kernel<M, true>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr[0], *tmr[1], *tmw[0], *tmw[1]) \
                     : launch_ex(wz::conv_wide_kernel<M, false>, grid, block, smem, st, cl, pdl, L, *tmx[0], *tmx[1], *tmr[0], *tmr[1], *tmw[0], *tmw[1]))

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
 
     if (tid == 0) {
         for (int s = 0; s < DMAX; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&l_full[s], NTW); mbar_init(&l_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&l_full[s], ATM ? NTW / 2 : NTW); mbar_init(&l_empty[s], 1); }
         mbar_init(done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -319,8 +319,8 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
         pdl_trigger();
     } else {
         // ---- transform warps: GroupNorm_c backward + TF32 split of (dz, y) -> dy hi / lo; split of the weight tile
-        // ATM: thread = tile row (= its TMEM lane) x 8 channels kc * 8 .. + 7 of the k-block; only entry 0 of the per-row arrays is used
-        const int r0 = ATM ? (warp & 3) * 32 + lane : tid >> 3, pc = tid & 7, lc = pc ^ (r0 & 7), kc = warp >> 2;
+        // ATM: thread = tile row (= its TMEM lane) x 16 channels kh * 16 .. + 15 of every second k-block; only entry 0 of the per-row arrays is used
+        const int r0 = ATM ? (warp & 3) * 32 + lane : tid >> 3, pc = tid & 7, lc = pc ^ (r0 & 7), kh = (warp >> 2) & 1, grp = warp >> 3;
         float* dyb = (L.dy_out != nullptr && nt == 0) ? L.dy_out + (size_t)b * H * W * Cout : nullptr;
         int hq[2], wq[2];                                   // pixel of layer c's output the two rows read at tap (0, 0)
         bool rowok[2];
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
         for (int q = 0; q < 2; ++q) {
             const int i = r0 + 64 * q, oh = i / W, ow = i - oh * W;
             hq[q] = h0 + oh + pad; wq[q] = ow + pad; rowok[q] = i < rows_valid;
-            dyq[q] = dyb + ((long long)hq[q] * W + wq[q]) * Cout + (ATM ? kc * 8 : lc * 4);       // only dereferenced for in-bounds taps
+            dyq[q] = dyb + ((long long)hq[q] * W + wq[q]) * Cout + (ATM ? kh * 16 : lc * 4);       // only dereferenced for in-bounds taps
         }
         int lgw = 0;
         while ((4 << lgw) < Cout) ++lgw;
@@ -356,53 +356,70 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
         const uint32_t lo_a32 = smem_u32(lo_a) + offA, lo_b32 = smem_u32(lo_b) + offA;
         uint32_t slot = slots32;
         if constexpr (ATM) {
+            // two groups of 8 warps alternate k-blocks (conv_wide.cu): thread = row r0 x 16 channels (logical chunks 4 kh .. 4 kh + 3)
+            // + float4 tg and tg + 256 of the weight tile; group g owns stage g of the TMEM operand and of the weight lo tile
             const uint32_t rowofs = (uint32_t)r0 * 128u, sw = (uint32_t)(r0 & 7);
-            const uint32_t pa0 = rowofs + (((uint32_t)(2 * kc) ^ sw) << 4), pa1 = rowofs + (((uint32_t)(2 * kc + 1) ^ sw) << 4);
-            const uint32_t ta = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN * NACC + kc * 8);
-            uint32_t sbase = smem_u32(slots);
+            uint32_t pa[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pa[j] = rowofs + (((uint32_t)(4 * kh + j) ^ sw) << 4);
+            const uint32_t ta = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(BN * NACC + grp * 2 * BK + kh * 16);
+            const uint32_t offW = (uint32_t)((warp & 7) * 32 + lane) * 16u;
+            const uint32_t lob = smem_u32(lo_b) + (uint32_t)grp * B_TILE + offW;
+            const uint32_t sl0 = smem_u32(slots);
+            auto step = [&]() { c += BK; if (c >= Cout) { c = 0; if (++s == ks) { s = 0; ++r; } } };
+            if (grp == 1) step();
+            int sl = grp % D;
+            uint32_t ph_full = (uint32_t)((grp / D) & 1);
+            uint32_t sbase = sl0 + (uint32_t)sl * SLOT;
 #pragma unroll 1
-            for (int it = 0; it < nkb; ++it) {
-                const int ls = it & 1;
-                const int cch = c + kc * 8;                      // 8 channels of one GroupNorm group (groups are >= 16 channels wide)
+            for (int it = grp; it < nkb; it += 2) {
+                const int cch = c + kh * 16;                     // 16 channels of one GroupNorm group (groups are >= 16 channels wide)
                 const uint32_t sg = st32 + (uint32_t)(cch >> lgw) * 4u;
-                const float4 ga0 = lds128(tab32 + (uint32_t)(cch - tc0) * 4u), ga1 = lds128(tab32 + (uint32_t)(cch - tc0) * 4u + 16u);
+                const uint32_t tg = tab32 + (uint32_t)(cch - tc0) * 4u;
                 const float mu = lds32(sg), gb = lds32(sg + 16), gc = lds32(sg + 32);
                 const bool desig = dyb != nullptr && (ks == 1 || (r == 1 && s == 1));
                 const int tapoff = c - (r * W + s) * Cout;
-                mbar_wait(&s_full[sl], ph_full);
-                if (it >= 2) mbar_wait(&l_empty[ls], (uint32_t)(((it >> 1) - 1) & 1));
-                const float4 d0 = lds128(sbase + pa0), d1 = lds128(sbase + pa1);
-                const float4 y0 = lds128(sbase + A_TILE + pa0), y1 = lds128(sbase + A_TILE + pa1);
-                const float4 vw = lds128(sbase + 2 * A_TILE + offA);
                 const bool in0 = rowok[0] && (unsigned)(hq[0] - r) < (unsigned)H && (unsigned)(wq[0] - s) < (unsigned)W;
-                float4 o0, o1;
-                o0.x = fmaf(mu - y0.x, gb, fmaf(d0.x, ga0.x, gc)); o0.y = fmaf(mu - y0.y, gb, fmaf(d0.y, ga0.y, gc));
-                o0.z = fmaf(mu - y0.z, gb, fmaf(d0.z, ga0.z, gc)); o0.w = fmaf(mu - y0.w, gb, fmaf(d0.w, ga0.w, gc));
-                o1.x = fmaf(mu - y1.x, gb, fmaf(d1.x, ga1.x, gc)); o1.y = fmaf(mu - y1.y, gb, fmaf(d1.y, ga1.y, gc));
-                o1.z = fmaf(mu - y1.z, gb, fmaf(d1.z, ga1.z, gc)); o1.w = fmaf(mu - y1.w, gb, fmaf(d1.w, ga1.w, gc));
-                if (!in0) { o0 = make_float4(0.f, 0.f, 0.f, 0.f); o1 = o0; }
-                if (desig && in0) {
-                    *reinterpret_cast<float4*>(dyq[0] + tapoff) = o0;
-                    *reinterpret_cast<float4*>(dyq[0] + tapoff + 4) = o1;
+                mbar_wait(&s_full[sl], ph_full);
+                float4 d[4], y[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[j] = lds128(sbase + pa[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) y[j] = lds128(sbase + A_TILE + pa[j]);
+                const float4 w0 = lds128(sbase + 2 * A_TILE + offW), w1 = lds128(sbase + 2 * A_TILE + offW + 4096u);
+                float4 h[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 ga = lds128(tg + 16 * j);
+                    float4 o;
+                    o.x = fmaf(mu - y[j].x, gb, fmaf(d[j].x, ga.x, gc)); o.y = fmaf(mu - y[j].y, gb, fmaf(d[j].y, ga.y, gc));
+                    o.z = fmaf(mu - y[j].z, gb, fmaf(d[j].z, ga.z, gc)); o.w = fmaf(mu - y[j].w, gb, fmaf(d[j].w, ga.w, gc));
+                    if (!in0) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (desig && in0) *reinterpret_cast<float4*>(dyq[0] + tapoff + 4 * j) = o;
+                    h[j] = make_float4(tf32_hi(o.x), tf32_hi(o.y), tf32_hi(o.z), tf32_hi(o.w));
+                    d[j] = make_float4(o.x - h[j].x, o.y - h[j].y, o.z - h[j].z, o.w - h[j].w);
                 }
-                const float4 h0v = make_float4(tf32_hi(o0.x), tf32_hi(o0.y), tf32_hi(o0.z), tf32_hi(o0.w));
-                const float4 h1v = make_float4(tf32_hi(o1.x), tf32_hi(o1.y), tf32_hi(o1.z), tf32_hi(o1.w));
-                const float4 hw = make_float4(tf32_hi(vw.x), tf32_hi(vw.y), tf32_hi(vw.z), tf32_hi(vw.w));
-                const uint32_t tah = ta + (uint32_t)(ls * 2 * BK);
-                tmem_st8(tah, h0v, h1v);
-                tmem_st8(tah + BK, make_float4(o0.x - h0v.x, o0.y - h0v.y, o0.z - h0v.z, o0.w - h0v.w),
-                         make_float4(o1.x - h1v.x, o1.y - h1v.y, o1.z - h1v.z, o1.w - h1v.w));
-                sts128(sbase + 2 * A_TILE + offA, hw);
-                sts128(lo_b32 + ls * B_TILE, make_float4(vw.x - hw.x, vw.y - hw.y, vw.z - hw.z, vw.w - hw.w));
+                const float4 hw0 = make_float4(tf32_hi(w0.x), tf32_hi(w0.y), tf32_hi(w0.z), tf32_hi(w0.w));
+                const float4 hw1 = make_float4(tf32_hi(w1.x), tf32_hi(w1.y), tf32_hi(w1.z), tf32_hi(w1.w));
+                // the MMAs of k-block it - 2 (the previous user of this group's TMEM / lo stage) must have completed
+                if (it >= 2) mbar_wait(&l_empty[grp], (uint32_t)(((it >> 1) - 1) & 1));
+                tmem_st8(ta, h[0], h[1]);
+                tmem_st8(ta + 8, h[2], h[3]);
+                tmem_st8(ta + BK, d[0], d[1]);
+                tmem_st8(ta + BK + 8, d[2], d[3]);
+                sts128(sbase + 2 * A_TILE + offW, hw0);
+                sts128(sbase + 2 * A_TILE + offW + 4096u, hw1);
+                sts128(lob, make_float4(w0.x - hw0.x, w0.y - hw0.y, w0.z - hw0.z, w0.w - hw0.w));
+                sts128(lob + 4096u, make_float4(w1.x - hw1.x, w1.y - hw1.y, w1.z - hw1.z, w1.w - hw1.w));
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&l_full[ls]);
-                sbase += SLOT;
-                if (++sl == D) { sl = 0; sbase = smem_u32(slots); ph_full ^= 1u; }
-                c += BK;
-                if (c >= Cout) { c = 0; if (++s == ks) { s = 0; ++r; } }
+                if (lane == 0) mbar_arrive(&l_full[grp]);
+                sl += 2;
+                while (sl >= D) { sl -= D; ph_full ^= 1u; }
+                sbase = sl0 + (uint32_t)sl * SLOT;
+                step(); step();
             }
         } else {
 #pragma unroll 1
@@ -518,14 +535,25 @@ __global__ void __launch_bounds__(NT, 1) dgrad_wide_kernel(const __grid_constant
                 if (nz == 1) {
                     acc = lds128(ra);
                 } else {
+                    // four DSMEM loads in flight per round (one remote-latency round per four K-slices); the additions keep the
+                    // order of the slices
                     acc = ldc128(ra, 0);
                     const float4 q1 = ldc128(ra, 1);
-                    acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
+                    if (nz >= 4) {
+                        const float4 q2 = ldc128(ra, 2), q3 = ldc128(ra, 3);
+                        acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
+                        acc.x += q2.x; acc.y += q2.y; acc.z += q2.z; acc.w += q2.w;
+                        acc.x += q3.x; acc.y += q3.y; acc.z += q3.z; acc.w += q3.w;
 #pragma unroll 1
-                    for (int z = 2; z < nz; z += 2) {
-                        const float4 qa = ldc128(ra, z), qb = ldc128(ra, z + 1);
-                        acc.x += qa.x; acc.y += qa.y; acc.z += qa.z; acc.w += qa.w;
-                        acc.x += qb.x; acc.y += qb.y; acc.z += qb.z; acc.w += qb.w;
+                        for (int z = 4; z < nz; z += 4) {
+                            const float4 qa = ldc128(ra, z), qb = ldc128(ra, z + 1), qc = ldc128(ra, z + 2), qd = ldc128(ra, z + 3);
+                            acc.x += qa.x; acc.y += qa.y; acc.z += qa.z; acc.w += qa.w;
+                            acc.x += qb.x; acc.y += qb.y; acc.z += qb.z; acc.w += qb.w;
+                            acc.x += qc.x; acc.y += qc.y; acc.z += qc.z; acc.w += qc.w;
+                            acc.x += qd.x; acc.y += qd.y; acc.z += qd.z; acc.w += qd.w;
+                        }
+                    } else {
+                        acc.x += q1.x; acc.y += q1.y; acc.z += q1.z; acc.w += q1.w;
                     }
                 }
                 if (L.addend != nullptr) { const float4 a = __ldcg(reinterpret_cast<const float4*>(L.addend + e)); acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w; }

@@ -114,6 +114,7 @@ static const Net& net() {
 // activation tape
 // ---------------------------------------------------------------------------------------------
 struct ConvTape { long long y, part, stats, a; };   // a == -1: output lives in the block's conv3 slot
+constexpr int kChainFlags = 128;            // one 32-bit counter per fused forward launch (conv_wide.cu: chain_wait)
 struct Tape {
     long long x0, p0, p0_idx;
     long long acc;                  // fixed-point GroupNorm statistics of the fused plan: long long [conv][B][4][2]
@@ -146,7 +147,7 @@ static Tape build_tape(int B) {
             const ConvLayer& c = n.convs[ci];
             t.conv[ci].a = take((long long)B * c.hout * c.hout * c.cout);
         }
-    t.acc = take((long long)n.convs.size() * B * 16);
+    t.acc = take((long long)n.convs.size() * B * 16 + kChainFlags);      // + the chain-dependency counters of the fused launches (zeroed with it)
     t.xc = take(3LL * B * HEAD_LD);
     t.h1pre = take(3LL * B * HID); t.h1post = take(3LL * B * HID);
     t.h2pre = take(3LL * B * HID); t.h2post = take(3LL * B * HID);
@@ -278,6 +279,10 @@ static bool g_fused_bwd = [] { const char* e = getenv("DBOA_FUSED_BWD"); return 
 void hmr_set_fused_backward(bool on) { g_fused_bwd = on; }
 // DBOA_FUSED_FWD=0 in the environment (or dboa_set_fused_forward(0)) selects the round-1 forward: one convolution launch and
 // one GroupNorm launch per layer (kept as the A/B reference of the fused path; both fill the same tape)
+// DBOA_CHAIN_FLAGS=1 (or dboa_set_chain_flags(1)): the fused forward launches wait for each other through counters instead of grid completion
+static bool g_chain_flags = [] { const char* e = getenv("DBOA_CHAIN_FLAGS"); return e && e[0] == '1'; }();
+void hmr_set_chain_flags(bool on) { g_chain_flags = on; }
+bool hmr_chain_flags() { return g_chain_flags; }
 static bool g_fused_fwd = [] { const char* e = getenv("DBOA_FUSED_FWD"); return !(e && e[0] == '0'); }();
 void hmr_set_fused_forward(bool on) { g_fused_fwd = on; }
 bool hmr_fused_forward() { return g_fused_fwd; }
@@ -428,7 +433,7 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
                             c.cout, relu, st);
     };
     if (g_fused_fwd && conv_tc_enabled())
-        cudaMemsetAsync(T + t.acc, 0, n.convs.size() * (size_t)B * 16 * sizeof(float), st);      // statistics accumulators of this forward
+        cudaMemsetAsync(T + t.acc, 0, (n.convs.size() * (size_t)B * 16 + kChainFlags) * sizeof(float), st);      // statistics accumulators and chain counters of this forward
     DBOA_TRY(nchw_to_nhwc(image, T + t.x0, B, 3, 224, 224, st));
     DBOA_TRY(conv_forward(n.convs[0], B, T + t.x0, P + n.convs[0].w_off, T + t.conv[0].y, sc.ws, st));
     DBOA_TRY(gn_plain(0, T + t.conv[0].a, 1, nullptr));
@@ -453,10 +458,22 @@ int hmr_forward(const float* P, const float* init_pose, const float* init_shape,
             f.gamma = P + c.g_off; f.beta = P + c.b_off;
             f.a_out = T + t.conv[src].a; f.stats_out = T + t.conv[src].stats;
         };
+        // consecutive fused launches depend on each other through per-launch counters in the tape instead of grid completion
+        unsigned* flags = reinterpret_cast<unsigned*>(T + t.acc + (long long)n.convs.size() * B * 16);
+        int n_run = 0;
+        unsigned prev_ctas = 0;
         auto run = [&](FusedConv* d, int np, int next_ci) {
             const int nz = conv_wide_plan(d, np, B);
             const ConvLayer* nx = next_ci >= 0 ? &n.convs[next_ci] : nullptr;
-            return conv_wide_launch(d, np, B, nz, nx ? P + nx->w_off : nullptr, nx ? (size_t)nx->cout * nx->kpitch * sizeof(float) : 0, st, true);
+            ChainDep dep = {nullptr, 0u, nullptr, nullptr};
+            const bool chained = g_chain_flags && pdl_enabled() && n_run < kChainFlags;
+            if (chained) {
+                if (n_run > 0) { dep.wait_flag = flags + n_run - 1; dep.wait_count = prev_ctas; }
+                dep.signal_flag = flags + n_run; dep.signal_count = &prev_ctas;
+            }
+            ++n_run;
+            return conv_wide_launch(d, np, B, nz, nx ? P + nx->w_off : nullptr, nx ? (size_t)nx->cout * nx->kpitch * sizeof(float) : 0, st, true,
+                                    chained ? &dep : nullptr);
         };
         for (size_t bi = 0; bi < n.blocks.size(); ++bi) {
             const Block& b = n.blocks[bi];

@@ -48,7 +48,15 @@ int conv_wide_plan(const FusedConv* d, int nprob, int B);
 void conv_wide_set_cta_budget(int n);                                  // 0: all SMs
 void conv_wide_set_operand_tmem(bool on);                              // transformed activation operand of conv_wide / dgrad_wide in tensor memory
 bool conv_wide_operand_tmem();
-int conv_wide_launch(const FusedConv* d, int nprob, int B, int nz, const float* next_w, size_t next_bytes, cudaStream_t st, bool pdl);
+// chain dependency between consecutive fused launches of one forward (conv_wide.cu: chain_wait): the launch waits until
+// *wait_flag >= wait_count instead of for the completion of its predecessor grid (wait_flag NULL: ordinary dependency), every CTA
+// of it increments *signal_flag when its outputs are stored, and *signal_count receives the number of CTAs (the next wait_count)
+struct ChainDep {
+    const unsigned* wait_flag; unsigned wait_count;
+    unsigned* signal_flag; unsigned* signal_count;
+};
+int conv_wide_launch(const FusedConv* d, int nprob, int B, int nz, const float* next_w, size_t next_bytes, cudaStream_t st, bool pdl,
+                     const ChainDep* dep = nullptr);
 int gn_acc_res_avgpool(const float* y, const float* res, const float* acc, const float* gamma, const float* beta, float* a_out, float* stats_out,
                        float* out, int B, int HW, int C, int ld, int ncopy, size_t copy_stride, cudaStream_t st);
 

@@ -51,6 +51,11 @@ int dboa_set_forward_cta_budget(int n);
  * Environment: DBOA_OPERAND_TMEM. */
 int dboa_set_operand_tmem(int enable);
 int dboa_get_operand_tmem(void);
+/* 1: consecutive fused convolution launches of dboa_hmr_forward depend on each other through per-launch counters in the tape
+ * (every producer CTA signals after its last store, the consumer's readers spin with acquire loads) instead of waiting for the
+ * producer grid to complete and flush.  Same results; needs programmatic dependent launch (DBOA_PDL).  Environment: DBOA_CHAIN_FLAGS. */
+int dboa_set_chain_flags(int enable);
+int dboa_get_chain_flags(void);
 
 /* ---- HMR regressor: parameter arena and tape layout ----------------------------------------
  * replaces: model/hmr.py:67-124 (HMR.__init__/_make_layer state_dict contract).

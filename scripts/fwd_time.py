@@ -5,9 +5,11 @@ import torch
 from dynaboa_b200 import _lib, hmr as hmr_mod, synthetic
 
 lib = _lib.load()
+if os.environ.get('FWD_KNOBS'):          # diagnostic library only (scripts/build_timeline.sh): wrong results, timing experiments
+    lib.dboa_debug_set_fused_knobs(int(os.environ['FWD_KNOBS']))
 m = hmr_mod.hmr(synthetic.make_mean_params()).cuda().eval()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
-for B in (1, 2, 9):
+for B in ((1, 9) if os.environ.get('FWD_KNOBS') else (1, 2, 9)):
     x = torch.randn(B, 3, 224, 224, device='cuda')
     tape = torch.empty(hmr_mod.tape_floats(B), device='cuda')
     for fused in ((1,) if os.environ.get('FWD_FUSED_ONLY') == '1' else (0, 1)):

@@ -212,6 +212,46 @@ def test_fused_forward_fills_the_same_tape_as_the_unfused_plan(L):
         assert ((G1 - G0).norm() / G0.norm()).item() < 2e-3, B
 
 
+def test_operand_placement_and_chain_dependency_do_not_change_results(L):
+    """The two execution-model switches of the fused kernels change WHERE the transformed activation operand lives (tensor memory
+    instead of shared memory: dboa_set_operand_tmem) and HOW consecutive launches wait for each other (per-launch counters
+    instead of grid completion: dboa_set_chain_flags), not the arithmetic: identical TF32 splits, products and accumulation
+    order.  Forward outputs, all 15 features and the gradient of a whole backward are compared bit for bit."""
+    from dynaboa_b200 import hmr as hmr_mod, synthetic
+    from oracle import hmr_ref
+    m = hmr_mod.hmr(synthetic.make_mean_params()).cuda()
+    m.load_state_dict(hmr_ref.strip_prefix(synthetic.make_basemodel()['model']), strict=True)
+    m.eval()
+    lib = L.load()
+    tmem0, chain0 = lib.dboa_get_operand_tmem(), lib.dboa_get_chain_flags()
+    try:
+        for B in (1, 2, 9):
+            x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(40 + B)).cuda()
+            res = {}
+            for tmem, chain in ((0, 0), (1, 0), (1, 1), (0, 1)):
+                lib.dboa_set_operand_tmem(tmem)
+                lib.dboa_set_chain_flags(chain)
+                tape = torch.empty(hmr_mod.tape_floats(B), device='cuda')
+                for rep in range(3 if chain else 1):            # the counters live in the tape: a re-used tape must be re-armed
+                    r, s_, c, p, t = hmr_mod.raw_forward(m.arena, m._buffers, x, tape=tape)
+                G = torch.zeros_like(m.arena)
+                gen = torch.Generator(device='cuda').manual_seed(7)
+                dr, dsh, dc = (torch.randn(v.shape, device='cuda', generator=gen) for v in (r, s_, c))
+                hmr_mod.raw_backward(m.arena, t, B, False, dr, dsh, dc, G)
+                torch.cuda.synchronize()
+                res[(tmem, chain)] = (r.clone(), s_.clone(), c.clone(), [f.clone() for f in hmr_mod._feature_views(t, B)], G)
+            ref = res[(0, 0)]
+            for key, got in res.items():
+                assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]), (B, key)
+                for i in range(15):
+                    assert torch.equal(got[3][i], ref[3][i]), (B, key, i)
+                # the backward runs weight gradients on side streams next to the chain: same kernels, same operands
+                assert (got[4] - ref[4]).abs().max().item() <= 1e-6 * ref[4].abs().max().item(), (B, key)
+    finally:
+        lib.dboa_set_operand_tmem(tmem0)
+        lib.dboa_set_chain_flags(chain0)
+
+
 WGRAD = [  # B, H (input), Cin, Cout, k, stride
     (1, 56, 64, 256, 1, 1), (1, 28, 128, 128, 3, 1), (2, 28, 512, 128, 1, 1), (1, 14, 256, 256, 3, 1), (3, 14, 1024, 256, 1, 1), (1, 7, 512, 512, 3, 1),
     (2, 7, 512, 2048, 1, 1), (9, 7, 2048, 512, 1, 1), (1, 14, 256, 1024, 1, 1), (1, 56, 128, 128, 3, 2), (2, 28, 256, 256, 3, 2), (1, 14, 512, 512, 3, 2),
