@@ -9,6 +9,7 @@ SURVEY.md §8d: adaptation + one output forward/SMPL).  Prints ONE JSON line (se
 cannot travel to the GPU box and has no importable package; see oracle/__init__.py).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -292,11 +293,14 @@ def run_ours(args, rank, world, local):
     keys = ('image', 'smpl_j2d')
     host = [{k: stream[t][k].pin_memory() for k in keys} for t in range(n_frames)]
     resident = [{k: host[t][k].to(dev) for k in keys} for t in range(n_frames)]
-    # two pinned output slots: the outputs of frame t are copied back while frame t+1 is adapted, and read (event wait) before
-    # the slot is reused two steps later -- every step copies its result to the host inside the timed region
+    # NSLOT pinned output slots: the outputs of frame t are copied back while the following frames are adapted, and read (event
+    # wait) before the slot is reused NSLOT steps later -- every step copies its result to the host inside the timed region.
+    # Four slots let the launching thread run up to four frames ahead of the device, so that a host-side hiccup (scheduler,
+    # allocator) shorter than a few frames does not drain the device queue.
+    NSLOT = 4
     out_host = [{k: torch.empty(s, pin_memory=True) for k, s in (('rotmat', (1, 24, 3, 3)), ('betas', (1, 10)), ('cam', (1, 3)),
-                                                                   ('joints', (1, 49, 3)), ('vertices', (1, 6890, 3)))} for _ in range(2)]
-    landed = [None, None]
+                                                                   ('joints', (1, 49, 3)), ('vertices', (1, 6890, 3)))} for _ in range(NSLOT)]
+    landed = [None] * NSLOT
     h2d = sum(v.numel() * 4 for v in host[0].values())
     d2h = sum(v.numel() * 4 for v in out_host[0].values())
 
@@ -316,7 +320,7 @@ def run_ours(args, rank, world, local):
         # output forward + SMPL of this frame on the adaptor's side stream: it overlaps the next frame's adaptation
         pred, ev = ad.predict_async(batch['image'])
         if from_host:
-            slot = t & 1
+            slot = t % NSLOT
             if landed[slot] is not None:
                 landed[slot].synchronize()                  # the host has the result that used this slot
             with torch.cuda.stream(ad.output_stream):
@@ -342,12 +346,19 @@ def run_ours(args, rank, world, local):
             sampler.start()
         l0 = lib.dboa_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for t in range(PRELUDE + args.warmup, n_frames):
-            step(t, from_host)
-        if getattr(ad, 'output_stream', None) is not None:        # the interval ends when the LAST frame's output forward (and its
-            torch.cuda.current_stream().wait_stream(ad.output_stream)   # copy-back) on the side stream has finished, not before
-        e1.record()
+        # no cyclic garbage collection inside the timed region (as timeit does): a full collection walks every object torch has
+        # imported (tens of ms) and would stall the launching thread of a 5 ms step
+        gc.collect()
+        gc.disable()
+        try:
+            e0.record()
+            for t in range(PRELUDE + args.warmup, n_frames):
+                step(t, from_host)
+            if getattr(ad, 'output_stream', None) is not None:        # the interval ends when the LAST frame's output forward (and its
+                torch.cuda.current_stream().wait_stream(ad.output_stream)   # copy-back) on the side stream has finished, not before
+            e1.record()
+        finally:
+            gc.enable()
         barrier()
         ms = e0.elapsed_time(e1)
         launches = lib.dboa_launch_count() - l0

@@ -26,6 +26,7 @@
 
 #include <map>
 #include <tuple>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -860,7 +861,17 @@ static const CUtensorMap* act_map(const float* x, int B, int H, int W, int C, in
     if (it != cache.end()) return &it->second->tm;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return nullptr;
-    if (cache.size() > 4096) { for (auto& kv : cache) delete kv.second; cache.clear(); }      // tapes come and go with the allocator
+    // Tapes come and go with the allocator, so the cache is bounded -- in two generations: a launch collects up to six map
+    // pointers before it dereferences them, and an eviction between two of those calls must not free the earlier ones (the
+    // allocator reuses the first bytes of a freed holder at once: a corrupted tensor map, i.e. TMA loads from a wild address).
+    // Holders evicted here are freed at the NEXT eviction, >= 4096 insertions later.
+    if (cache.size() > 4096) {
+        static std::vector<TmHolder*> retired;
+        for (TmHolder* h : retired) delete h;
+        retired.clear();
+        for (auto& kv : cache) retired.push_back(kv.second);
+        cache.clear();
+    }
     TmHolder* h = new TmHolder;
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
