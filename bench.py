@@ -57,7 +57,7 @@ def default_options(**over):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML, every 5 ms from a
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML, every 20 ms from a
     thread (the timed region is ~0.15 s: `nvidia-smi -lms` starts too slowly to see it)."""
     REASONS = (('hw_slowdown', 0x8), ('sw_thermal_slowdown', 0x20), ('hw_thermal_slowdown', 0x40), ('sw_power_cap', 0x4))
 
@@ -92,7 +92,7 @@ class ClockSampler:
             except Exception as e:      # noqa: BLE001
                 self.err = str(e)
                 return
-            time.sleep(0.005)
+            time.sleep(0.02)
 
     def start(self):
         if self.h is None:
@@ -341,7 +341,7 @@ def run_ours(args, rank, world, local):
         for t in range(PRELUDE + args.warmup):
             step(t, from_host)
         barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
+        sampler = ClockSampler(local) if rank == 0 and not args.no_clock_sampler else None
         if sampler:
             sampler.start()
         l0 = lib.dboa_launch_count()
@@ -352,8 +352,12 @@ def run_ours(args, rank, world, local):
         gc.disable()
         try:
             e0.record()
+            marks = []
             for t in range(PRELUDE + args.warmup, n_frames):
                 step(t, from_host)
+                if args.frame_times:                     # diagnostic: one event per frame on the adaptation stream
+                    marks.append(torch.cuda.Event(enable_timing=True))
+                    marks[-1].record()
             if getattr(ad, 'output_stream', None) is not None:        # the interval ends when the LAST frame's output forward (and its
                 torch.cuda.current_stream().wait_stream(ad.output_stream)   # copy-back) on the side stream has finished, not before
             e1.record()
@@ -361,6 +365,10 @@ def run_ours(args, rank, world, local):
             gc.enable()
         barrier()
         ms = e0.elapsed_time(e1)
+        if args.frame_times and marks:
+            ts = [e0.elapsed_time(m) for m in marks]
+            sys.stderr.write('[bench] frame times (ms, adaptation stream): ' + ' '.join(f'{b - a:.2f}' for a, b in zip([0.0] + ts[:-1], ts)) +
+                             f' | drain {ms - ts[-1]:.2f}\n')
         launches = lib.dboa_launch_count() - l0
         clocks = sampler.stop() if sampler else None
         return ddist.max_over_ranks(ms, dev), launches, clocks
@@ -453,6 +461,8 @@ def main():
     ap.add_argument('--cos-threshold', type=float, default=None,
                     help='override cos_sim_threshold of a dynamic_boa workload (the reference default 3.1e-4 never fires on the synthetic stream)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--frame-times', action='store_true', help='diagnostic: per-frame times of the timed region on stderr')
+    ap.add_argument('--no-clock-sampler', action='store_true', help='diagnostic: no NVML polling during the timed region')
     ap.add_argument('--serial-output', action='store_true',
                     help='run the output forward on the adaptation stream (no overlap with the next frame)')
     ap.add_argument('--tc', type=int, default=-1, help='tensor-core conv mode override (0 fp32 CUDA cores, 1 forward, 2 forward+dgrad+wgrad, 3 forward+dgrad)')

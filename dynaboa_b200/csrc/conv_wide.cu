@@ -864,8 +864,11 @@ static const CUtensorMap* act_map(const float* x, int B, int H, int W, int C, in
     // Tapes come and go with the allocator, so the cache is bounded -- in two generations: a launch collects up to six map
     // pointers before it dereferences them, and an eviction between two of those calls must not free the earlier ones (the
     // allocator reuses the first bytes of a freed holder at once: a corrupted tensor map, i.e. TMA loads from a wild address).
-    // Holders evicted here are freed at the NEXT eviction, >= 4096 insertions later.
-    if (cache.size() > 4096) {
+    // Holders evicted here are freed at the NEXT eviction, >= kMaxMaps insertions later.  The bound is generous (32768 maps = ~10 MB
+    // of host memory): a stream in steady state re-uses a few thousand (address, shape) pairs; with a bound of 4096 the one eviction
+    // while the allocator's addresses were still settling cost a 1.4 - 4.6 ms host stall around frame 16 (bench.py --frame-times).
+    constexpr size_t kMaxMaps = 32768;
+    if (cache.size() > kMaxMaps) {
         static std::vector<TmHolder*> retired;
         for (TmHolder* h : retired) delete h;
         retired.clear();
