@@ -1,7 +1,14 @@
 #!/bin/bash
-# the whole GPU suite with the complete log kept (gpurun_out/suite.log); optional pytest arguments
+# the GPU suite in the form the driver runs it, N times (default 1), complete logs kept in gpurun_out/suite_<i>.log -- repeated runs
+# are how the intermittent tensor-map use-after-free of round 2 was pinned down (one core dump in five runs); then smoke() and,
+# with BENCH=1, two default bench lines
 cd "$GRAFT_REPO_ROOT"
-timeout 1800 python -X faulthandler -m pytest tests -m gpu -x -q -p no:cacheprovider "$@" > gpurun_out/suite.log 2>&1
-echo "rc=$?"
-grep -n "passed\|failed\|error\|Fatal\|Error" gpurun_out/suite.log | tail -20
-tail -5 gpurun_out/suite.log | cut -c1-300
+for i in $(seq 1 ${1:-1}); do
+  timeout 1800 python -m pytest tests/ -x -q -m gpu > gpurun_out/suite_$i.log 2>&1
+  echo "run $i rc=$?"
+  grep -n "passed\|failed\|Fatal\|Segmentation\|Abort\|core" gpurun_out/suite_$i.log | tail -5 | cut -c1-200
+done
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+if [ -n "$BENCH" ]; then
+  for i in 1 2; do timeout 900 python bench.py --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('C2', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'fwd ms', round(d['roofline']['ms_per_launch'],4), 'launches', d['gpu_launches'], d['clocks'])"; done
+fi
