@@ -26,6 +26,18 @@ class MAML(nn.Module):
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)
 
+    # A learner returned by clone() exposes its FAST weights (non-leaf views of the flat fast arena), as learn2learn's cloned
+    # module does; nn.Module's own traversal would walk the registered leaf parameters of the wrapped model instead.
+    def parameters(self, recurse=True):
+        if getattr(self.module, '_fast', None) is not None:
+            return self.module.parameters(recurse)
+        return super().parameters(recurse)
+
+    def named_parameters(self, prefix='', recurse=True, remove_duplicate=True):
+        if getattr(self.module, '_fast', None) is not None:
+            return self.module.named_parameters(prefix + ('.' if prefix else '') + 'module', recurse, remove_duplicate)
+        return super().named_parameters(prefix, recurse, remove_duplicate)
+
     def clone(self, first_order=None, allow_unused=None, allow_nograd=None):
         if first_order is not None and not first_order:
             raise NotImplementedError('only first_order=True is implemented')

@@ -61,3 +61,23 @@ def test_dropin_modules_import_without_gpu():
         for m in names:
             sys.modules.pop(m, None)
         sys.modules.update(saved)
+
+
+def test_maml_learner_exposes_fast_weights():
+    """learn2learn's cloned module yields its fast (non-leaf) weights from parameters() / named_parameters(); the wrapper
+    does the same for a learner and keeps nn.Module's leaf traversal for the meta-model (reference: l2l 0.1.5 BaseLearner /
+    clone_module as used at base_adaptor.py:119, dynaboa_benchmark.py:136).  CPU only: the learner state is emulated with a
+    flat arena, the clone itself is a CUDA call."""
+    from dynaboa_b200 import hmr as hmr_mod, maml, synthetic
+    m = hmr_mod.hmr(synthetic.make_mean_params())
+    mm = maml.MAML(m, lr=1e-3, first_order=True)
+    leaf = list(mm.named_parameters())
+    assert len(leaf) == 169 and leaf[0][0] == 'module.conv1.weight' and all(p.is_leaf for _, p in leaf)
+    object.__setattr__(m, '_fast', m.arena.detach().clone().requires_grad_() * 1.0)
+    try:
+        fast = list(mm.named_parameters())
+        assert [n for n, _ in fast] == [n for n, _ in leaf]
+        assert all(not p.is_leaf for _, p in fast) and [tuple(p.shape) for _, p in fast] == [tuple(p.shape) for _, p in leaf]
+        assert len(list(mm.parameters())) == 169
+    finally:
+        object.__setattr__(m, '_fast', None)
