@@ -52,6 +52,7 @@ SIGNATURES = {
     'dboa_get_operand_tmem': (I, []),
     'dboa_set_chain_flags': (I, [I]),
     'dboa_get_chain_flags': (I, []),
+    'dboa_selftest_map_cache': (I, [I, I, I]),
     'dboa_dgrad_fused': (I, [C.POINTER(DgradFusedStruct), I, I, I, I, I, P]),
     'dboa_conv_fused_part_floats': (L, [I, I, I]),
     'dboa_conv_fused_fwd': (I, [C.POINTER(FusedConvStruct), I, I, P]),

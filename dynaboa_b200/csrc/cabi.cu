@@ -78,6 +78,7 @@ int dboa_get_fused_forward(void) { return hmr_fused_forward() ? 1 : 0; }
 int dboa_set_fused_backward(int enable) { hmr_set_fused_backward(enable != 0); return DBOA_OK; }
 int dboa_set_forward_cta_budget(int n) { conv_wide_set_cta_budget(n < 0 ? 0 : n); return DBOA_OK; }
 int dboa_set_operand_tmem(int enable) { conv_wide_set_operand_tmem(enable != 0); return DBOA_OK; }
+int dboa_selftest_map_cache(int bound, int n, int window) { return map_cache_selftest(bound, n, window); }
 int dboa_set_chain_flags(int enable) { hmr_set_chain_flags(enable != 0); return DBOA_OK; }
 int dboa_get_chain_flags(void) { return hmr_chain_flags() ? 1 : 0; }
 int dboa_get_operand_tmem(void) { return conv_wide_operand_tmem() ? 1 : 0; }

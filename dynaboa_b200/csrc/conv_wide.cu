@@ -813,6 +813,39 @@ static EncodeTiledFn encode_fn() {
 }
 struct alignas(64) TmHolder { CUtensorMap tm; };
 
+// Bounded cache of tensor maps with POINTER-STABLE eviction.  Tapes come and go with the allocator, so the activation maps must be
+// bounded; but a launch collects up to six map pointers before it dereferences them, and an eviction between two of those lookups
+// must not free the earlier ones (the allocator reuses the first bytes of a freed holder at once: a corrupted tensor map, i.e. TMA
+// loads from a wild address -- seen in round 2 as one core dump in five suite runs).  Eviction therefore works in two generations:
+// holders evicted now are freed at the NEXT eviction, more than `bound` insertions later.  Checked on the CPU by
+// dboa_selftest_map_cache (tests/test_cabi.py).
+template <class Key>
+struct MapCache {
+    std::map<Key, TmHolder*> live;
+    std::vector<TmHolder*> retired;
+    size_t bound;
+    explicit MapCache(size_t b) : bound(b) {}
+    TmHolder* find(const Key& k) const {
+        auto it = live.find(k);
+        return it == live.end() ? nullptr : it->second;
+    }
+    TmHolder* insert(const Key& k) {                 // the caller fills the holder (or calls drop on failure)
+        if (live.size() > bound) {
+            for (TmHolder* h : retired) delete h;
+            retired.clear();
+            for (auto& kv : live) retired.push_back(kv.second);
+            live.clear();
+        }
+        TmHolder* h = new TmHolder;
+        live[k] = h;
+        return h;
+    }
+    void drop(const Key& k) {
+        auto it = live.find(k);
+        if (it != live.end()) { delete it->second; live.erase(it); }
+    }
+};
+
 static const CUtensorMap* weight_map(const float* w, int K, int Cout) {
     static std::map<std::tuple<const float*, int, int>, TmHolder*> cache;
     auto key = std::make_tuple(w, K, Cout);
@@ -855,35 +888,22 @@ static const CUtensorMap* weight_map_mn(const float* w, int K, int Cout) {
 // stride: the box delivers bw x bh pixels sampled every `stride`-th pixel (boxDim = N * elementStride, as cuTensorMapEncodeTiled
 // specifies for element strides other than one)
 static const CUtensorMap* act_map(const float* x, int B, int H, int W, int C, int bw, int bh, bool atom32 = false, int stride = 1) {
-    static std::map<std::tuple<const float*, int, int, int, int, int, int, bool, int>, TmHolder*> cache;
-    auto key = std::make_tuple(x, B, H, W, C, bw, bh, atom32, stride);
-    auto it = cache.find(key);
-    if (it != cache.end()) return &it->second->tm;
+    // 32768 maps = ~10 MB of host memory: a stream in steady state re-uses a few thousand (address, shape) pairs; with a bound of 4096
+    // the one eviction while the allocator's addresses were still settling cost a 1.4 - 4.6 ms host stall around frame 16
+    // (bench.py --frame-times)
+    static MapCache<std::tuple<const float*, int, int, int, int, int, int, bool, int>> cache(32768);
+    const auto key = std::make_tuple(x, B, H, W, C, bw, bh, atom32, stride);
+    if (TmHolder* hit = cache.find(key)) return &hit->tm;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return nullptr;
-    // Tapes come and go with the allocator, so the cache is bounded -- in two generations: a launch collects up to six map
-    // pointers before it dereferences them, and an eviction between two of those calls must not free the earlier ones (the
-    // allocator reuses the first bytes of a freed holder at once: a corrupted tensor map, i.e. TMA loads from a wild address).
-    // Holders evicted here are freed at the NEXT eviction, >= kMaxMaps insertions later.  The bound is generous (32768 maps = ~10 MB
-    // of host memory): a stream in steady state re-uses a few thousand (address, shape) pairs; with a bound of 4096 the one eviction
-    // while the allocator's addresses were still settling cost a 1.4 - 4.6 ms host stall around frame 16 (bench.py --frame-times).
-    constexpr size_t kMaxMaps = 32768;
-    if (cache.size() > kMaxMaps) {
-        static std::vector<TmHolder*> retired;
-        for (TmHolder* h : retired) delete h;
-        retired.clear();
-        for (auto& kv : cache) retired.push_back(kv.second);
-        cache.clear();
-    }
-    TmHolder* h = new TmHolder;
+    TmHolder* h = cache.insert(key);
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
     const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(bw * stride), (cuuint32_t)(bh * stride), 1};
     const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     if (enc(&h->tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { delete h; return nullptr; }
-    cache[key] = h;
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { cache.drop(key); return nullptr; }
     return &h->tm;
 }
 
@@ -894,6 +914,32 @@ static int num_sms() {
 static int rows_of(int Ho) { return Ho * Ho <= BM ? Ho : BM / Ho; }          // image rows per output tile (square images)
 
 }  // namespace wz
+
+// Host-only self test of the eviction rule (no CUDA call): `n` insertions into a cache of bound `bound`; like a launch, the caller
+// keeps the pointers of its last `window` lookups and requires that they still carry the signature written into their first bytes
+// (exactly the bytes a freed chunk loses to the allocator).  Returns 0, or 1 + the index of the first insertion after which a kept
+// pointer was found corrupted.
+int map_cache_selftest(int bound, int n, int window) {
+    if (bound < 1 || n < 1 || window < 1 || window > 16 || window > bound) return -1;
+    wz::MapCache<int> cache((size_t)bound);
+    wz::TmHolder* kept[16];
+    for (int i = 0; i < n; ++i) {
+        wz::TmHolder* h = cache.insert(i);
+        unsigned long long sig[2] = {0xD0B0A5EED0000000ull + (unsigned long long)i, ~(unsigned long long)i};
+        memcpy(&h->tm, sig, sizeof sig);
+        kept[i % window] = h;
+        for (int j = 0; j < window && j <= i; ++j) {
+            const int k = i - j;
+            unsigned long long got[2];
+            memcpy(got, &kept[k % window]->tm, sizeof got);
+            if (got[0] != 0xD0B0A5EED0000000ull + (unsigned long long)k || got[1] != ~(unsigned long long)k) return 1 + i;
+        }
+        if (cache.find(i) != h) return 1 + i;
+    }
+    for (auto& kv : cache.live) delete kv.second;
+    for (wz::TmHolder* h : cache.retired) delete h;
+    return 0;
+}
 
 // shared with conv_wgrad_wide.cu / dgrad_wide.cu
 const void* tma_weight_map_mn(const float* w, int K, int Cout) { return wz::weight_map_mn(w, K, Cout); }

@@ -46,6 +46,7 @@ struct FusedConv {
 bool conv_wide_ok(const FusedConv& d);
 int conv_wide_plan(const FusedConv* d, int nprob, int B);
 void conv_wide_set_cta_budget(int n);                                  // 0: all SMs
+int map_cache_selftest(int bound, int n, int window);                   // host-only check of the tensor-map cache's eviction rule
 void conv_wide_set_operand_tmem(bool on);                              // transformed activation operand of conv_wide / dgrad_wide in tensor memory
 bool conv_wide_operand_tmem();
 // chain dependency between consecutive fused launches of one forward (conv_wide.cu: chain_wait): the launch waits until

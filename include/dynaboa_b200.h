@@ -56,6 +56,10 @@ int dboa_get_operand_tmem(void);
  * producer grid to complete and flush.  Same results; needs programmatic dependent launch (DBOA_PDL).  Environment: DBOA_CHAIN_FLAGS. */
 int dboa_set_chain_flags(int enable);
 int dboa_get_chain_flags(void);
+/* Host-only self test (no CUDA call, runs without a GPU) of the TMA tensor-map cache: `n` insertions into a cache bounded at
+ * `bound` entries while the caller, like a launch, holds the pointers of its last `window` (<= 16) lookups; evictions must leave
+ * those pointers intact (they are freed one eviction later).  0 = ok, 1 + i = a held map was corrupted after insertion i. */
+int dboa_selftest_map_cache(int bound, int n, int window);
 
 /* ---- HMR regressor: parameter arena and tape layout ----------------------------------------
  * replaces: model/hmr.py:67-124 (HMR.__init__/_make_layer state_dict contract).

@@ -62,3 +62,15 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     off, nd = ctypes.c_longlong(), ctypes.c_int()
     shp, st = (ctypes.c_longlong * 4)(), (ctypes.c_longlong * 4)()
     assert lib.dboa_hmr_param_info(999, None, 0, ctypes.byref(off), ctypes.byref(nd), shp, st) == -1
+
+
+def test_tensor_map_cache_keeps_held_pointers_across_evictions(lib):
+    """Host logic of the TMA tensor-map cache (csrc/conv_wide.cu: MapCache): a launch looks up to six maps up before it
+    dereferences them, and an eviction between two of those lookups must not free the earlier ones.  Round 2 shipped for a while
+    with a cache that freed everything at 4096 entries -- one core dump in five GPU suite runs.  The self test inserts far past the
+    bound while holding the last `window` pointers and checks the bytes a freed chunk would lose to the allocator."""
+    assert lib.dboa_selftest_map_cache(64, 5000, 6) == 0
+    assert lib.dboa_selftest_map_cache(6, 5000, 6) == 0           # eviction every seven insertions, six pointers held
+    assert lib.dboa_selftest_map_cache(1, 1000, 1) == 0
+    assert lib.dboa_selftest_map_cache(4, 100, 6) == -1           # more pointers held than one generation guarantees: rejected
+    assert lib.dboa_selftest_map_cache(0, 10, 1) == -1
