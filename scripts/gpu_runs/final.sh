@@ -2,7 +2,8 @@
 # end-of-round verification on one B200: whole GPU suite, smoke(), the driver's bench line (with the CPU baseline), the reference arm,
 # C3 / C5 lines; `bash scripts/gpu_runs/final.sh evidence` also runs scripts/gpu_runs/evidence.sh
 cd "$GRAFT_REPO_ROOT"
-timeout 1800 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/final_tests.log
+timeout 1800 python -m pytest tests/ -x -q -m gpu > gpurun_out/final_tests_full.log 2>&1; echo "suite rc=$?" | tee gpurun_out/final_tests.log      # the complete log is kept: a crash must be attributable to a test
+grep -n "passed\|failed\|Fatal\|Segmentation\|Abort\|core" gpurun_out/final_tests_full.log | tail -4 | cut -c1-200 | tee -a gpurun_out/final_tests.log
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/final_smoke.log
 timeout 1200 python bench.py 2> gpurun_out/final_bench_c2.err | tail -1 > gpurun_out/final_bench_c2.json
 timeout 1200 python bench.py --impl reference --steps 4 --warmup 1 2> gpurun_out/final_bench_ref.err | tail -1 > gpurun_out/final_bench_c2_reference_arm.json
