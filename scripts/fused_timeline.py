@@ -54,7 +54,7 @@ for l in range(128):
     prev_end = end
 print(f'sum of spans {tot:.1f} us')
 
-print('per-k-block stamps of CTA 0 (us relative to its dependency wait): loop top | tiles landed | lo free | arrive | - || mma: lo-full | issued || tma issued')
+print('per-k-block stamps of CTA 0 (us relative to its dependency wait): loop top | tiles landed | lo free (tensor-memory operand: loads + math done) | arrive | - (tensor-memory operand: operand stage free) || mma: lo-full | issued || tma issued;  with the tensor-memory operand even / odd k-blocks belong to transform group 0 / 1')
 for l in (0, 1, 2, 3, 20, 28, 29, 30):
     base = t[l][0][2].item()
     if base == 0:
